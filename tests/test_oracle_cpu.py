@@ -1,0 +1,130 @@
+"""The oracle (oracle/) against the committed golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import boxes_np, net_ref, nms_c, weights
+
+GRIDS_320 = [(20, 20), (10, 10), (5, 5), (3, 3), (2, 2), (1, 1)]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_default_boxes_bit_exact(golden_dir):
+    g = _load(golden_dir, "v3_ssdlite.npz")
+    a = boxes_np.default_boxes(GRIDS_320, (320, 320))
+    assert a.dtype == np.float32 and a.shape == (3234, 4)
+    assert np.array_equal(a, g["anchors"])
+    # scales and value range
+    assert np.allclose(boxes_np.default_box_scales(6, 0.2, 0.95), [0.2, 0.35, 0.5, 0.65, 0.8, 0.95, 1.0])
+    assert abs(a.min() + 106.7) < 0.1 and abs(a.max() - 426.7) < 0.1
+
+
+def test_default_boxes_v2_sizes(golden_dir):
+    g = _load(golden_dir, "v2_ssdlite.npz")
+    a300 = boxes_np.default_boxes([(19, 19), (10, 10), (5, 5), (3, 3), (2, 2), (1, 1)], (300, 300))
+    a512 = boxes_np.default_boxes([(32, 32), (16, 16), (8, 8), (4, 4), (2, 2), (1, 1)], (512, 512))
+    assert np.array_equal(a300, g["s300_priors"]) and a300.shape[0] == 3000
+    assert np.array_equal(a512, g["s512_priors"]) and a512.shape[0] == 8190
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_nms_cases(golden_dir, impl):
+    g = _load(golden_dir, "nms_cases.npz")
+    for c in range(int(g["n_cases"])):
+        boxes, scores, thr = g["c%d_boxes" % c], g["c%d_scores" % c], float(g["c%d_thr" % c])
+        idxs, want = g["c%d_idxs" % c], g["c%d_keep" % c]
+        if impl == "numpy" and boxes.shape[0] > 5000:
+            continue            # the NumPy restatement is O(n) Python steps; C covers the big ones
+        if idxs.shape[0] == 0:
+            got = boxes_np.nms(boxes, scores, thr) if impl == "numpy" else nms_c.nms(boxes, scores, thr)
+        elif impl == "numpy":
+            got = boxes_np.batched_nms_vanilla(boxes, scores, idxs, thr)
+        else:
+            got = nms_c.batched_nms(boxes, scores, idxs, thr)
+        assert np.array_equal(got, want), "case %d" % c
+
+
+def test_nms_empty():
+    assert boxes_np.nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).shape == (0,)
+    assert nms_c.nms(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), 0.5).shape == (0,)
+
+
+def test_v3_oracle_against_reference_golden(golden_dir):
+    """fp32 restatement == reference output (bit-equal where the CPU conv kernels are the same
+    machine/ISA as the generating run; tolerance 1e-4 otherwise)."""
+    g = _load(golden_dir, "v3_ssdlite.npz")
+    torch.manual_seed(0)
+    import torchvision
+    tv = torchvision.models.detection.ssdlite320_mobilenet_v3_large(weights=None, weights_backbone=None,
+                                                                    num_classes=91)
+    sd = weights.seeded_state_dict(tv.state_dict())
+    assert list(sd.keys()) == [str(k) for k in g["state_dict_keys"]]
+    x = weights.synthetic_images(2, 320)
+    with torch.no_grad():
+        cls, reg, grids = net_ref.v3_forward_raw(sd, x, "fp32")
+    assert grids == GRIDS_320
+    stride = int(g["row_stride"])
+    np.testing.assert_allclose(cls[:, ::stride].numpy(), g["logits_rows"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(reg.numpy(), g["bbox_regression"], rtol=0, atol=2e-4)
+    anchors = torch.from_numpy(g["anchors"])
+    with torch.no_grad():
+        dets = net_ref.postprocess_detections_torch(cls, reg, anchors, (320, 320))
+    for i in range(2):
+        assert np.array_equal(dets[i]["labels"].numpy(), g["det_labels"][i])
+        np.testing.assert_allclose(dets[i]["scores"].numpy(), g["det_scores"][i], atol=1e-5)
+        np.testing.assert_allclose(dets[i]["boxes"].numpy(), g["det_boxes"][i], atol=2e-2)
+        # NumPy restatement of the whole post-processing, fed the oracle's softmax
+        o = boxes_np.postprocess_detections(cls[i].numpy(), reg[i].numpy(), g["anchors"], (320, 320),
+                                            scores=torch.softmax(cls[i], -1).numpy())
+        assert np.array_equal(o["labels"], g["det_labels"][i])
+
+
+def test_v3_bf16_emulation_matches_golden(golden_dir):
+    g = _load(golden_dir, "v3_ssdlite.npz")
+    import torchvision
+    tv = torchvision.models.detection.ssdlite320_mobilenet_v3_large(weights=None, weights_backbone=None,
+                                                                    num_classes=91)
+    sd = weights.seeded_state_dict(tv.state_dict())
+    x = weights.synthetic_images(2, 320)
+    with torch.no_grad():
+        cls, reg, _ = net_ref.v3_forward_raw(sd, x, "bf16")
+    stride = int(g["row_stride"])
+    # bf16 rounding decisions can flip with a different CPU conv kernel; stay loose but meaningful
+    d = np.abs(cls[:, ::stride].numpy() - g["logits_bf16emu_rows"])
+    assert np.sqrt((d ** 2).mean()) < 0.05
+
+
+def test_stress_postprocess_golden(golden_dir):
+    g = _load(golden_dir, "postprocess_stress.npz")
+    B = int(g["batch"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    logits = torch.randn(B, 3234, 91, generator=gen) * 4.0
+    bbox = torch.randn(B, 3234, 4, generator=gen) * 1.5
+    anchors = boxes_np.default_boxes(GRIDS_320, (320, 320))
+    scores = torch.softmax(logits, -1).numpy()
+    for i in range(B):
+        o = boxes_np.postprocess_detections(None, bbox[i].numpy(), anchors, (320, 320), topk_candidates=400,
+                                            scores=scores[i])
+        assert np.array_equal(o["labels"], g["det_labels"][i])
+        assert np.array_equal(o["scores"], g["det_scores"][i])
+        np.testing.assert_allclose(o["boxes"], g["det_boxes"][i], atol=1e-3)
+
+
+def test_decode_matches_torch_port():
+    gen = torch.Generator().manual_seed(3)
+    rel = torch.randn(3234, 4, generator=gen) * 2
+    anchors = boxes_np.default_boxes(GRIDS_320, (320, 320))
+    want = net_ref.decode_boxes_torch(rel, torch.from_numpy(anchors)).numpy()
+    got = boxes_np.decode_single(rel.numpy(), anchors)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-4)       # exp() differs by ulps across libms
+    # clip: dw above log(1000/16) saturates
+    big = np.array([[0, 0, 100.0, 100.0]], np.float32)
+    b = boxes_np.decode_single(big, anchors[:1])
+    w = anchors[0, 2] - anchors[0, 0]
+    assert abs((b[0, 2] - b[0, 0]) - np.float32(1000.0 / 16) * w) < 1e-2
