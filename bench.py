@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the SSDLite inference hot path (BASELINE.json metric: SSDLite320 images/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = forward + post-processing of one batch of synthetic 320x320 images per GPU
+(config 2 of BASELINE.json: ssdlite320_mobilenet_v3_large, 91 classes, batch 256, bf16).
+For N > 1 the driver launches this file under torch.distributed.run; the image batch is sharded
+(256 per GPU, weak scaling), there is no inter-GPU traffic on the hot path and one NCCL all-gather
+of the fixed-shape detections closes each step.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ssdlite320_mobilenet_v3_large images/sec (forward + postprocess)"
+UNIT = "img/s"
+S = 320
+NUM_CLASSES = 91
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="also print the per-layer time table to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path: the oracle's torch port of the reference (conv stack through the same ATen CPU kernels
+# the reference uses + SSD.postprocess_detections restated with the same torch/torchvision calls)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(n_images, steps, warmup):
+    import torch
+    from oracle import boxes_np, net_ref, weights
+    from demonet_b200 import plan as dplan
+    import demonet_b200
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    model = demonet_b200.ssdlite320_mobilenet_v3_large()          # only for the state_dict template / plan
+    sd = weights.seeded_state_dict(model.state_dict())
+    anchors = torch.from_numpy(dplan.default_boxes(model.plan))
+    x = weights.synthetic_images(n_images, S)
+
+    def step():
+        with torch.no_grad():
+            cls, reg, _ = net_ref.v3_forward_raw(sd, x, "fp32", NUM_CLASSES)
+            return net_ref.postprocess_detections_torch(cls, reg, anchors, (S, S))
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n_images * steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, ms, cores = cpu_reference_rate(args.cpu_sample, args.steps, args.warmup)
+    sample = "%d images/step, fp32, %d threads; oracle port of SSD.forward (reference is pure Python/PyTorch)" % (
+        args.cpu_sample, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ssdlite320_mobilenet_v3_large 91 classes 320x320 forward+postprocess on the host CPU",
+                       "batch_per_step": args.cpu_sample, "weights": "seeded re-init 1234", "images": "torch.rand seed 1"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# roofline bookkeeping: algorithmic bytes / flops of every launch of the plan
+# ------------------------------------------------------------------------------------------------
+def layer_costs(plan, B):
+    """[(kernel_name, bytes, flops)] per launch, in plan order, then the 3 post-processing kernels.
+    Algorithmic bytes = input + output activations at their stored width + weights."""
+    out = []
+    P, K = plan.num_priors, plan.num_classes
+    for L in plan.layers:
+        hi, wi, ho, wo = L.h_in, L.w_in, L.h_out, L.w_out
+        if L.kind == "stem":
+            out.append(("stem_conv_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
+        elif L.kind == "dw":
+            out.append(("dwconv_kernel", B * (hi * wi + ho * wo) * L.cin * 2 + L.k * L.k * L.cin * 4,
+                        2 * B * ho * wo * L.cin * L.k * L.k))
+        elif L.kind == "se":
+            out.append(("se_inplace_kernel", B * hi * wi * L.cin * 2 * 2 + 2 * L.cin * L.se_mid * 4,
+                        2 * B * 2 * L.cin * L.se_mid))
+        else:
+            ob = 4 if L.head else 2
+            res = B * hi * wi * L.cout * 2 if L.res else 0
+            out.append(("pwconv_tc_kernel", B * hi * wi * (L.cin * 2 + L.cout * ob) + res + L.cin * L.cout * 2,
+                        2 * B * hi * wi * L.cin * L.cout))
+    out.append(("softmax_decode_kernel", B * (P * K * 4 + P * 16) + P * 16 + B * (P * (K - 1) * 4 + P * 16), 0))
+    out.append(("class_nms_kernel", B * (K - 1) * P * 4, 0))
+    out.append(("merge_topd_kernel", B * plan_D(plan) * 28, 0))
+    return out
+
+
+def plan_D(plan):
+    return 300
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import demonet_b200
+    from demonet_b200 import _C
+    from oracle import weights            # seeded re-init recipe + synthetic images (bench infrastructure)
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, D = args.batch, 300
+
+    model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=NUM_CLASSES)
+    model.load_state_dict(weights.seeded_state_dict(model.state_dict()))
+    model = model.to(dev)
+    eng = model.reserve(B, dev)
+    lib = _C.lib()
+    stream = torch.cuda.current_stream(dev)
+
+    # inputs resident in HBM (value) and in pinned host memory (e2e); different images per rank
+    imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
+    imgs = imgs_host.to(dev)
+    # one packed output buffer per rank so that the final gather is ONE collective
+    nb_boxes, nb_scores, nb_labels, nb_counts = B * D * 16, B * D * 4, B * D * 8, ((B * 4 + 7) // 8) * 8
+    packed = torch.zeros(nb_boxes + nb_scores + nb_labels + nb_counts, dtype=torch.uint8, device=dev)
+    o = 0
+    out_boxes = packed[o:o + nb_boxes].view(torch.float32).view(B, D, 4); o += nb_boxes
+    out_scores = packed[o:o + nb_scores].view(torch.float32).view(B, D); o += nb_scores
+    out_labels = packed[o:o + nb_labels].view(torch.int64).view(B, D); o += nb_labels
+    out_counts = packed[o:o + B * 4].view(torch.int32)
+    io = {"boxes": out_boxes, "scores": out_scores, "labels": out_labels, "counts": out_counts}
+    gathered = torch.empty(world * packed.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    host_out = {"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
+                "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
+                "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
+                "counts": torch.empty(B, dtype=torch.int32).pin_memory()}
+
+    def step_device():
+        eng.forward(imgs, io)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def step_host():
+        eng.forward_host(imgs_host, host_out)       # results land in each rank's own host memory: no gather
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, clocks = timed(step_device, args.steps, warm, sampler)
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    e2e_ms, _ = timed(step_host, args.steps, warm)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    counts_ok = int(host_out["counts"].min()) >= 0
+
+    # per-launch device times, live, with CUDA events on the launching stream
+    n_launch = eng.launches_per_forward
+    ms = (ctypes.c_float * n_launch)()
+    with torch.cuda.device(dev):
+        _C.check(lib.dn_engine_profile(eng._handle, imgs.data_ptr(), B, 10, ms, stream.cuda_stream))
+    costs = layer_costs(model.plan, B)
+    per_kernel = {}
+    for (name, nbytes, flops), t in zip(costs, list(ms)):
+        k = per_kernel.setdefault(name, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+        k["ms"] += t; k["bytes"] += nbytes; k["flops"] += flops; k["launches"] += 1
+    sum_ms = sum(k["ms"] for k in per_kernel.values())
+    dominant = max(per_kernel, key=lambda n: per_kernel[n]["ms"])
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": float(mp["hbm_gbs"]), "bf16_tflops": float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])),
+                 "src": "measured"}
+    except Exception:
+        pass
+    dk = per_kernel[dominant]
+    achieved = dk["bytes"] / (dk["ms"] * 1e-3) / 1e9
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
+                "launches_per_step": dk["launches"], "avg_launch_ms": dk["ms"] / dk["launches"],
+                "share_of_step": dk["ms"] / sum_ms,
+                "tensor_tflops": dk["flops"] / (dk["ms"] * 1e-3) / 1e12 if dk["flops"] else None,
+                "per_kernel": {n: {"ms": round(k["ms"], 4), "share": round(k["ms"] / sum_ms, 4),
+                                   "GBps": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1),
+                                   "TFLOPs": round(k["flops"] / (k["ms"] * 1e-3) / 1e12, 2), "launches": k["launches"]}
+                               for n, k in per_kernel.items()}}
+    if args.layers and rank == 0:
+        for i, ((name, nbytes, flops), t) in enumerate(zip(costs, list(ms))):
+            L = model.plan.layers[i] if i < len(model.plan.layers) else None
+            desc = "%s %dx%d c%d->%d k%d s%d" % (L.kind, L.h_in, L.w_in, L.cin, L.cout, L.k, L.stride) if L else name
+            print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (t * 1e-3) / 1e9,
+                                                             flops / (t * 1e-3) / 1e12), file=sys.stderr)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "ssdlite320_mobilenet_v3_large, 91 classes, 320x320, batch %d per GPU, bf16 activations, "
+                                   "forward + softmax/decode/top-k/NMS/top-300 (BASELINE.json configs[1])" % B,
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (image shards, final NCCL "
+                       "all-gather of detections)" % world, "weights": "seeded re-init 1234 (oracle/weights.py)",
+                       "images": "torch.rand seed 1+rank", "l2": "inputs larger than L2 (%.0f MB fp32 images per step; "
+                       "activation arena %.1f GB)" % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
+                       "cuda_graph": True},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                    "api": "dn_engine_forward_host (pinned fp32 images in, detections out)", "ok": counts_ok},
+            "gpu_launches": n_launch * args.steps,
+            "gpu_launches_per_step": n_launch,
+            "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cpu_ms, cores = cpu_reference_rate(args.cpu_sample, 3, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d images x 3 steps, fp32, oracle torch port of SSD.forward (%.0f ms/step)"
+                                          % (args.cpu_sample, cpu_ms)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

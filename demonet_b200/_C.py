@@ -1,0 +1,114 @@
+"""ctypes binding of libdemonet_b200.so (the C ABI declared in include/demonet_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdemonet_b200.so")
+
+DN_OK = 0
+DN_ERR_INVALID = -1
+DN_ERR_CUDA = -2
+DN_ERR_UNSUPPORTED = -3
+DN_ERR_WORKSPACE = -4
+
+ACT = {"none": 0, "relu": 1, "relu6": 2, "hardswish": 3}
+OP_STEM, OP_DW, OP_PW, OP_SE = 0, 1, 2, 3
+BUF_NONE, BUF_IMAGES = -1, -2
+
+c_void_p, c_int, c_int32, c_int64, c_float, c_double, c_size_t = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_size_t)
+
+
+class PostprocessParams(ctypes.Structure):
+    _fields_ = [("num_priors", c_int32), ("num_classes", c_int32), ("image_h", c_int32), ("image_w", c_int32),
+                ("score_thresh", c_float), ("nms_thresh", c_double), ("topk_candidates", c_int32),
+                ("detections_per_img", c_int32), ("min_box_size", c_float), ("box_weights", c_float * 4),
+                ("bbox_xform_clip", c_float)]
+
+
+class Op(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("act", c_int32), ("in_buf", c_int32), ("out_buf", c_int32), ("res_buf", c_int32),
+                ("h_in", c_int32), ("w_in", c_int32), ("c_in", c_int32), ("h_out", c_int32), ("w_out", c_int32),
+                ("c_out", c_int32), ("ksize", c_int32), ("stride", c_int32), ("c_mid", c_int32), ("out_fp32", c_int32),
+                ("reserved", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
+                ("out_batch_stride", c_int64), ("out_row_stride", c_int64), ("out_offset", c_int64)]
+
+
+class Buf(ctypes.Structure):
+    _fields_ = [("elems_per_image", c_int64), ("elem_bytes", c_int32), ("reserved", c_int32)]
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("image_h", c_int32), ("image_w", c_int32), ("image_mean", c_float * 3), ("image_std", c_float * 3),
+                ("n_ops", c_int32), ("n_bufs", c_int32), ("ops_host", ctypes.POINTER(Op)),
+                ("bufs_host", ctypes.POINTER(Buf)), ("logits_buf", c_int32), ("bbox_buf", c_int32),
+                ("anchors_host", ctypes.POINTER(c_float)), ("post", PostprocessParams), ("gemm_impl", c_int32),
+                ("use_cuda_graph", c_int32)]
+
+
+_SIGNATURES = {
+    "dn_last_error": (ctypes.c_char_p, []),
+    "dn_abi_version": (c_int, []),
+    "dn_dwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_pwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_int64, c_int64, c_int, c_void_p]),
+    "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
+                             c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_se_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_postprocess_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(PostprocessParams)]),
+    "dn_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p, c_size_t,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dn_postprocess_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p,
+                                       c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_float),
+                                       c_void_p]),
+    "dn_batched_nms_workspace_bytes": (c_size_t, [c_int64]),
+    "dn_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
+                               c_void_p]),
+    "dn_engine_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(ModelDesc), c_int]),
+    "dn_engine_destroy": (c_int, [c_void_p]),
+    "dn_engine_load_weights": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "dn_engine_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dn_engine_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dn_engine_buffer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
+    "dn_engine_copy_buffer": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "dn_engine_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
+    "dn_engine_launches_per_forward": (c_int, [c_void_p]),
+    "dn_engine_device_bytes": (c_size_t, [c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once). Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "demonet_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or demonet_b200/csrc/build.sh); there is no CPU or PyTorch fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        if handle.dn_abi_version() != 1:
+            raise RuntimeError("demonet_b200: ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    """Map a dn_status to the exception type the reference would raise for the same mistake."""
+    if rc == DN_OK:
+        return
+    msg = lib().dn_last_error().decode("utf-8", "replace")
+    if rc == DN_ERR_INVALID:
+        raise ValueError("demonet_b200: " + msg)
+    if rc == DN_ERR_UNSUPPORTED:
+        raise NotImplementedError("demonet_b200: " + msg)
+    raise RuntimeError("demonet_b200 (status %d): %s" % (rc, msg))

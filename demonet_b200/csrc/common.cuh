@@ -1,0 +1,102 @@
+// Shared helpers for the demonet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/demonet_b200.h"
+
+// measurement aid shared by postprocess.cu and engine.cu (C++ linkage, not part of the C ABI)
+int dn_postprocess_timed(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                         const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                         float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
+                         float* ms3);
+
+namespace dn {
+
+void set_error(const char* fmt, ...);
+
+#define DN_CHECK_CUDA(expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            dn::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DN_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define DN_REQUIRE(cond, code, ...)          \
+    do {                                     \
+        if (!(cond)) {                       \
+            dn::set_error(__VA_ARGS__);      \
+            return (code);                   \
+        }                                    \
+    } while (0)
+
+#define DN_CHECK_LAUNCH()                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess) {                                                                 \
+            dn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return DN_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+// ---- activations (fp32) --------------------------------------------------------------
+// hardswish(x) = x * relu6(x + 3) / 6   (torch.nn.Hardswish; mobilenetv3.py:72,141-142)
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case DN_ACT_RELU: return fmaxf(v, 0.f);
+        case DN_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+        case DN_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        default: return v;
+    }
+}
+
+// ---- bf16 packing --------------------------------------------------------------------
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+    float2 r;
+    r.x = __uint_as_float(v << 16);
+    r.y = __uint_as_float(v & 0xffff0000u);
+    return r;
+}
+__device__ __forceinline__ uint32_t float2_to_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    float2 t;
+    t = bf16x2_to_float2(v.x); f[0] = t.x; f[1] = t.y;
+    t = bf16x2_to_float2(v.y); f[2] = t.x; f[3] = t.y;
+    t = bf16x2_to_float2(v.z); f[4] = t.x; f[5] = t.y;
+    t = bf16x2_to_float2(v.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 v;
+    v.x = float2_to_bf16x2(f[0], f[1]);
+    v.y = float2_to_bf16x2(f[2], f[3]);
+    v.z = float2_to_bf16x2(f[4], f[5]);
+    v.w = float2_to_bf16x2(f[6], f[7]);
+    return v;
+}
+
+}  // namespace dn

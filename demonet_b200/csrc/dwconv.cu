@@ -1,0 +1,275 @@
+// Bandwidth-bound CUDA-core kernels of the SSDLite backbone for sm_100a:
+//   * depthwise k x k stencil (k in {3,5}, stride in {1,2}) + folded BN + activation   (dn_dwconv)
+//   * stem: input normalisation + dense 3x3 stride-2 conv + folded BN + activation     (dn_stem_conv)
+//   * squeeze-excitation, applied in place                                              (dn_se_inplace)
+// Activations are NHWC bf16, 8 channels (16 B) per thread access, fp32 accumulation.
+#include "common.cuh"
+
+namespace dn {
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise conv.  Thread = 8 channels x TW consecutive output columns of one output row.
+// Consecutive threads walk the channel vectors of a pixel, then the next column tile, so every
+// global access of a warp is a run of contiguous 16-byte vectors; the k-row / k-column overlap
+// between neighbouring threads is served by L1.
+// Reference: ConvBNActivation(groups=C), demonet/models/mobilenetv2.py:32-55.
+// ---------------------------------------------------------------------------------------------
+template <int KS, int S, int TW>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              uint4* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+    constexpr int PAD = (KS - 1) / 2;
+    constexpr int NV = (TW - 1) * S + KS;
+    const int CV = C >> 3;
+    const int WT = (Wo + TW - 1) / TW;
+    const long long total = (long long)B * Ho * WT * CV;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const int cv = (int)(tid % CV);
+    long long r = tid / CV;
+    const int wt = (int)(r % WT);
+    r /= WT;
+    const int oh = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int ow0 = wt * TW;
+    const int iw0 = ow0 * S - PAD;
+
+    float acc[TW][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2 + 1);
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+            acc[t][0] = b0.x; acc[t][1] = b0.y; acc[t][2] = b0.z; acc[t][3] = b0.w;
+            acc[t][4] = b1.x; acc[t][5] = b1.y; acc[t][6] = b1.z; acc[t][7] = b1.w;
+        }
+    }
+    const uint4* xb = x + (long long)b * H * W * CV + cv;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+        const int ih = oh * S - PAD + kh;
+        if (ih < 0 || ih >= H) continue;
+        const uint4* xr = xb + (long long)ih * W * CV;
+        uint4 raw[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int iw = iw0 + i;
+            raw[i] = (iw >= 0 && iw < W) ? __ldg(xr + (long long)iw * CV) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int kw = 0; kw < KS; ++kw) {
+            const float4* wp = reinterpret_cast<const float4*>(w + (long long)(kh * KS + kw) * C) + cv * 2;
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int t = 0; t < TW; ++t) {
+                float f[8];
+                unpack8(raw[t * S + kw], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[t][q] = fmaf(f[q], wv[q], acc[t][q]);
+            }
+        }
+    }
+    uint4* yo = y + (((long long)b * Ho + oh) * Wo + ow0) * CV + cv;
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+        if (ow0 + t < Wo) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[t][q] = apply_act(acc[t][q], act);
+            yo[(long long)t * CV] = pack8(acc[t]);
+        }
+    }
+}
+
+template <int KS, int S, int TW>
+static int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int Ho,
+                     int Wo, int act, cudaStream_t stream) {
+    const long long total = (long long)B * Ho * ((Wo + TW - 1) / TW) * (C / 8);
+    const long long blocks = (total + 255) / 256;
+    DN_REQUIRE(blocks < (1ll << 31), DN_ERR_UNSUPPORTED, "depthwise problem too large");
+    dwconv_kernel<KS, S, TW><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)x, w, bias, (uint4*)y, B, H, W, C, Ho,
+                                                                  Wo, act);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem.  Thread = one output pixel, all COUT channels in registers; weights broadcast from smem.
+// Reads the caller's fp32 NCHW image, normalises on the fly ((x - mean) / std, zero padding is
+// applied AFTER normalisation exactly as conv2d pads the normalised tensor: transform.py:129-138,
+// mobilenetv3.py:141-142) and writes NHWC bf16.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                 uint4* __restrict__ y, int B, int H, int W, int Ho, int Wo, float m0, float m1, float m2, float s0,
+                 float s1, float s2, int act) {
+    __shared__ __align__(16) float sw[27 * COUT];
+    __shared__ float sb[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
+    __syncthreads();
+    const long long total = (long long)B * Ho * Wo;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const int ow = (int)(tid % Wo);
+    const int oh = (int)((tid / Wo) % Ho);
+    const int b = (int)(tid / ((long long)Wo * Ho));
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const float* plane = img + ((long long)b * 3 + ci) * H * W;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = oh * 2 - 1 + kh;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = ow * 2 - 1 + kw;
+                float v = 0.f;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    v = __fdiv_rn(__fsub_rn(__ldg(plane + (long long)ih * W + iw), mean[ci]), stdv[ci]);
+                const float4* wr = reinterpret_cast<const float4*>(sw + ((ci * 3 + kh) * 3 + kw) * COUT);
+#pragma unroll
+                for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                    const float4 ww = wr[c4];
+                    acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
+                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = apply_act(acc[c], act);
+    uint4* yo = y + tid * (COUT / 8);
+#pragma unroll
+    for (int v = 0; v < COUT / 8; ++v) yo[v] = pack8(acc + v * 8);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Squeeze-Excitation, one CTA per image, in place:  x *= hardsigmoid(fc2(relu(fc1(mean_hw(x))))).
+// Reference: SqueezeExcitation, demonet/models/mobilenetv3.py:22-40.
+// w1: fp32 [Cs][C]; w2t: fp32 [Cs][C] (fc2 weight TRANSPOSED so that threads read it coalesced).
+// ---------------------------------------------------------------------------------------------
+constexpr int SE_THREADS = 512;
+
+__global__ void __launch_bounds__(SE_THREADS)
+se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const float* __restrict__ w2t, const float* __restrict__ b2, int HW, int C, int Cs) {
+    extern __shared__ float s_se[];
+    float* pooled = s_se;              // [C]
+    float* hidden = pooled + C;        // [Cs]
+    float* scale = hidden + Cs;        // [C]
+    float* part = scale + C;           // [slices][C]
+    const int CV = C >> 3;
+    const int b = blockIdx.x;
+    uint4* xb = x + (long long)b * HW * CV;
+    const int slices = SE_THREADS / CV;          // >= 1 because C <= 8 * SE_THREADS is checked on the host
+    const int cv = threadIdx.x % CV, sl = threadIdx.x / CV;
+    if (sl < slices) {
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int p = sl; p < HW; p += slices) {
+            float f[8];
+            unpack8(xb[(long long)p * CV + cv], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s[q] += f[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) part[sl * C + cv * 8 + q] = s[q];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += SE_THREADS) {
+        float s = 0.f;
+        for (int i = 0; i < slices; ++i) s += part[i * C + c];
+        pooled[c] = __fdiv_rn(s, (float)HW);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < Cs; j += SE_THREADS / 32) {
+        const float* wr = w1 + (long long)j * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), pooled[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hidden[j] = fmaxf(s + __ldg(b1 + j), 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += SE_THREADS) {
+        float s = __ldg(b2 + c);
+        for (int j = 0; j < Cs; ++j) s = fmaf(__ldg(w2t + (long long)j * C + c), hidden[j], s);
+        // hardsigmoid(x) = relu6(x + 3) / 6
+        scale[c] = __fdiv_rn(fminf(fmaxf(s + 3.f, 0.f), 6.f), 6.f);
+    }
+    __syncthreads();
+    const int nvec = HW * CV;
+    for (int i = threadIdx.x; i < nvec; i += SE_THREADS) {
+        const int c0 = (i % CV) * 8;
+        float f[8];
+        unpack8(xb[i], f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] *= scale[c0 + q];
+        xb[i] = pack8(f);
+    }
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
+                         int stride, int act, void* stream_) {
+    DN_REQUIRE(x && w && bias && y, DN_ERR_INVALID, "NULL tensor pointer");
+    DN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, DN_ERR_INVALID, "bad shape");
+    DN_REQUIRE(C % 8 == 0, DN_ERR_UNSUPPORTED, "depthwise channels must be a multiple of 8 (got %d)", C);
+    DN_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), DN_ERR_UNSUPPORTED,
+               "depthwise supports k in {3,5}, stride in {1,2} (got k=%d stride=%d)", k, stride);
+    const int pad = (k - 1) / 2;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (k == 3 && stride == 1) return launch_dw<3, 1, 4>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
+    if (k == 3 && stride == 2) return launch_dw<3, 2, 2>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
+    if (k == 5 && stride == 1) return launch_dw<5, 1, 4>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
+    return launch_dw<5, 2, 2>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
+}
+
+extern "C" int dn_stem_conv(const float* images, const float* w, const float* bias, const float* mean3_host,
+                            const float* std3_host, void* y, int B, int H, int W, int Cout, int act, void* stream_) {
+    DN_REQUIRE(images && w && bias && y && mean3_host && std3_host, DN_ERR_INVALID, "NULL pointer");
+    DN_REQUIRE(B > 0 && H > 0 && W > 0, DN_ERR_INVALID, "bad shape");
+    DN_REQUIRE(Cout == 16 || Cout == 32, DN_ERR_UNSUPPORTED, "stem supports 16 or 32 output channels (got %d)", Cout);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = (long long)B * Ho * Wo;
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (Cout == 16)
+        stem_conv_kernel<16><<<blocks, 128, 0, s>>>(images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0], mean3_host[1],
+                                                   mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
+    else
+        stem_conv_kernel<32><<<blocks, 128, 0, s>>>(images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0], mean3_host[1],
+                                                   mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
+                             int C, int Cs, void* stream_) {
+    DN_REQUIRE(x && w1 && b1 && w2t && b2, DN_ERR_INVALID, "NULL tensor pointer");
+    DN_REQUIRE(B > 0 && HW > 0 && C > 0 && Cs > 0, DN_ERR_INVALID, "bad shape");
+    DN_REQUIRE(C % 8 == 0 && C / 8 <= SE_THREADS, DN_ERR_UNSUPPORTED, "SE channels must be a multiple of 8 and <= %d",
+               8 * SE_THREADS);
+    const int slices = SE_THREADS / (C / 8);
+    const size_t smem = ((size_t)2 * C + Cs + (size_t)slices * C) * sizeof(float);
+    DN_REQUIRE(smem <= 200 * 1024, DN_ERR_UNSUPPORTED, "SE block too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(se_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    se_inplace_kernel<<<B, SE_THREADS, smem, (cudaStream_t)stream_>>>((uint4*)x, w1, b1, w2t, b2, HW, C, Cs);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}

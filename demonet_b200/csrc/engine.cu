@@ -1,0 +1,349 @@
+// Engine: the whole SSDLite forward (SSD.forward eval branch, demonet/models/generalized_ssd.py:271-349)
+// as a pre-planned launch sequence over a device arena, replayed from a CUDA graph.
+// The layer list (dn_op[]) is produced by the Python host side from the reference's module
+// structure (demonet_b200/plan.py); this file only owns memory, tensor maps and launch order.
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "pwconv.cuh"
+
+using namespace dn;
+
+struct GraphKey {
+    int B;
+    const void* images;
+    void *boxes, *scores, *labels, *counts;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(B, images, boxes, scores, labels, counts) <
+               std::tie(o.B, o.images, o.boxes, o.scores, o.labels, o.counts);
+    }
+};
+struct GraphEntry {
+    bool warm = false;
+    cudaGraphExec_t exec = nullptr;
+};
+
+struct dn_engine {
+    dn_model_desc desc;
+    std::vector<dn_op> ops;
+    std::vector<dn_buf> bufs;
+    std::vector<float> anchors_host;
+    int max_batch = 0;
+    int device = 0;
+    unsigned char* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<size_t> buf_off;
+    unsigned char* weights = nullptr;
+    size_t weight_bytes = 0;
+    float* anchors_dev = nullptr;
+    void* post_ws = nullptr;
+    size_t post_ws_bytes = 0;
+    std::vector<CUtensorMap> tmap_a, tmap_w;       // per op (PW only)
+    bool tmaps_ready = false;
+    std::map<GraphKey, GraphEntry> graphs;
+    cudaStream_t capture_stream = nullptr;
+    // staging for dn_engine_forward_host
+    float* stage_images = nullptr;
+    unsigned char* stage_out = nullptr;
+    size_t so_boxes = 0, so_scores = 0, so_labels = 0, so_counts = 0, so_total = 0;
+    size_t device_bytes = 0;
+};
+
+static void* buf_ptr(dn_engine* e, int id) { return (id >= 0) ? (void*)(e->arena + e->buf_off[id]) : nullptr; }
+
+static void drop_graphs(dn_engine* e) {
+    for (auto& kv : e->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
+}
+
+extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max_batch) {
+    DN_REQUIRE(out && d, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(max_batch > 0, DN_ERR_INVALID, "max_batch must be positive");
+    DN_REQUIRE(d->n_ops > 0 && d->n_bufs > 0 && d->ops_host && d->bufs_host && d->anchors_host, DN_ERR_INVALID,
+               "model description is incomplete");
+    DN_REQUIRE(d->logits_buf >= 0 && d->logits_buf < d->n_bufs && d->bbox_buf >= 0 && d->bbox_buf < d->n_bufs,
+               DN_ERR_INVALID, "bad head buffer ids");
+    for (int i = 0; i < d->n_ops; ++i) {
+        const dn_op& o = d->ops_host[i];
+        DN_REQUIRE(o.kind >= DN_OP_STEM && o.kind <= DN_OP_SE, DN_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        DN_REQUIRE(o.in_buf == DN_BUF_IMAGES || (o.in_buf >= 0 && o.in_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad in_buf", i);
+        DN_REQUIRE(o.kind == DN_OP_SE || (o.out_buf >= 0 && o.out_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad out_buf", i);
+        DN_REQUIRE(o.res_buf == DN_BUF_NONE || (o.res_buf >= 0 && o.res_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad res_buf", i);
+    }
+    dn_engine* e = new dn_engine();
+    e->desc = *d;
+    e->ops.assign(d->ops_host, d->ops_host + d->n_ops);
+    e->bufs.assign(d->bufs_host, d->bufs_host + d->n_bufs);
+    e->anchors_host.assign(d->anchors_host, d->anchors_host + (size_t)d->post.num_priors * 4);
+    e->desc.ops_host = nullptr;
+    e->desc.bufs_host = nullptr;
+    e->desc.anchors_host = nullptr;
+    e->max_batch = max_batch;
+    auto fail = [&](int rc) {
+        dn_engine_destroy(e);
+        return rc;
+    };
+    if (cudaGetDevice(&e->device) != cudaSuccess) {
+        set_error("cudaGetDevice failed");
+        return fail(DN_ERR_CUDA);
+    }
+    size_t off = 0;
+    e->buf_off.resize(e->bufs.size());
+    for (size_t i = 0; i < e->bufs.size(); ++i) {
+        e->buf_off[i] = off;
+        size_t bytes = (size_t)e->bufs[i].elems_per_image * e->bufs[i].elem_bytes * max_batch;
+        off += (bytes + 1023) & ~(size_t)1023;
+    }
+    e->arena_bytes = off;
+    e->post_ws_bytes = dn_postprocess_workspace_bytes(max_batch, &e->desc.post);
+    const size_t D = e->desc.post.detections_per_img;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    e->so_boxes = 0;
+    e->so_scores = al(e->so_boxes + (size_t)max_batch * D * 16);
+    e->so_labels = al(e->so_scores + (size_t)max_batch * D * 4);
+    e->so_counts = al(e->so_labels + (size_t)max_batch * D * 8);
+    e->so_total = al(e->so_counts + (size_t)max_batch * 4);
+    const size_t img_bytes = (size_t)max_batch * 3 * e->desc.image_h * e->desc.image_w * sizeof(float);
+#define TRY(x)                                                                  \
+    if ((x) != cudaSuccess) {                                                   \
+        set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); \
+        return fail(DN_ERR_CUDA);                                               \
+    }
+    TRY(cudaMalloc(&e->arena, e->arena_bytes));
+    TRY(cudaMemset(e->arena, 0, e->arena_bytes));
+    TRY(cudaMalloc(&e->anchors_dev, e->anchors_host.size() * sizeof(float)));
+    TRY(cudaMemcpy(e->anchors_dev, e->anchors_host.data(), e->anchors_host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TRY(cudaMalloc(&e->post_ws, e->post_ws_bytes));
+    TRY(cudaMalloc(&e->stage_images, img_bytes));
+    TRY(cudaMalloc(&e->stage_out, e->so_total));
+    TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+#undef TRY
+    e->device_bytes = e->arena_bytes + e->post_ws_bytes + img_bytes + e->so_total + e->anchors_host.size() * 4;
+    *out = e;
+    return DN_OK;
+}
+
+extern "C" int dn_engine_destroy(dn_engine* e) {
+    if (!e) return DN_OK;
+    drop_graphs(e);
+    if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
+    cudaFree(e->arena);
+    cudaFree(e->weights);
+    cudaFree(e->anchors_dev);
+    cudaFree(e->post_ws);
+    cudaFree(e->stage_images);
+    cudaFree(e->stage_out);
+    delete e;
+    return DN_OK;
+}
+
+extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes) {
+    DN_REQUIRE(e && blob_host && bytes > 0, DN_ERR_INVALID, "NULL argument");
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const dn_op& o = e->ops[i];
+        DN_REQUIRE(o.w_off >= 0 && (size_t)o.w_off < bytes && o.b_off >= 0 && (size_t)o.b_off < bytes, DN_ERR_INVALID,
+                   "op %zu: weight offsets outside the blob", i);
+        DN_REQUIRE(o.w_off % 16 == 0 && o.b_off % 16 == 0, DN_ERR_INVALID, "op %zu: weight offsets must be 16-byte aligned", i);
+    }
+    DN_CHECK_CUDA(cudaDeviceSynchronize());
+    drop_graphs(e);
+    if (bytes != e->weight_bytes) {
+        cudaFree(e->weights);
+        e->weights = nullptr;
+        DN_CHECK_CUDA(cudaMalloc(&e->weights, bytes));
+        e->device_bytes += bytes - e->weight_bytes;
+        e->weight_bytes = bytes;
+        e->tmaps_ready = false;
+    }
+    DN_CHECK_CUDA(cudaMemcpy(e->weights, blob_host, bytes, cudaMemcpyHostToDevice));
+    if (!e->tmaps_ready && e->desc.gemm_impl == 0) {
+        e->tmap_a.resize(e->ops.size());
+        e->tmap_w.resize(e->ops.size());
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            const dn_op& o = e->ops[i];
+            if (o.kind != DN_OP_PW) continue;
+            int bn, nt, st, cols;
+            size_t smem;
+            pwconv_tc_plan(o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
+            const long long m_max = (long long)e->max_batch * o.h_in * o.w_in;
+            int rc = make_tmap_bf16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128);
+            if (rc) return rc;
+            rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn);
+            if (rc) return rc;
+        }
+        e->tmaps_ready = true;
+    }
+    return DN_OK;
+}
+
+static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaStream_t s) {
+    {
+        const dn_op& o = e->ops[i];
+        const unsigned char* W = e->weights;
+        int rc = DN_OK;
+        switch (o.kind) {
+            case DN_OP_STEM:
+                rc = dn_stem_conv(images, (const float*)(W + o.w_off), (const float*)(W + o.b_off), e->desc.image_mean,
+                                  e->desc.image_std, buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_out, o.act, s);
+                break;
+            case DN_OP_DW:
+                rc = dn_dwconv(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
+                               buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize, o.stride, o.act, s);
+                break;
+            case DN_OP_PW: {
+                PwEpilogue ep;
+                const int hw = o.h_in * o.w_in;
+                ep.bias = (const float*)(W + o.b_off);
+                ep.residual = (const __nv_bfloat16*)buf_ptr(e, o.res_buf);
+                ep.y = (unsigned char*)buf_ptr(e, o.out_buf) + (size_t)o.out_offset * (o.out_fp32 ? 4 : 2);
+                ep.N = o.c_out;
+                ep.act = o.act;
+                ep.out_fp32 = o.out_fp32;
+                ep.hw = hw;
+                ep.out_batch_stride = o.out_batch_stride ? o.out_batch_stride : (long long)hw * o.c_out;
+                ep.out_row_stride = o.out_row_stride ? o.out_row_stride : o.c_out;
+                const int M = B * hw;
+                if (e->desc.gemm_impl == 0)
+                    rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], ep, M, o.c_in, o.c_out, s);
+                else
+                    rc = pwconv_simt(buf_ptr(e, o.in_buf), W + o.w_off, ep, M, o.c_in, o.c_out, s);
+                break;
+            }
+            case DN_OP_SE:
+                rc = dn_se_inplace(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
+                                   (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
+                                   o.c_mid, s);
+                break;
+        }
+        return rc;
+    }
+}
+
+static int enqueue_forward(dn_engine* e, const float* images, int B, float* out_boxes, float* out_scores,
+                           int64_t* out_labels, int32_t* out_counts, cudaStream_t s) {
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        int rc = enqueue_op(e, i, images, B, s);
+        if (rc) return rc;
+    }
+    return dn_postprocess((const float*)buf_ptr(e, e->desc.logits_buf), (const float*)buf_ptr(e, e->desc.bbox_buf),
+                          e->anchors_dev, B, &e->desc.post, e->post_ws, e->post_ws_bytes, out_boxes, out_scores, out_labels,
+                          out_counts, s);
+}
+
+extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
+                                 int64_t* out_labels, int32_t* out_counts, void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    DN_REQUIRE(e->weights != nullptr, DN_ERR_INVALID, "weights have not been loaded");
+    DN_REQUIRE(B > 0 && B <= e->max_batch, DN_ERR_INVALID, "batch %d outside [1, %d]", B, e->max_batch);
+    DN_REQUIRE(images_dev && out_boxes && out_scores && out_labels && out_counts, DN_ERR_INVALID, "NULL tensor pointer");
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!e->desc.use_cuda_graph) return enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, s);
+    GraphKey key{B, images_dev, out_boxes, out_scores, out_labels, out_counts};
+    GraphEntry& g = e->graphs[key];
+    if (!g.warm) {      // first call with these buffers runs eagerly (also configures kernel attributes)
+        g.warm = true;
+        return enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, s);
+    }
+    if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        DN_CHECK_CUDA(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, e->capture_stream);
+        cudaError_t ce = cudaStreamEndCapture(e->capture_stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        DN_REQUIRE(ce == cudaSuccess && graph, DN_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        DN_REQUIRE(ce == cudaSuccess, DN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    }
+    DN_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
+    return DN_OK;
+}
+
+extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
+                                      float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
+                                      void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    DN_REQUIRE(B > 0 && B <= e->max_batch, DN_ERR_INVALID, "batch %d outside [1, %d]", B, e->max_batch);
+    DN_REQUIRE(images_host && out_boxes_host && out_scores_host && out_labels_host && out_counts_host, DN_ERR_INVALID,
+               "NULL host pointer");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const size_t D = e->desc.post.detections_per_img;
+    const size_t img_bytes = (size_t)B * 3 * e->desc.image_h * e->desc.image_w * sizeof(float);
+    DN_CHECK_CUDA(cudaMemcpyAsync(e->stage_images, images_host, img_bytes, cudaMemcpyHostToDevice, s));
+    unsigned char* so = e->stage_out;
+    int rc = dn_engine_forward(e, e->stage_images, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
+                               (int64_t*)(so + e->so_labels), (int32_t*)(so + e->so_counts), s);
+    if (rc) return rc;
+    DN_CHECK_CUDA(cudaMemcpyAsync(out_boxes_host, so + e->so_boxes, (size_t)B * D * 16, cudaMemcpyDeviceToHost, s));
+    DN_CHECK_CUDA(cudaMemcpyAsync(out_scores_host, so + e->so_scores, (size_t)B * D * 4, cudaMemcpyDeviceToHost, s));
+    DN_CHECK_CUDA(cudaMemcpyAsync(out_labels_host, so + e->so_labels, (size_t)B * D * 8, cudaMemcpyDeviceToHost, s));
+    DN_CHECK_CUDA(cudaMemcpyAsync(out_counts_host, so + e->so_counts, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    return DN_OK;
+}
+
+extern "C" int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out) {
+    DN_REQUIRE(e && ptr_out, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(buf_id >= 0 && buf_id < (int)e->bufs.size(), DN_ERR_INVALID, "bad buffer id %d", buf_id);
+    *ptr_out = buf_ptr(e, buf_id);
+    if (elems_per_image_out) *elems_per_image_out = e->bufs[buf_id].elems_per_image;
+    return DN_OK;
+}
+
+extern "C" int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, size_t bytes, void* stream_) {
+    DN_REQUIRE(e && dst_dev, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(buf_id >= 0 && buf_id < (int)e->bufs.size(), DN_ERR_INVALID, "bad buffer id %d", buf_id);
+    const size_t cap = (size_t)e->bufs[buf_id].elems_per_image * e->bufs[buf_id].elem_bytes * e->max_batch;
+    DN_REQUIRE(bytes <= cap, DN_ERR_INVALID, "copy of %zu bytes exceeds the buffer (%zu)", bytes, cap);
+    DN_CHECK_CUDA(cudaMemcpyAsync(dst_dev, buf_ptr(e, buf_id), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    return DN_OK;
+}
+
+extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, int iters, float* ms_out_host, void* stream_) {
+    DN_REQUIRE(e && images_dev && ms_out_host, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(e->weights != nullptr, DN_ERR_INVALID, "weights have not been loaded");
+    DN_REQUIRE(B > 0 && B <= e->max_batch && iters > 0, DN_ERR_INVALID, "bad batch / iters");
+    cudaStream_t s = (cudaStream_t)stream_;
+    unsigned char* so = e->stage_out;
+    float* ob = (float*)(so + e->so_boxes);
+    float* os = (float*)(so + e->so_scores);
+    int64_t* ol = (int64_t*)(so + e->so_labels);
+    int32_t* oc = (int32_t*)(so + e->so_counts);
+    int rc = enqueue_forward(e, images_dev, B, ob, os, ol, oc, s);          // valid inputs for every layer
+    if (rc) return rc;
+    cudaEvent_t ev0, ev1;
+    DN_CHECK_CUDA(cudaEventCreate(&ev0));
+    DN_CHECK_CUDA(cudaEventCreate(&ev1));
+    const size_t n = e->ops.size();
+    for (size_t i = 0; i < n; ++i) {
+        // SE runs in place: re-running it rescales its input again, which does not change its cost
+        DN_CHECK_CUDA(cudaEventRecord(ev0, s));
+        for (int it = 0; it < iters; ++it) {
+            rc = enqueue_op(e, i, images_dev, B, s);
+            if (rc) return rc;
+        }
+        DN_CHECK_CUDA(cudaEventRecord(ev1, s));
+        DN_CHECK_CUDA(cudaEventSynchronize(ev1));
+        float ms = 0.f;
+        DN_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        ms_out_host[i] = ms / iters;
+    }
+    // the three post-processing kernels are bracketed inside postprocess.cu
+    rc = dn_postprocess_timed((const float*)buf_ptr(e, e->desc.logits_buf), (const float*)buf_ptr(e, e->desc.bbox_buf),
+                              e->anchors_dev, B, &e->desc.post, e->post_ws, e->post_ws_bytes, ob, os, ol, oc, s, iters,
+                              ms_out_host + n);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    // leave the arena in a consistent state (SE layers were re-applied)
+    if (!rc) rc = enqueue_forward(e, images_dev, B, ob, os, ol, oc, s);
+    if (!rc) DN_CHECK_CUDA(cudaStreamSynchronize(s));
+    return rc;
+}
+
+extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 3 : 0; }
+extern "C" size_t dn_engine_device_bytes(dn_engine* e) { return e ? e->device_bytes : 0; }

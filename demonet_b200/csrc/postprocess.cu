@@ -1,0 +1,799 @@
+// Fused SSD post-processing for sm_100a: softmax + box decode + clip, per-(image,class) threshold /
+// top-k / greedy NMS, and the per-image top-D merge.  Replaces SSD.postprocess_detections
+// (demonet/models/generalized_ssd.py:351-397), the legacy PostProcess.forward
+// (demonet/models/box_head.py:323-381) and torchvision.ops.batched_nms as called from both.
+//
+// Bit-exactness contract, all in fp32 WITHOUT fused multiply-add:
+//   area = (x2-x1)*(y2-y1);  inter = max(0,xx2-xx1)*max(0,yy2-yy1);
+//   iou  = inter / ((area_i + area_j) - inter);   suppress iff (double)iou > thr   (strict)
+//   candidates visited in stable descending-score order; NaN IoU never suppresses.
+// `(double)iou > thr` is evaluated as `iou >= thr_up`, thr_up = the smallest float whose double
+// value exceeds thr (computed on the host) -- identical for every float iou, NaN included.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace dn {
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t orderable(float f) {      // monotone float -> uint map
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t u) {
+    return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+// ascending sort of this key == (score descending, index ascending)
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t idx) {
+    return ((unsigned long long)(~orderable(score)) << 32) | idx;
+}
+__device__ __forceinline__ float key_score(unsigned long long k) { return from_orderable(~(uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_index(unsigned long long k) { return (uint32_t)k; }
+
+__device__ __forceinline__ float box_area(const float4& b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+// true iff box j is suppressed by kept box i
+__device__ __forceinline__ bool iou_exceeds(const float4& a, float aarea, const float4& b, float barea,
+                                            float thr_up) {
+    float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+    float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
+    float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    float ovr = __fdiv_rn(inter, uni);
+    return ovr >= thr_up;
+}
+
+// in-smem bitonic sort (ascending) of n_pad (power of two) 64-bit keys by the whole CTA
+__device__ void bitonic_sort_u64(unsigned long long* keys, int n_pad) {
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int hi = lo | j;
+                unsigned long long a = keys[lo], b = keys[hi];
+                bool up = ((lo & k) == 0);
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Greedy-NMS consumer.  Candidates arrive in visiting order in chunks of <= 32 (one per lane of
+// warp 0); the kept list (boxes + areas) lives in shared memory.  Every warp of the CTA helps with
+// the candidate-vs-kept test; warp 0 resolves the 32x32 dependencies inside the chunk with ballots.
+// A candidate is kept iff no EARLIER KEPT box overlaps it by more than the threshold -- exactly the
+// greedy loop of the CPU kernel.
+// ---------------------------------------------------------------------------------------------
+struct NmsState {
+    float4* kept_box;        // smem [max_keep]
+    float* kept_area;        // smem [max_keep]
+    float4* chunk_box;       // smem [32]
+    float* chunk_area;       // smem [32]
+    unsigned int* dead;      // smem word
+    int* n_kept;             // smem word
+};
+
+// cand_cnt <= 32 candidates already staged in st.chunk_box/area by the caller (and synced).
+// Returns (to every thread) a 32-bit mask of the candidates that were kept AND fit under max_keep;
+// appends them to the kept list.  Must be called by all threads of the CTA.
+__device__ unsigned int nms_consume_chunk(NmsState& st, int cand_cnt, float thr_up, int max_keep) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int nk = *st.n_kept;
+    // phase A: candidate (lane) vs kept boxes (strided over warps)
+    bool dead = false;
+    if (lane < cand_cnt) {
+        const float4 cb = st.chunk_box[lane];
+        const float ca = st.chunk_area[lane];
+        for (int k = warp; k < nk; k += nwarps) {
+            if (iou_exceeds(st.kept_box[k], st.kept_area[k], cb, ca, thr_up)) {
+                dead = true;
+                break;
+            }
+        }
+    }
+    unsigned int dead_bits = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0 && dead_bits) atomicOr(st.dead, dead_bits);
+    __syncthreads();
+    // phase B: warp 0 resolves the chunk
+    __shared__ unsigned int s_result;
+    if (warp == 0) {
+        unsigned int valid = (cand_cnt >= 32) ? 0xffffffffu : ((1u << cand_cnt) - 1u);
+        unsigned int alive = valid & ~(*st.dead);
+        float4 mb = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ma = 0.f;
+        if (lane < cand_cnt) {
+            mb = st.chunk_box[lane];
+            ma = st.chunk_area[lane];
+        }
+        for (int i = 0; i < cand_cnt; ++i) {
+            if (!((alive >> i) & 1u)) continue;          // warp-uniform
+            float4 ib;
+            ib.x = __shfl_sync(0xffffffffu, mb.x, i);
+            ib.y = __shfl_sync(0xffffffffu, mb.y, i);
+            ib.z = __shfl_sync(0xffffffffu, mb.z, i);
+            ib.w = __shfl_sync(0xffffffffu, mb.w, i);
+            float ia = __shfl_sync(0xffffffffu, ma, i);
+            bool sup = (lane > i) && ((alive >> lane) & 1u) && iou_exceeds(ib, ia, mb, ma, thr_up);
+            alive &= ~__ballot_sync(0xffffffffu, sup);
+        }
+        int room = max_keep - nk;
+        int rank = __popc(alive & ((1u << lane) - 1u));
+        bool mine = ((alive >> lane) & 1u) && rank < room;
+        if (mine) {
+            st.kept_box[nk + rank] = mb;
+            st.kept_area[nk + rank] = ma;
+        }
+        unsigned int taken = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) {
+            *st.n_kept = nk + __popc(taken);
+            *st.dead = 0u;
+            s_result = taken;
+        }
+    }
+    __syncthreads();
+    return s_result;
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1: softmax over classes + box decode + clip.  One CTA = 32 consecutive priors of one image.
+//   scores_t[b][k-1][p] = softmax(logits[b][p][:])[k]   (class-major so that P2 reads contiguously)
+//   boxes[b][p]         = clip(decode(bbox[b][p], anchors[p]))
+// ---------------------------------------------------------------------------------------------
+constexpr int P1_ROWS = 32;
+constexpr int P1_THREADS = 256;
+
+__global__ void __launch_bounds__(P1_THREADS)
+softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict__ bbox,
+                      const float* __restrict__ anchors, float* __restrict__ scores_t,
+                      float4* __restrict__ boxes, int P, int K, dn_postprocess_params prm) {
+    extern __shared__ float s_tile[];                    // [P1_ROWS][K + 1]
+    const int ld = K + 1;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * P1_ROWS;
+    const int rows = min(P1_ROWS, P - p0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // decode + clip (BoxCoder.decode_single, _utils.py:187-224; clip_boxes_to_image)
+    if (threadIdx.x < rows) {
+        const int p = p0 + threadIdx.x;
+        const float4 r = reinterpret_cast<const float4*>(bbox)[(size_t)b * P + p];
+        const float4 a = reinterpret_cast<const float4*>(anchors)[p];
+        const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
+        const float cx = __fadd_rn(a.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(a.y, __fmul_rn(0.5f, h));
+        const float dx = __fdiv_rn(r.x, prm.box_weights[0]), dy = __fdiv_rn(r.y, prm.box_weights[1]);
+        const float dw = fminf(__fdiv_rn(r.z, prm.box_weights[2]), prm.bbox_xform_clip);
+        const float dh = fminf(__fdiv_rn(r.w, prm.box_weights[3]), prm.bbox_xform_clip);
+        const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+        const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+        const float hw = __fmul_rn(0.5f, pw), hh = __fmul_rn(0.5f, ph);
+        float4 o;
+        o.x = fminf(fmaxf(__fsub_rn(pcx, hw), 0.f), (float)prm.image_w);
+        o.y = fminf(fmaxf(__fsub_rn(pcy, hh), 0.f), (float)prm.image_h);
+        o.z = fminf(fmaxf(__fadd_rn(pcx, hw), 0.f), (float)prm.image_w);
+        o.w = fminf(fmaxf(__fadd_rn(pcy, hh), 0.f), (float)prm.image_h);
+        boxes[(size_t)b * P + p] = o;
+    }
+
+    // softmax, one warp per row
+    for (int r = warp; r < rows; r += P1_THREADS / 32) {
+        const float* src = logits + ((size_t)b * P + p0 + r) * K;
+        float* dst = s_tile + r * ld;
+        float m = -FLT_MAX;
+        for (int k = lane; k < K; k += 32) {
+            float v = src[k];
+            dst[k] = v;
+            m = fmaxf(m, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            float e = expf(dst[k] - m);
+            dst[k] = e;
+            s += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        for (int k = lane; k < K; k += 32) dst[k] = __fdiv_rn(dst[k], s);
+    }
+    __syncthreads();
+    // transposed, coalesced store of classes 1..K-1
+    for (int k = 1 + warp; k < K; k += P1_THREADS / 32) {
+        if (lane < rows) scores_t[((size_t)b * (K - 1) + (k - 1)) * P + p0 + lane] = s_tile[lane * ld + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P2: one CTA per (class, image): threshold, stable top-k, greedy NMS, first D kept.
+// ---------------------------------------------------------------------------------------------
+constexpr int P2_THREADS = 256;
+constexpr int P2_STAGE = 1024;       // candidates staged in smem per round
+
+struct Entry {                        // one kept detection of a class list
+    float score;
+    int prior;
+};
+
+__global__ void __launch_bounds__(P2_THREADS)
+class_nms_kernel(const float* __restrict__ scores_t, const float4* __restrict__ boxes,
+                 Entry* __restrict__ out_entries, int* __restrict__ out_counts, int P, int K, int n_pad_max,
+                 float score_thresh, float thr_up, int topk, int D, float min_box_size) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_raw);              // [n_pad_max]
+    float4* kept_box = reinterpret_cast<float4*>(keys + n_pad_max);                        // [D]
+    float4* stage_box = kept_box + D;                                                     // [P2_STAGE]
+    float* kept_area = reinterpret_cast<float*>(stage_box + P2_STAGE);                     // [D]
+    float* stage_area = kept_area + D;                                                    // [P2_STAGE]
+    __shared__ int s_n, s_nkept;
+    __shared__ unsigned int s_dead;
+    __shared__ float4 s_chunk_box[32];
+    __shared__ float s_chunk_area[32];
+
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const float* sc = scores_t + ((size_t)b * (K - 1) + c) * P;
+    const float4* bx = boxes + (size_t)b * P;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_nkept = 0;
+        s_dead = 0u;
+    }
+    __syncthreads();
+
+    // (a) threshold (fp32 compare, generalized_ssd.py:371) [+ legacy remove_small_boxes, box_head.py:370]
+    for (int p0 = 0; p0 < P; p0 += P2_THREADS) {
+        const int p = p0 + threadIdx.x;
+        float s = 0.f;
+        bool pass = false;
+        if (p < P) {
+            s = sc[p];
+            pass = s > score_thresh;
+            if (pass && min_box_size >= 0.f) {
+                const float4 q = bx[p];
+                pass = (__fsub_rn(q.z, q.x) >= min_box_size) && (__fsub_rn(q.w, q.y) >= min_box_size);
+            }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) keys[base + __popc(m & ((1u << lane) - 1u))] = make_key(s, (uint32_t)p);
+    }
+    __syncthreads();
+    const int n = s_n;
+    Entry* dst = out_entries + ((size_t)b * (K - 1) + c) * D;
+    if (n == 0) {
+        if (threadIdx.x == 0) out_counts[b * (K - 1) + c] = 0;
+        return;
+    }
+    // (b) stable descending sort (score desc, prior asc)
+    int n_pad = 32;
+    while (n_pad < n) n_pad <<= 1;
+    for (int i = n + threadIdx.x; i < n_pad; i += P2_THREADS) keys[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(keys, n_pad);
+    // (c) top-k (generalized_ssd.py:376-378)
+    const int m = (topk > 0 && topk < n) ? topk : n;
+
+    // (d) greedy NMS over the first m candidates, stop at D kept
+    NmsState st{kept_box, kept_area, s_chunk_box, s_chunk_area, &s_dead, &s_nkept};
+    for (int s0 = 0; s0 < m; s0 += P2_STAGE) {
+        const int scnt = min(P2_STAGE, m - s0);
+        for (int i = threadIdx.x; i < scnt; i += P2_THREADS) {
+            const float4 q = bx[key_index(keys[s0 + i])];
+            stage_box[i] = q;
+            stage_area[i] = box_area(q);
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < scnt; c0 += 32) {
+            const int cnt = min(32, scnt - c0);
+            if (threadIdx.x < cnt) {
+                s_chunk_box[threadIdx.x] = stage_box[c0 + threadIdx.x];
+                s_chunk_area[threadIdx.x] = stage_area[c0 + threadIdx.x];
+            }
+            __syncthreads();
+            const int nk_before = s_nkept;
+            const unsigned int taken = nms_consume_chunk(st, cnt, thr_up, D);
+            if (threadIdx.x < 32 && ((taken >> lane) & 1u)) {
+                const unsigned long long kk = keys[s0 + c0 + lane];
+                Entry e;
+                e.score = key_score(kk);
+                e.prior = (int)key_index(kk);
+                dst[nk_before + __popc(taken & ((1u << lane) - 1u))] = e;
+            }
+            if (s_nkept >= D) break;         // uniform: s_nkept written before the closing barrier
+        }
+        if (s_nkept >= D) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_counts[b * (K - 1) + c] = s_nkept;
+}
+
+// ---------------------------------------------------------------------------------------------
+// P3: one warp per image merges the (K-1) per-class kept lists (each already in descending
+// order) and emits the first D by (score desc, class asc, rank asc) -- keep[:detections_per_img].
+// ---------------------------------------------------------------------------------------------
+constexpr int P3_MAX_PER_LANE = 8;     // supports K-1 <= 256 classes
+
+__global__ void __launch_bounds__(32)
+merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts,
+                  const float4* __restrict__ boxes, float4* __restrict__ out_boxes,
+                  float* __restrict__ out_scores, long long* __restrict__ out_labels,
+                  int* __restrict__ out_counts, int P, int K, int D) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int nc = K - 1;
+    int pos[P3_MAX_PER_LANE], cnt[P3_MAX_PER_LANE];
+    Entry head[P3_MAX_PER_LANE];
+#pragma unroll
+    for (int i = 0; i < P3_MAX_PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        pos[i] = 0;
+        cnt[i] = (c < nc) ? counts[b * nc + c] : 0;
+        head[i].score = 0.f;
+        head[i].prior = 0;
+        if (cnt[i] > 0) head[i] = entries[((size_t)b * nc + c) * D];
+    }
+    int d = 0;
+    for (; d < D; ++d) {
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int i = 0; i < P3_MAX_PER_LANE; ++i) {
+            if (pos[i] < cnt[i]) {
+                unsigned long long k = ((unsigned long long)orderable(head[i].score) << 32) |
+                                       (0xffffffffu - (uint32_t)(lane + 32 * i));
+                best = (k > best) ? k : best;
+            }
+        }
+        unsigned long long w = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long t = __shfl_xor_sync(0xffffffffu, w, o);
+            w = (t > w) ? t : w;
+        }
+        if (w == 0ull) break;
+        const int cls = (int)(0xffffffffu - (uint32_t)w);
+        if ((cls & 31) == lane) {
+            const int i = cls >> 5;
+            Entry e = head[0];
+#pragma unroll
+            for (int q = 1; q < P3_MAX_PER_LANE; ++q)
+                if (q == i) e = head[q];
+            out_scores[(size_t)b * D + d] = e.score;
+            out_labels[(size_t)b * D + d] = (long long)(cls + 1);
+            out_boxes[(size_t)b * D + d] = boxes[(size_t)b * P + e.prior];
+#pragma unroll
+            for (int q = 0; q < P3_MAX_PER_LANE; ++q) {
+                if (q == i) {
+                    pos[q] += 1;
+                    if (pos[q] < cnt[q]) head[q] = entries[((size_t)b * nc + cls) * D + pos[q]];
+                }
+            }
+        }
+    }
+    if (lane == 0) out_counts[b] = d;
+    for (int i = d + lane; i < D; i += 32) {
+        out_scores[(size_t)b * D + i] = 0.f;
+        out_labels[(size_t)b * D + i] = 0;
+        out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static float threshold_up(double thr) {
+    // smallest float f with (double)f > thr
+    float f = (float)thr;
+    if ((double)f > thr) {
+        float g = nextafterf(f, -INFINITY);
+        while ((double)g > thr) {
+            f = g;
+            g = nextafterf(f, -INFINITY);
+        }
+        return f;
+    }
+    while (!((double)f > thr)) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+static int next_pow2(int v) {
+    int p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct PostLayout {
+    size_t scores_off, boxes_off, entries_off, counts_off, total;
+};
+static PostLayout post_layout(int B, const dn_postprocess_params* p) {
+    PostLayout L;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t P = p->num_priors, K = p->num_classes, D = p->detections_per_img;
+    size_t off = 0;
+    L.scores_off = off; off = al(off + (size_t)B * (K - 1) * P * sizeof(float));
+    L.boxes_off = off;  off = al(off + (size_t)B * P * sizeof(float4));
+    L.entries_off = off; off = al(off + (size_t)B * (K - 1) * D * sizeof(Entry));
+    L.counts_off = off; off = al(off + (size_t)B * (K - 1) * sizeof(int));
+    L.total = off;
+    return L;
+}
+
+static size_t p2_smem_bytes(int n_pad_max, int D) {
+    return (size_t)n_pad_max * 8 + (size_t)(D + P2_STAGE) * (sizeof(float4) + sizeof(float));
+}
+
+}  // namespace dn
+
+using namespace dn;
+
+extern "C" size_t dn_postprocess_workspace_bytes(int B, const dn_postprocess_params* p) {
+    if (!p || B <= 0) return 0;
+    return post_layout(B, p).total;
+}
+
+static int validate_post(const dn_postprocess_params* p) {
+    DN_REQUIRE(p != nullptr, DN_ERR_INVALID, "postprocess params are NULL");
+    DN_REQUIRE(p->num_priors > 0 && p->num_classes >= 2, DN_ERR_INVALID, "need num_priors > 0 and num_classes >= 2");
+    DN_REQUIRE(p->num_classes - 1 <= 32 * P3_MAX_PER_LANE, DN_ERR_UNSUPPORTED, "at most %d foreground classes",
+               32 * P3_MAX_PER_LANE);
+    DN_REQUIRE(p->detections_per_img > 0 && p->detections_per_img <= 4096, DN_ERR_UNSUPPORTED,
+               "detections_per_img must be in [1,4096]");
+    DN_REQUIRE(p->num_priors <= 32768, DN_ERR_UNSUPPORTED, "at most 32768 priors per image");
+    const size_t smem = p2_smem_bytes(next_pow2(p->num_priors), p->detections_per_img);
+    DN_REQUIRE(smem <= 200 * 1024, DN_ERR_UNSUPPORTED, "priors/detections too large for the shared-memory NMS (%zu B)", smem);
+    return DN_OK;
+}
+
+static int postprocess_impl(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                            const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                            float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
+                            float* ms3) {
+    int rc = validate_post(p);
+    if (rc) return rc;
+    DN_REQUIRE(B > 0, DN_ERR_INVALID, "batch must be positive");
+    DN_REQUIRE(cls_logits && bbox_regression && anchors && out_boxes && out_scores && out_labels && out_counts,
+               DN_ERR_INVALID, "NULL tensor pointer");
+    const PostLayout L = post_layout(B, p);
+    DN_REQUIRE(workspace && workspace_bytes >= L.total, DN_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    const int P = p->num_priors, K = p->num_classes, D = p->detections_per_img;
+    unsigned char* ws = (unsigned char*)workspace;
+    float* scores_t = (float*)(ws + L.scores_off);
+    float4* boxes = (float4*)(ws + L.boxes_off);
+    Entry* entries = (Entry*)(ws + L.entries_off);
+    int* counts = (int*)(ws + L.counts_off);
+    const size_t smem1 = (size_t)P1_ROWS * (K + 1) * sizeof(float);
+    if (smem1 > 48 * 1024)
+        DN_CHECK_CUDA(cudaFuncSetAttribute(softmax_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    const int n_pad_max = next_pow2(P);
+    const size_t smem2 = p2_smem_bytes(n_pad_max, D);
+    static size_t configured = 0;
+    if (smem2 > configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(class_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        configured = smem2;
+    }
+    const float thr_up = threshold_up(p->nms_thresh);
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (ms3) {
+        DN_CHECK_CUDA(cudaEventCreate(&ev[0]));
+        DN_CHECK_CUDA(cudaEventCreate(&ev[1]));
+    }
+    for (int phase = 0; phase < 3; ++phase) {
+        if (ms3) DN_CHECK_CUDA(cudaEventRecord(ev[0], stream));
+        for (int it = 0; it < iters; ++it) {
+            if (phase == 0) {
+                dim3 grid(ceil_div(P, P1_ROWS), B);
+                softmax_decode_kernel<<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors, scores_t,
+                                                                          boxes, P, K, *p);
+            } else if (phase == 1) {
+                dim3 grid(K - 1, B);
+                class_nms_kernel<<<grid, P2_THREADS, smem2, stream>>>(scores_t, boxes, entries, counts, P, K, n_pad_max,
+                                                                     p->score_thresh, thr_up, p->topk_candidates, D,
+                                                                     p->min_box_size);
+            } else {
+                merge_topd_kernel<<<B, 32, 0, stream>>>(entries, counts, boxes, (float4*)out_boxes, out_scores,
+                                                        (long long*)out_labels, out_counts, P, K, D);
+            }
+            DN_CHECK_LAUNCH();
+        }
+        if (ms3) {
+            DN_CHECK_CUDA(cudaEventRecord(ev[1], stream));
+            DN_CHECK_CUDA(cudaEventSynchronize(ev[1]));
+            DN_CHECK_CUDA(cudaEventElapsedTime(&ms3[phase], ev[0], ev[1]));
+            ms3[phase] /= iters;
+        }
+    }
+    if (ms3) {
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    }
+    return DN_OK;
+}
+
+extern "C" int dn_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                              const dn_postprocess_params* p, void* workspace, size_t workspace_bytes,
+                              float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_counts,
+                              void* stream_) {
+    return postprocess_impl(cls_logits, bbox_regression, anchors, B, p, workspace, workspace_bytes, out_boxes, out_scores,
+                            out_labels, out_counts, (cudaStream_t)stream_, 1, nullptr);
+}
+
+// measurement aid used by dn_engine_profile / dn_postprocess_profile: mean ms of P1, P2, P3
+int dn_postprocess_timed(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                         const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                         float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
+                         float* ms3) {
+    return postprocess_impl(cls_logits, bbox_regression, anchors, B, p, workspace, workspace_bytes, out_boxes, out_scores,
+                            out_labels, out_counts, stream, iters, ms3);
+}
+
+extern "C" int dn_postprocess_profile(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                                      const dn_postprocess_params* p, void* workspace, size_t workspace_bytes,
+                                      float* out_boxes, float* out_scores, int64_t* out_labels, int32_t* out_counts,
+                                      int iters, float* ms3_host, void* stream_) {
+    DN_REQUIRE(iters > 0 && ms3_host, DN_ERR_INVALID, "bad iters / NULL output");
+    return postprocess_impl(cls_logits, bbox_regression, anchors, B, p, workspace, workspace_bytes, out_boxes, out_scores,
+                            out_labels, out_counts, (cudaStream_t)stream_, iters, ms3_host);
+}
+
+// =============================================================================================
+// dn_batched_nms: torchvision.ops.batched_nms, per-class ("vanilla") semantics, arbitrary n.
+//   1. global stable sort of (score desc, index asc) keys  -> visiting order
+//   2. one CTA per class streams the sorted keys, picks its members in order and runs the same
+//      greedy consumer; kept flags are written per rank
+//   3. order-preserving compaction of the flagged ranks -> keep[] (already in descending score)
+// =============================================================================================
+namespace dn {
+
+constexpr int BN_MAX_LABEL = 4096;
+constexpr int BN_MAX_KEEP = 4096;
+constexpr int BN_THREADS = 256;
+
+__global__ void bnms_prepare_kernel(const float* __restrict__ scores, const long long* __restrict__ idxs,
+                                    long long n, long long n_pad, unsigned long long* __restrict__ keys,
+                                    int* __restrict__ hist, int* __restrict__ err) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n) {
+            keys[i] = make_key(scores[i], (uint32_t)i);
+            long long l = idxs[i];
+            if (l < 0 || l >= BN_MAX_LABEL) atomicExch(err, 1);
+            else atomicAdd(&hist[l], 1);
+        } else {
+            keys[i] = ~0ull;
+        }
+    }
+}
+
+// one bitonic (k, j) step over global memory
+__global__ void bnms_bitonic_step_kernel(unsigned long long* __restrict__ keys, long long n_pad, long long k, long long j) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (n_pad >> 1); t += (long long)gridDim.x * blockDim.x) {
+        long long lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        long long hi = lo | j;
+        unsigned long long a = keys[lo], b = keys[hi];
+        bool up = ((lo & k) == 0);
+        if ((a > b) == up) {
+            keys[lo] = b;
+            keys[hi] = a;
+        }
+    }
+}
+
+// every (k, j) step with j < BN_TILE is tile-local: phases k_lo..k_hi run inside shared memory
+constexpr int BN_TILE = 4096;
+__global__ void __launch_bounds__(1024)
+bnms_bitonic_tile_kernel(unsigned long long* __restrict__ keys, long long k_lo, long long k_hi) {
+    __shared__ unsigned long long s[BN_TILE];
+    const long long base = (long long)blockIdx.x * BN_TILE;
+    for (int i = threadIdx.x; i < BN_TILE; i += blockDim.x) s[i] = keys[base + i];
+    __syncthreads();
+    for (long long k = k_lo; k <= k_hi; k <<= 1) {
+        const int j0 = (int)((k >> 1) < (BN_TILE / 2) ? (k >> 1) : (BN_TILE / 2));
+        for (int j = j0; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < BN_TILE / 2; t += blockDim.x) {
+                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int hi = lo | j;
+                unsigned long long a = s[lo], b = s[hi];
+                bool up = (((base + lo) & k) == 0);
+                if ((a > b) == up) {
+                    s[lo] = b;
+                    s[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < BN_TILE; i += blockDim.x) keys[base + i] = s[i];
+}
+
+__global__ void __launch_bounds__(BN_THREADS)
+bnms_class_kernel(const float4* __restrict__ boxes, const long long* __restrict__ idxs,
+                  const unsigned long long* __restrict__ keys, long long n, const int* __restrict__ hist,
+                  unsigned char* __restrict__ kept_flag, int* __restrict__ err, float thr_up) {
+    const int cls = blockIdx.x;
+    const int members = hist[cls];
+    if (members == 0) return;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float4* kept_box = reinterpret_cast<float4*>(s_raw);                    // [BN_MAX_KEEP]
+    float* kept_area = reinterpret_cast<float*>(kept_box + BN_MAX_KEEP);    // [BN_MAX_KEEP]
+    __shared__ int s_nkept, s_cnt;
+    __shared__ unsigned int s_dead;
+    __shared__ float4 s_chunk_box[32];
+    __shared__ float s_chunk_area[32];
+    __shared__ long long s_chunk_rank[32];
+    __shared__ int s_warp_cnt[BN_THREADS / 32];
+    if (threadIdx.x == 0) {
+        s_nkept = 0;
+        s_dead = 0u;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    NmsState st{kept_box, kept_area, s_chunk_box, s_chunk_area, &s_dead, &s_nkept};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int seen = 0;
+    // stream ranks in tiles of BN_THREADS; members of this class are compacted IN ORDER into chunks of 32
+    for (long long r0 = 0; r0 < n && seen < members; r0 += BN_THREADS) {
+        const long long r = r0 + threadIdx.x;
+        bool mine = false;
+        uint32_t idx = 0;
+        if (r < n) {
+            idx = key_index(keys[r]);
+            mine = (idxs[idx] == (long long)cls);
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < BN_THREADS / 32; ++w) {
+            int cw = s_warp_cnt[w];
+            if (w < warp) before += cw;
+            total += cw;
+        }
+        const int my_pos = before + __popc(bal & ((1u << lane) - 1u));    // order-preserving position in this tile
+        __syncthreads();                                                   // s_warp_cnt is rewritten next tile
+        // feed the tile's members to the consumer in groups that complete 32-wide chunks
+        int fed = 0;
+        while (fed < total) {
+            const int room = 32 - s_cnt;                                   // uniform (read after barrier)
+            const int take = min(room, total - fed);
+            if (mine && my_pos >= fed && my_pos < fed + take) {
+                const int slot = s_cnt + (my_pos - fed);
+                const float4 q = boxes[idx];
+                s_chunk_box[slot] = q;
+                s_chunk_area[slot] = box_area(q);
+                s_chunk_rank[slot] = r;
+            }
+            __syncthreads();
+            const int cnt = s_cnt + take;
+            fed += take;
+            const bool last_of_class = (seen + fed == members);
+            if (cnt == 32 || last_of_class) {
+                const unsigned int taken = nms_consume_chunk(st, cnt, thr_up, BN_MAX_KEEP);
+                if (threadIdx.x < 32 && ((taken >> lane) & 1u)) kept_flag[s_chunk_rank[lane]] = 1;
+                if (threadIdx.x == 0) s_cnt = 0;
+                if (s_nkept >= BN_MAX_KEEP && !last_of_class) {             // uniform: kept list is full
+                    if (threadIdx.x == 0) atomicExch(err, 2);
+                    return;
+                }
+            } else {
+                if (threadIdx.x == 0) s_cnt = cnt;
+            }
+            __syncthreads();
+        }
+        seen += total;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+bnms_compact_kernel(const unsigned long long* __restrict__ keys, const unsigned char* __restrict__ kept_flag,
+                    long long n, long long* __restrict__ keep_out, long long* __restrict__ nkeep_out,
+                    const int* __restrict__ err) {
+    __shared__ int s_warp[32];
+    __shared__ long long s_base;
+    if (*err != 0) {
+        if (threadIdx.x == 0) *nkeep_out = -(long long)(*err);
+        return;
+    }
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long r0 = 0; r0 < n; r0 += 1024) {
+        const long long r = r0 + threadIdx.x;
+        const bool f = (r < n) && kept_flag[r];
+        const unsigned int bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            int cw = s_warp[w];
+            if (w < warp) before += cw;
+            total += cw;
+        }
+        if (f) keep_out[s_base + before + __popc(bal & ((1u << lane) - 1u))] = (long long)key_index(keys[r]);
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nkeep_out = s_base;
+}
+
+struct BnmsLayout {
+    size_t keys_off, hist_off, flag_off, err_off, total;
+    long long n_pad;
+};
+static BnmsLayout bnms_layout(long long n) {
+    BnmsLayout L;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    long long n_pad = BN_TILE;
+    while (n_pad < n) n_pad <<= 1;
+    L.n_pad = n_pad;
+    size_t off = 0;
+    L.keys_off = off; off = al(off + (size_t)n_pad * 8);
+    L.hist_off = off; off = al(off + (size_t)BN_MAX_LABEL * sizeof(int));
+    L.flag_off = off; off = al(off + (size_t)(n > 0 ? n : 1));
+    L.err_off = off;  off = al(off + sizeof(int));
+    L.total = off;
+    return L;
+}
+
+}  // namespace dn
+
+extern "C" size_t dn_batched_nms_workspace_bytes(int64_t n) { return bnms_layout(n < 0 ? 0 : n).total; }
+
+extern "C" int dn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n,
+                              double iou_threshold, void* workspace, size_t workspace_bytes, int64_t* keep_out,
+                              int64_t* nkeep_out, void* stream_) {
+    DN_REQUIRE(n >= 0 && n < (1ll << 31), DN_ERR_INVALID, "n out of range");
+    DN_REQUIRE(nkeep_out != nullptr, DN_ERR_INVALID, "nkeep_out is NULL");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) {
+        DN_CHECK_CUDA(cudaMemsetAsync(nkeep_out, 0, sizeof(int64_t), stream));
+        return DN_OK;
+    }
+    DN_REQUIRE(boxes && scores && idxs && keep_out, DN_ERR_INVALID, "NULL tensor pointer");
+    const BnmsLayout L = bnms_layout(n);
+    DN_REQUIRE(workspace && workspace_bytes >= L.total, DN_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
+    unsigned char* ws = (unsigned char*)workspace;
+    unsigned long long* keys = (unsigned long long*)(ws + L.keys_off);
+    int* hist = (int*)(ws + L.hist_off);
+    unsigned char* flag = ws + L.flag_off;
+    int* err = (int*)(ws + L.err_off);
+    DN_CHECK_CUDA(cudaMemsetAsync(ws + L.hist_off, 0, L.total - L.hist_off, stream));
+    const int blocks = (int)std::min<long long>(ceil_div<long long>(L.n_pad, 256), 148 * 8);
+    bnms_prepare_kernel<<<blocks, 256, 0, stream>>>(scores, (const long long*)idxs, n, L.n_pad, keys, hist, err);
+    DN_CHECK_LAUNCH();
+    // bitonic sort: phases k <= BN_TILE in one in-smem launch; then, per larger k, global steps
+    // while j >= BN_TILE followed by one in-smem launch for the remaining j
+    const unsigned tiles = (unsigned)(L.n_pad / BN_TILE);
+    bnms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(keys, 2, BN_TILE);
+    DN_CHECK_LAUNCH();
+    for (long long k = 2 * (long long)BN_TILE; k <= L.n_pad; k <<= 1) {
+        for (long long j = k >> 1; j >= BN_TILE; j >>= 1) {
+            bnms_bitonic_step_kernel<<<blocks, 256, 0, stream>>>(keys, L.n_pad, k, j);
+            DN_CHECK_LAUNCH();
+        }
+        bnms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(keys, k, k);
+        DN_CHECK_LAUNCH();
+    }
+    const size_t smem = (size_t)BN_MAX_KEEP * (sizeof(float4) + sizeof(float));
+    static bool configured = false;
+    if (!configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(bnms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    bnms_class_kernel<<<BN_MAX_LABEL, BN_THREADS, smem, stream>>>((const float4*)boxes, (const long long*)idxs, keys, n,
+                                                                hist, flag, err, threshold_up(iou_threshold));
+    DN_CHECK_LAUNCH();
+    bnms_compact_kernel<<<1, 1024, 0, stream>>>(keys, flag, n, (long long*)keep_out, (long long*)nkeep_out, err);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}

@@ -1,0 +1,47 @@
+// Epilogue shared by the pointwise-GEMM kernels: folded-BN bias, activation, residual add and the
+// strided output addressing that turns the head's view/permute/reshape/cat into plain stores.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dn {
+
+struct PwEpilogue {
+    const float* bias;                 // [N]
+    const __nv_bfloat16* residual;     // [M, N] or nullptr
+    void* y;
+    int N;
+    int act;
+    int out_fp32;
+    int hw;                            // rows per image
+    long long out_batch_stride;        // elements
+    long long out_row_stride;          // elements
+
+    __device__ __forceinline__ long long row_offset(int m) const {
+        const int b = m / hw, r = m - b * hw;
+        return (long long)b * out_batch_stride + (long long)r * out_row_stride;
+    }
+    // y = act(acc + bias[n]) (+ residual[m][n]), single rounding at the end
+    __device__ __forceinline__ float finish(int m, int n, float acc) const {
+        float v = apply_act(acc + __ldg(bias + n), act);
+        if (residual) v += __bfloat162float(residual[(long long)m * N + n]);
+        return v;
+    }
+    __device__ __forceinline__ void store(int m, int n, float acc) const {
+        const float v = finish(m, n, acc);
+        const long long o = row_offset(m) + n;
+        if (out_fp32) reinterpret_cast<float*>(y)[o] = v;
+        else reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(v);
+    }
+};
+
+int pwconv_simt(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream);
+int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream);
+// pieces of pwconv_tc that the engine caches per layer
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows);
+void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes);
+int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilogue& ep, int M, int K, int N,
+                     cudaStream_t stream);
+
+}  // namespace dn

@@ -1,0 +1,307 @@
+"""Drop-in `nn.Module` for demonet's SSDLite detectors, executing on the B200 engine.
+
+Same constructor arguments, `state_dict` keys, `forward(images, targets=None)` input contract and
+`List[Dict[boxes, scores, labels]]` output contract as the reference's `SSD`
+(demonet/models/generalized_ssd.py:95-397), inference only.  The arithmetic runs in
+libdemonet_b200.so through ctypes; PyTorch only owns parameters, device memory and streams.
+"""
+import ctypes
+import math
+import warnings
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import _C, plan as _plan
+
+
+class _Engine:
+    """Owns one dn_engine (one device, one max batch) and the weight blob uploaded to it."""
+
+    def __init__(self, plan: _plan.Plan, desc_kwargs: dict, max_batch: int, device: torch.device):
+        self.plan = plan
+        self.device = device
+        self.max_batch = max_batch
+        self.t2b, self.bufs, self.logits_buf, self.bbox_buf = _plan.assign_buffers(
+            plan, reuse=not desc_kwargs.get("keep_activations", False))
+        self.anchors = _plan.default_boxes(plan)
+        self._handle = ctypes.c_void_p()
+        self._weights_token = None
+        self._desc_kwargs = desc_kwargs
+        self._ops = None
+        self._created = False
+
+    def _create(self, offsets):
+        lib = _C.lib()
+        plan, kw = self.plan, self._desc_kwargs
+        self._ops = _plan.build_ops(plan, offsets, self.t2b, self.logits_buf, self.bbox_buf)
+        bufs = (_C.Buf * len(self.bufs))()
+        for i, (elems, nbytes) in enumerate(self.bufs):
+            bufs[i].elems_per_image, bufs[i].elem_bytes = elems, nbytes
+        d = _C.ModelDesc()
+        d.image_h = d.image_w = plan.size
+        d.image_mean = (ctypes.c_float * 3)(*kw["image_mean"])
+        d.image_std = (ctypes.c_float * 3)(*kw["image_std"])
+        d.n_ops, d.n_bufs = len(plan.layers), len(self.bufs)
+        d.ops_host = ctypes.cast(self._ops, ctypes.POINTER(_C.Op))
+        d.bufs_host = ctypes.cast(bufs, ctypes.POINTER(_C.Buf))
+        d.logits_buf, d.bbox_buf = self.logits_buf, self.bbox_buf
+        d.anchors_host = self.anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        d.post = make_post_params(plan.num_priors, plan.num_classes, plan.size, plan.size, kw["score_thresh"],
+                                  kw["nms_thresh"], kw["topk_candidates"], kw["detections_per_img"],
+                                  kw.get("min_box_size", -1.0))
+        d.gemm_impl = int(kw.get("gemm_impl", 0))
+        d.use_cuda_graph = int(kw.get("use_cuda_graph", 1))
+        with torch.cuda.device(self.device):
+            _C.check(lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
+        self._created = True
+
+    def load_weights(self, sd, token):
+        blob, offsets = _plan.pack_weights(self.plan, sd)
+        if not self._created:
+            self._create(offsets)
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_load_weights(self._handle, buf, len(blob)))
+        self._weights_token = token
+
+    def forward(self, images: Tensor, out):
+        B = images.shape[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_forward(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
+                                               out["scores"].data_ptr(), out["labels"].data_ptr(),
+                                               out["counts"].data_ptr(), stream))
+
+    def forward_host(self, images: Tensor, out):
+        B = images.shape[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_forward_host(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
+                                                    out["scores"].data_ptr(), out["labels"].data_ptr(),
+                                                    out["counts"].data_ptr(), stream))
+
+    def buffer(self, tensor_name: str, batch: int) -> Tensor:
+        """Copy of an intermediate activation as fp32 NCHW (for stage-by-stage parity tests)."""
+        h, w, c = self.plan.tensors[tensor_name]
+        return self._read(self.t2b[tensor_name], batch, (h, w, c), torch.bfloat16).permute(0, 3, 1, 2).float()
+
+    def head_outputs(self, batch: int) -> Tuple[Tensor, Tensor]:
+        P, K = self.plan.num_priors, self.plan.num_classes
+        return (self._read(self.logits_buf, batch, (P, K), torch.float32),
+                self._read(self.bbox_buf, batch, (P, 4), torch.float32))
+
+    def _read(self, buf_id, batch, shape, dtype):
+        n = batch * int(np.prod(shape))
+        out = torch.empty(n, dtype=dtype, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_copy_buffer(self._handle, buf_id, out.data_ptr(), n * out.element_size(), stream))
+        return out.view(batch, *shape)
+
+    @property
+    def launches_per_forward(self):
+        return _C.lib().dn_engine_launches_per_forward(self._handle)
+
+    @property
+    def device_bytes(self):
+        return _C.lib().dn_engine_device_bytes(self._handle)
+
+    def close(self):
+        if self._created and self._handle:
+            _C.lib().dn_engine_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+            self._created = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_post_params(P, K, image_h, image_w, score_thresh, nms_thresh, topk_candidates, detections_per_img,
+                     min_box_size=-1.0) -> _C.PostprocessParams:
+    p = _C.PostprocessParams()
+    p.num_priors, p.num_classes, p.image_h, p.image_w = P, K, image_h, image_w
+    p.score_thresh = score_thresh
+    p.nms_thresh = float(nms_thresh)
+    p.topk_candidates = int(topk_candidates) if topk_candidates else 0
+    p.detections_per_img = int(detections_per_img)
+    p.min_box_size = float(min_box_size)
+    p.box_weights = (ctypes.c_float * 4)(10.0, 10.0, 5.0, 5.0)      # generalized_ssd.py:170
+    p.bbox_xform_clip = math.log(1000.0 / 16)                        # _utils.py:135
+    return p
+
+
+class SSDLiteB200(nn.Module):
+    """Inference-only SSDLite detector on the B200 engine.
+
+    Args mirror `SSD.__init__` (generalized_ssd.py:154-163): score_thresh, nms_thresh,
+    detections_per_img, topk_candidates, image_mean, image_std.  `postprocess` selects the
+    reference flavour: "ssd" = SSD.postprocess_detections (generalized_ssd.py:351-397),
+    "legacy" = PostProcess.forward (box_head.py:323-381: no per-class top-k, remove_small_boxes).
+    """
+
+    def __init__(self, plan: _plan.Plan, score_thresh=0.01, nms_thresh=0.45, detections_per_img=200,
+                 topk_candidates=400, image_mean=None, image_std=None, postprocess="ssd", init="normal",
+                 gemm_impl=0, use_cuda_graph=True, keep_activations=False):
+        super().__init__()
+        if postprocess not in ("ssd", "legacy"):
+            raise ValueError("postprocess must be 'ssd' or 'legacy'")
+        self.plan = plan
+        self.size = (plan.size, plan.size)
+        self.score_thresh = score_thresh
+        self.nms_thresh = nms_thresh
+        self.detections_per_img = detections_per_img
+        self.topk_candidates = topk_candidates if postprocess == "ssd" else 0
+        self.postprocess_flavour = postprocess
+        self.image_mean = list(image_mean) if image_mean is not None else [0.485, 0.456, 0.406]
+        self.image_std = list(image_std) if image_std is not None else [0.229, 0.224, 0.225]
+        self._gemm_impl = gemm_impl
+        self._use_cuda_graph = use_cuda_graph
+        self._keep_activations = keep_activations      # debug: one arena buffer per tensor
+        self._engines: Dict[Tuple[str, int], _Engine] = {}
+        self._io: Dict[Tuple[str, int], dict] = {}
+        self._register_parameters(init)
+        self.eval()
+
+    # ---- parameters: same keys / shapes as the reference's state_dict ----------------------
+    def _register_parameters(self, init):
+        g = torch.Generator().manual_seed(0)
+        for key, shape, role in self.plan.param_specs:
+            parts = key.split(".")
+            mod = self
+            for name in parts[:-1]:
+                if name not in mod._modules:
+                    mod.add_module(name, nn.Module())
+                mod = mod._modules[name]
+            if role == "conv_w":
+                # _normal_init: N(0, 0.03) weights, zero biases (ssd_mobilenetv3.py:57-62)
+                t = torch.randn(shape, generator=g) * 0.03 if init == "normal" else torch.zeros(shape)
+                mod.register_parameter(parts[-1], nn.Parameter(t, requires_grad=False))
+            elif role == "conv_b":
+                mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape), requires_grad=False))
+            elif role == "bn_w":
+                mod.register_parameter(parts[-1], nn.Parameter(torch.ones(shape), requires_grad=False))
+            elif role == "bn_b":
+                mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape), requires_grad=False))
+            elif role == "bn_m":
+                mod.register_buffer(parts[-1], torch.zeros(shape))
+            elif role == "bn_v":
+                mod.register_buffer(parts[-1], torch.ones(shape))
+            else:
+                mod.register_buffer(parts[-1], torch.tensor(0, dtype=torch.long))
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError(
+                "demonet_b200 implements the inference hot path only (SSD.forward eval branch, "
+                "generalized_ssd.py:335-342); training / losses are out of scope")
+        return super().train(False)
+
+    # ---- engine management -----------------------------------------------------------------
+    def _weights_token(self):
+        return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
+
+    def _engine_for(self, device: torch.device, batch: int) -> _Engine:
+        key = str(device)
+        eng = self._engines.get(key)
+        if eng is None or eng.max_batch < batch:
+            if eng is not None:
+                eng.close()
+                self._io = {k: v for k, v in self._io.items() if k[0] != key}
+            kw = dict(image_mean=self.image_mean, image_std=self.image_std, score_thresh=self.score_thresh,
+                      nms_thresh=self.nms_thresh, topk_candidates=self.topk_candidates,
+                      detections_per_img=self.detections_per_img, gemm_impl=self._gemm_impl,
+                      use_cuda_graph=int(self._use_cuda_graph), keep_activations=self._keep_activations,
+                      min_box_size=1e-2 if self.postprocess_flavour == "legacy" else -1.0)
+            eng = _Engine(self.plan, kw, max(batch, 1), device)
+            self._engines[key] = eng
+        token = self._weights_token()
+        if eng._weights_token != token:
+            eng.load_weights(self.state_dict(), token)
+        return eng
+
+    def _io_buffers(self, device: torch.device, batch: int, host: bool):
+        key = (str(device) + ("/host" if host else ""), batch)
+        io = self._io.get(key)
+        if io is None:
+            D, S = self.detections_per_img, self.plan.size
+            kw = dict(device="cpu", pin_memory=True) if host else dict(device=device)
+            io = {"images": torch.empty(batch, 3, S, S, dtype=torch.float32, **kw),
+                  "boxes": torch.empty(batch, D, 4, dtype=torch.float32, **kw),
+                  "scores": torch.empty(batch, D, dtype=torch.float32, **kw),
+                  "labels": torch.empty(batch, D, dtype=torch.int64, **kw),
+                  "counts": torch.empty(batch, dtype=torch.int32, **kw)}
+            self._io[key] = io
+        return io
+
+    def reserve(self, batch: int, device=None):
+        """Pre-build the engine for `batch` images (otherwise done lazily on the first forward)."""
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return self._engine_for(device, batch)
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward(self, images: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
+        if self.training:
+            raise NotImplementedError("training mode is out of scope")
+        if isinstance(images, Tensor):
+            if images.dim() != 4:
+                raise ValueError("images is expected to be a list of 3d tensors of shape [C, H, W] "
+                                 "or a batched 4d tensor, got {}".format(images.shape))
+            images = list(images.unbind(0))
+        if len(images) == 0:
+            return []
+        original_sizes: List[Tuple[int, int]] = []
+        for img in images:
+            if img.dim() != 3:
+                raise ValueError("images is expected to be a list of 3d tensors "
+                                 "of shape [C, H, W], got {}".format(img.shape))       # transform.py:110-112
+            if not img.is_floating_point():
+                raise TypeError("Expected input images to be of floating type (in range [0, 1]), "
+                                f"but found type {img.dtype} instead")                # transform.py:130-134
+            original_sizes.append((int(img.shape[-2]), int(img.shape[-1])))
+        if not torch.cuda.is_available():
+            raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        B, S = len(images), self.plan.size
+        in_dev = images[0].device
+        host = in_dev.type != "cuda"
+        device = torch.device("cuda", torch.cuda.current_device()) if host else in_dev
+        eng = self._engine_for(device, B)
+        io = self._io_buffers(device, B, host)
+        batch = io["images"]
+        for i, img in enumerate(images):
+            if tuple(img.shape[-2:]) != (S, S):
+                # fixed-size bilinear resize, transform.py:27-53 (next-row f1: done with torch here)
+                img = torch.nn.functional.interpolate(img[None].float(), size=(S, S), mode="bilinear",
+                                                      align_corners=False)[0]
+            batch[i].copy_(img)
+        if host:
+            eng.forward_host(batch, io)
+            torch.cuda.current_stream(device).synchronize()
+        else:
+            eng.forward(batch, io)
+        counts = io["counts"].tolist()            # the one host sync: data-dependent output shapes
+        detections = []
+        for i in range(B):
+            n = counts[i]
+            boxes = io["boxes"][i, :n].clone()
+            oh, ow = original_sizes[i]
+            if (oh, ow) != (S, S):                # transform.postprocess / resize_boxes, transform.py:228-292
+                rh = torch.tensor(oh, dtype=torch.float32) / torch.tensor(S, dtype=torch.float32)
+                rw = torch.tensor(ow, dtype=torch.float32) / torch.tensor(S, dtype=torch.float32)
+                boxes = boxes * torch.stack([rw, rh, rw, rh]).to(boxes.device)
+            detections.append({"boxes": boxes, "scores": io["scores"][i, :n].clone(),
+                               "labels": io["labels"][i, :n].clone()})
+        return detections
+
+    def head_outputs(self, images: Tensor):
+        """(cls_logits [B,P,K], bbox_regression [B,P,4]) of a [B,3,S,S] CUDA batch -- parity hook."""
+        eng = self._engine_for(images.device, images.shape[0])
+        io = self._io_buffers(images.device, images.shape[0], False)
+        io["images"].copy_(images)
+        eng.forward(io["images"], io)
+        return eng.head_outputs(images.shape[0])

@@ -1,0 +1,198 @@
+/* demonet_b200 -- C ABI of the B200-native (sm_100a) SSDLite inference hot path.
+ *
+ * The reference (zhiqwang/demonet) has NO plugin / FFI layer ("There are no extra compiled
+ * components in DEMONET", README.md:18); its hot path runs entirely inside torch / torchvision
+ * operators.  This header is therefore the boundary a reference maintainer would bind with
+ * ctypes: each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no torch types; every data pointer is CALLER-OWNED DEVICE memory
+ *     unless the name ends in `_host`;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); no host
+ *     synchronisation, no allocation per call (workspaces are sized by a query and passed in);
+ *   - return value 0 = ok, negative = dn_status; dn_last_error() gives a thread-local message;
+ *   - activations are NHWC bf16 (row-major [B*H*W, C], C % 8 == 0), head outputs / scores / boxes fp32.
+ */
+#ifndef DEMONET_B200_H_
+#define DEMONET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DN_ABI_VERSION 1
+
+typedef enum {
+    DN_OK = 0,
+    DN_ERR_INVALID = -1,        /* bad argument (maps to ValueError on the Python side)           */
+    DN_ERR_CUDA = -2,           /* CUDA runtime / driver error (RuntimeError)                      */
+    DN_ERR_UNSUPPORTED = -3,    /* shape / option the engine cannot honour (NotImplementedError)   */
+    DN_ERR_WORKSPACE = -4       /* workspace too small                                             */
+} dn_status;
+
+typedef enum { DN_ACT_NONE = 0, DN_ACT_RELU = 1, DN_ACT_RELU6 = 2, DN_ACT_HSWISH = 3 } dn_act;
+
+const char* dn_last_error(void);
+int dn_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage-level entry points (also what the parity tests call)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Depthwise k x k convolution + folded BatchNorm + activation.
+ * Replaces ConvBNActivation with groups == channels: demonet/models/mobilenetv2.py:32-55 as used at
+ * mobilenetv3.py:80-83, mobilenetv2.py:87, ssd_mobilenetv3.py:31-32,48-49, backbone.py:106, and the
+ * biased depthwise of SeperableConv2d, box_head.py:30.
+ * x: bf16 [B,H,W,C]; w: fp32 [k*k, C] (tap-major, BN folded); bias: fp32 [C]; y: bf16 [B,Ho,Wo,C],
+ * Ho = (H + 2*(k/2) - k)/stride + 1.  k in {3,5}, stride in {1,2}, C % 8 == 0. */
+int dn_dwconv(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
+              int stride, int act, void* stream);
+
+/* Pointwise (1x1) convolution as a GEMM on the tcgen05 tensor cores, with folded BatchNorm / bias,
+ * activation and the residual add fused in the epilogue.
+ * Replaces the 1x1 ConvBNActivation / Conv2d(+BN) / Conv2d(bias): mobilenetv3.py:75-77,88-89,149-152,
+ * mobilenetv2.py:84,89-90,166, ssd_mobilenetv3.py:35,44-45,52-53, box_head.py:33,55-56, and the
+ * `result += input` of InvertedResidual.forward (mobilenetv3.py:95-99, mobilenetv2.py:96-100).
+ * x: bf16 [M,K] (M = B*H*W); w: bf16 [N,K]; bias: fp32 [N]; residual: bf16 [M,N] or NULL.
+ * Output element (m,n) is written at  y + (m / hw) * out_batch_stride + (m % hw) * out_row_stride + n
+ * (element units), as bf16 or, when out_fp32 != 0, fp32 -- this is how the head's
+ * view/permute/reshape/cat (generalized_ssd.py:66-74, box_head.py:107-146) becomes a no-op.
+ * K % 8 == 0.  impl: 0 = tcgen05/TMA kernel (product path), 1 = SIMT self-check kernel. */
+int dn_pwconv(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
+              int N, int act, int out_fp32, int hw, int64_t out_batch_stride, int64_t out_row_stride,
+              int impl, void* stream);
+
+/* Stem: input normalisation + dense 3x3 stride-2 convolution + folded BN + activation.
+ * Replaces GeneralizedRCNNTransform.normalize (transform.py:129-138) followed by the first
+ * ConvBNActivation (mobilenetv3.py:141-142, mobilenetv2.py:157).
+ * images: fp32 NCHW [B,3,H,W] in [0,1]; w: fp32 [27, Cout] ((ci*3+kh)*3+kw major); y: bf16 NHWC. */
+int dn_stem_conv(const float* images, const float* w, const float* bias, const float* mean3_host,
+                 const float* std3_host, void* y, int B, int H, int W, int Cout, int act, void* stream);
+
+/* Squeeze-Excitation applied in place: x *= hardsigmoid(fc2(relu(fc1(avgpool(x))))).
+ * Replaces SqueezeExcitation.forward, mobilenetv3.py:22-40.
+ * x: bf16 [B,HW,C] (in/out); w1: fp32 [Cs,C] (fc1); b1: fp32 [Cs]; w2t: fp32 [Cs,C] (fc2 weight
+ * TRANSPOSED); b2: fp32 [C]. */
+int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
+                  int C, int Cs, void* stream);
+
+typedef struct {
+    int32_t num_priors;          /* P                                                          */
+    int32_t num_classes;         /* K, including background column 0                           */
+    int32_t image_h, image_w;    /* clip window (clip_boxes_to_image)                          */
+    float score_thresh;          /* compared in fp32: score > thresh                           */
+    double nms_thresh;           /* compared in double: (double)iou > thresh                   */
+    int32_t topk_candidates;     /* per-class top-k before NMS; <= 0 means "no top-k" (legacy) */
+    int32_t detections_per_img;  /* D                                                          */
+    float min_box_size;          /* legacy remove_small_boxes(min_size); < 0 disables          */
+    float box_weights[4];        /* BoxCoder weights (10,10,5,5)                               */
+    float bbox_xform_clip;       /* log(1000/16)                                               */
+} dn_postprocess_params;
+
+/* Fused softmax + box decode + clip + score threshold + per-class top-k + per-class NMS + top-D.
+ * Replaces SSD.postprocess_detections (generalized_ssd.py:351-397) and, with topk_candidates <= 0
+ * and min_box_size = 1e-2, the legacy PostProcess.forward (box_head.py:323-381).
+ * cls_logits fp32 [B,P,K]; bbox_regression fp32 [B,P,4]; anchors fp32 [P,4] xyxy pixels.
+ * Outputs (fixed shape, padded): boxes fp32 [B,D,4], scores fp32 [B,D], labels int64 [B,D],
+ * counts int32 [B]; rows >= counts[b] are zero.  Detections are in descending score order, ties
+ * broken by (class, rank within class). */
+size_t dn_postprocess_workspace_bytes(int B, const dn_postprocess_params* p);
+int dn_postprocess(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                   const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                   float* out_scores, int64_t* out_labels, int32_t* out_counts, void* stream);
+
+/* measurement aid: same as dn_postprocess, each of its 3 kernels launched `iters` times between CUDA
+ * events; ms3_host[0..3) = mean ms of softmax+decode, per-class top-k+NMS, top-D merge.  Synchronises. */
+int dn_postprocess_profile(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                           const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                           float* out_scores, int64_t* out_labels, int32_t* out_counts, int iters, float* ms3_host,
+                           void* stream);
+
+/* torchvision.ops.batched_nms with per-class ("vanilla") semantics, bit-exact against the CPU
+ * kernel (the call at generalized_ssd.py:389 / box_head.py:374): boxes fp32 [n,4], scores fp32 [n],
+ * idxs int64 [n] with 0 <= idx < 4096 and fewer than 4096 KEPT boxes per class (nkeep_out = -1 / -2
+ * otherwise).  keep_out int64 [n] receives
+ * the kept indices in descending score order (ties: lower index first), nkeep_out int64 [1]. */
+size_t dn_batched_nms_workspace_bytes(int64_t n);
+int dn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, double iou_threshold,
+                   void* workspace, size_t workspace_bytes, int64_t* keep_out, int64_t* nkeep_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: the whole forward (SSD.forward eval branch, generalized_ssd.py:271-349) as one
+ * pre-planned launch sequence replayed from a CUDA graph.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+    DN_OP_STEM = 0,      /* normalise + dense 3x3 s2 conv                      */
+    DN_OP_DW = 1,        /* depthwise conv                                      */
+    DN_OP_PW = 2,        /* pointwise GEMM                                      */
+    DN_OP_SE = 3         /* squeeze-excitation, in place on in_buf              */
+} dn_op_kind;
+
+#define DN_BUF_NONE (-1)
+#define DN_BUF_IMAGES (-2)      /* the caller's fp32 NCHW images          */
+
+typedef struct {
+    int32_t kind, act;
+    int32_t in_buf, out_buf, res_buf;     /* arena buffer ids                              */
+    int32_t h_in, w_in, c_in;
+    int32_t h_out, w_out, c_out;
+    int32_t ksize, stride;
+    int32_t c_mid;                         /* SE squeeze width                              */
+    int32_t out_fp32;
+    int32_t reserved;
+    int64_t w_off, b_off, w2_off, b2_off;  /* byte offsets into the weight blob             */
+    int64_t out_batch_stride, out_row_stride, out_offset;   /* PW output addressing (elements) */
+} dn_op;
+
+typedef struct {
+    int64_t elems_per_image;
+    int32_t elem_bytes;                    /* 2 = bf16, 4 = fp32 */
+    int32_t reserved;
+} dn_buf;
+
+typedef struct {
+    int32_t image_h, image_w;
+    float image_mean[3], image_std[3];
+    int32_t n_ops, n_bufs;
+    const dn_op* ops_host;
+    const dn_buf* bufs_host;
+    int32_t logits_buf, bbox_buf;          /* arena ids of fp32 [P,K] and [P,4] per image    */
+    const float* anchors_host;             /* fp32 [P,4]                                      */
+    dn_postprocess_params post;
+    int32_t gemm_impl;                     /* 0 = tcgen05 (product), 1 = SIMT self-check      */
+    int32_t use_cuda_graph;
+} dn_model_desc;
+
+typedef struct dn_engine dn_engine;
+
+int dn_engine_create(dn_engine** out, const dn_model_desc* desc, int max_batch);
+int dn_engine_destroy(dn_engine* e);
+/* (re)upload the packed weight blob (BN already folded, layouts as documented in DESIGN.md) */
+int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes);
+/* images_dev: fp32 [B,3,H,W]; outputs as in dn_postprocess */
+int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
+                      int64_t* out_labels, int32_t* out_counts, void* stream);
+/* same, taking PINNED HOST buffers: H2D copy, forward, D2H copy, all enqueued on `stream` */
+int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
+                           float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
+                           void* stream);
+/* device pointers of intermediate arena buffers (valid after a forward), for stage-by-stage parity */
+int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out);
+/* enqueue a device-to-device copy of the first `bytes` bytes of an arena buffer into dst_dev */
+int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, size_t bytes, void* stream);
+/* Per-launch device time: runs one eager forward, then re-launches every step of the plan `iters`
+ * times bracketed by CUDA events on `stream` and writes the mean milliseconds of each into
+ * ms_out_host[0 .. n_ops + 3) (the n_ops layers in plan order, then the 3 post-processing kernels).
+ * Synchronises the stream; a measurement aid for bench.py, not part of the hot path. */
+int dn_engine_profile(dn_engine* e, const float* images_dev, int B, int iters, float* ms_out_host, void* stream);
+/* number of kernel launches one forward enqueues (for bench.py's gpu_launches) */
+int dn_engine_launches_per_forward(dn_engine* e);
+size_t dn_engine_device_bytes(dn_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMONET_B200_H_ */

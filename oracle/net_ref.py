@@ -18,6 +18,10 @@ Modes
          BatchNorm folded into the conv in float64 then rounded to fp32, pointwise-GEMM
          weights rounded to bf16, every stored activation rounded to bf16, fp32 accumulate,
          head 1x1 outputs / softmax / decode kept in fp32.
+  w16  : like bf16 but WITHOUT rounding the activations (folded BN + bf16 GEMM weights only).  The
+         bf16 chain is chaotic on a random-weight network (a different summation order alone moves
+         the logits by rms 0.14, see DESIGN.md "Numerics"), so plan-wiring tests compare in this
+         mode, where only fp32 summation-order noise remains.
 """
 from collections import OrderedDict
 
@@ -51,6 +55,10 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def _ident(x):
+    return x
+
+
 def _act(x, act):
     if act == "RE":
         return F.relu(x)
@@ -63,23 +71,27 @@ def _act(x, act):
     raise ValueError(act)
 
 
-def fold_bn(w, gamma, beta, mean, var, eps):
-    """W' = W*g/sqrt(v+eps), b' = beta - mean*g/sqrt(v+eps); float64 math, fp32 result."""
+def fold_bn(w, gamma, beta, mean, var, eps, conv_bias=None):
+    """W' = W*s, b' = beta - mean*s (+ conv_bias*s), s = g/sqrt(v+eps); float64 math, one rounding to fp32."""
     s = gamma.double() / torch.sqrt(var.double() + eps)
     wf = (w.double() * s.view(-1, 1, 1, 1)).float()
-    bf = (beta.double() - mean.double() * s).float()
-    return wf, bf
+    bf = beta.double() - mean.double() * s
+    if conv_bias is not None:
+        bf = bf + conv_bias.double() * s
+    return wf, bf.float()
 
 
 class _Net:
     def __init__(self, sd, mode, eps):
-        assert mode in ("fp32", "bf16")
+        assert mode in ("fp32", "bf16", "w16")
         self.sd = sd
         self.mode = mode
         self.eps = eps
+        self.rnd = _bf16 if mode == "bf16" else _ident          # rounding of stored activations
 
     # ConvBNActivation: conv (no bias) -> BN -> act      mobilenetv2.py:32-55
-    def cba(self, x, prefix, stride, act, depthwise=False, conv_key=".0", bn_key=".1", conv_bias=False):
+    def cba(self, x, prefix, stride, act, depthwise=False, conv_key=".0", bn_key=".1", conv_bias=False,
+            residual=None):
         sd = self.sd
         w = sd[prefix + conv_key + ".weight"]
         k = w.shape[-1]
@@ -90,21 +102,20 @@ class _Net:
         m, v = sd[prefix + bn_key + ".running_mean"], sd[prefix + bn_key + ".running_var"]
         if self.mode == "fp32":
             y = F.conv2d(x, w, cb, stride, pad, 1, groups)
-            y = F.batch_norm(y, m, v, g, b, False, 0.0, self.eps)
-            return _act(y, act)
-        wf, bf = fold_bn(w, g, b, m, v, self.eps)
-        if cb is not None:      # conv bias passes through BN scale:  b' += cb * s
-            s = (g.double() / torch.sqrt(v.double() + self.eps))
-            bf = (bf.double() + cb.double() * s).float()
+            y = _act(F.batch_norm(y, m, v, g, b, False, 0.0, self.eps), act)
+            return y if residual is None else y + residual          # mobilenetv3.py:95-99
+        wf, bf = fold_bn(w, g, b, m, v, self.eps, cb)
         if k == 1 and not depthwise:
             wf = _bf16(wf)
-        y = F.conv2d(x, wf, bf, stride, pad, 1, groups)
-        return _bf16(_act(y, act))
+        y = _act(F.conv2d(x, wf, bf, stride, pad, 1, groups), act)
+        if residual is not None:        # the engine adds the residual in the GEMM epilogue: one rounding
+            y = y + residual
+        return self.rnd(y)
 
     # plain conv with bias, no BN (head 1x1): fp32 output in both modes
     def conv_bias(self, x, prefix):
         w, b = self.sd[prefix + ".weight"], self.sd[prefix + ".bias"]
-        if self.mode == "bf16":
+        if self.mode != "fp32":
             w = _bf16(w)
         return F.conv2d(x, w, b)
 
@@ -114,8 +125,7 @@ class _Net:
         s = F.adaptive_avg_pool2d(x, 1)
         s = F.relu(F.conv2d(s, sd[prefix + ".fc1.weight"], sd[prefix + ".fc1.bias"]))
         s = F.hardsigmoid(F.conv2d(s, sd[prefix + ".fc2.weight"], sd[prefix + ".fc2.bias"]))
-        y = s * x
-        return _bf16(y) if self.mode == "bf16" else y
+        return self.rnd(s * x)
 
 
 def _score_layout(results, num_columns):
@@ -169,11 +179,8 @@ def v3_forward_raw(sd, images, mode="fp32", num_classes=91, image_mean=(0.5, 0.5
             if use_se:
                 x = net.se(x, bp + str(j))
                 j += 1
-            x = net.cba(x, bp + str(j), 1, "ID")
-            if stride == 1 and cin == cout:                    # mobilenetv3.py:69,95-99
-                x = x + inp
-                if mode == "bf16":
-                    x = _bf16(x)
+            x = net.cba(x, bp + str(j), 1, "ID",               # mobilenetv3.py:69,95-99
+                        residual=inp if (stride == 1 and cin == cout) else None)
         cin = cout
     x = net.cba(x, "backbone.features.1.3", 1, "HS")           # last 1x1, mobilenetv3.py:149-152
     feats.append(x)
@@ -213,12 +220,8 @@ def _v2_ir(net, x, prefix, inp, oup, stride, hidden, expand):
     y = net.cba(y, prefix + ".conv.%d" % j, stride, "R6", depthwise=True)
     j += 1
     # pw-linear: Conv2d + BN as siblings conv.j / conv.j+1
-    y = net.cba(y, prefix + ".conv", 1, "ID", conv_key=".%d" % j, bn_key=".%d" % (j + 1))
-    if stride == 1 and inp == oup:
-        y = x + y
-        if net.mode == "bf16":
-            y = _bf16(y)
-    return y
+    return net.cba(y, prefix + ".conv", 1, "ID", conv_key=".%d" % j, bn_key=".%d" % (j + 1),
+                   residual=x if (stride == 1 and inp == oup) else None)
 
 
 def v2_forward_raw(sd, images, mode="fp32", num_classes=21, image_mean=(0.485, 0.456, 0.406),

@@ -1,0 +1,125 @@
+"""Host-side logic on the CPU: state_dict contract, plans, weight packing, buffer assignment, and
+the C ABI surface (symbols only -- no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import demonet_b200
+from demonet_b200 import _C, plan as dplan
+from oracle import boxes_np, net_ref, weights
+from tests.plan_interp import run_plan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_v3_state_dict_contract(golden_dir):
+    g = np.load(os.path.join(golden_dir, "v3_ssdlite.npz"))
+    model = demonet_b200.ssdlite320_mobilenet_v3_large()
+    sd = model.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["state_dict_keys"]]          # 476 keys, reference order
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in g["state_dict_shapes"]]
+    assert sum(p.numel() for p in model.parameters()) == 3440060
+    # reference defaults, ssd_mobilenetv3.py:207-217
+    assert (model.score_thresh, model.nms_thresh, model.detections_per_img, model.topk_candidates) == (0.001, 0.55, 300, 300)
+    assert model.image_mean == [0.5] * 3 and model.image_std == [0.5] * 3
+
+
+def test_v2_state_dict_contract(golden_dir):
+    g = np.load(os.path.join(golden_dir, "v2_ssdlite.npz"))
+    model = demonet_b200.ssd_lite_mobilenet_v2()
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(str(k) for k in g["state_dict_keys"])
+    ref_shapes = dict(zip((str(k) for k in g["state_dict_keys"]), (str(s) for s in g["state_dict_shapes"])))
+    assert all(str(tuple(v.shape)) == ref_shapes[k] for k, v in sd.items())
+    assert (model.score_thresh, model.nms_thresh, model.detections_per_img) == (0.5, 0.45, 100)   # test_model.py:42-48
+
+
+def test_builder_argument_errors():
+    with pytest.raises(NotImplementedError):
+        demonet_b200.ssdlite320_mobilenet_v3_large(norm_layer=torch.nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        demonet_b200.ssdlite320_mobilenet_v3_large(width_mult=0.5)
+    with pytest.raises(TypeError):
+        demonet_b200.ssdlite320_mobilenet_v3_large(bogus=1)
+    m = demonet_b200.ssdlite320_mobilenet_v3_large(topk_candidates=400, score_thresh=0.01)      # kwargs quirk, SURVEY 8(b)
+    assert m.topk_candidates == 400 and m.score_thresh == 0.01
+    with pytest.raises(NotImplementedError):
+        m.train()
+    with pytest.raises(ValueError):
+        m([torch.rand(320, 320)])                 # transform.py:110-112
+    with pytest.raises(TypeError):
+        m([torch.zeros(3, 320, 320, dtype=torch.uint8)])          # transform.py:130-134
+
+
+def test_plan_shapes():
+    p = dplan.plan_ssdlite320_mobilenet_v3_large()
+    assert p.grid_sizes == [(20, 20), (10, 10), (5, 5), (3, 3), (2, 2), (1, 1)] and p.num_priors == 3234
+    kinds = [L.kind for L in p.layers]
+    assert kinds.count("dw") == 31 and kinds.count("pw") == 50 and kinds.count("se") == 8 and kinds.count("stem") == 1
+    assert sum(1 for L in p.layers if L.kind == "dw" and L.k == 5) == 6
+    for S, P in ((300, 3000), (320, 3234), (512, 8190)):
+        assert dplan.plan_ssd_lite_mobilenet_v2(21, S).num_priors == P
+    a = dplan.default_boxes(p)
+    assert np.array_equal(a, boxes_np.default_boxes(p.grid_sizes, (320, 320)))
+
+
+def _interp(plan, sd, x, mean, std, round_activations):
+    blob, offs = dplan.pack_weights(plan, sd)
+    t2b, bufs, lb, bb = dplan.assign_buffers(plan)
+    ops = dplan.build_ops(plan, offs, t2b, lb, bb)
+    return run_plan(plan, blob, ops, bufs, lb, bb, x, mean, std, round_activations)
+
+
+def _check_plan(model, sd, x, mean, std, forward_raw):
+    """dn_op array + packed blob + arena reuse, interpreted on the CPU, against the oracle.
+    Tight in `w16` mode (no activation rounding -> only fp32 summation noise); statistical in `bf16`
+    mode, where rounding flips make the chain chaotic (the oracle itself moves by rms 0.14 on the
+    logits when only its summation order changes)."""
+    with torch.no_grad():
+        cls, reg = _interp(model.plan, sd, x, mean, std, False)
+        ocls, oreg, _ = forward_raw(sd, x, "w16")
+        assert not torch.isnan(cls).any() and not torch.isnan(reg).any()
+        assert (cls - ocls).abs().max() < 2e-3 and (reg - oreg).abs().max() < 2e-3
+        cls, reg = _interp(model.plan, sd, x, mean, std, True)
+        ocls, oreg, _ = forward_raw(sd, x, "bf16")
+        assert (cls - ocls).pow(2).mean().sqrt() < 0.3 and (reg - oreg).pow(2).mean().sqrt() < 0.3
+        assert ocls.std() > 3.0
+
+
+def test_v3_plan_reproduces_oracle():
+    model = demonet_b200.ssdlite320_mobilenet_v3_large()
+    sd = weights.seeded_state_dict(model.state_dict())
+    _check_plan(model, sd, weights.synthetic_images(1, 320), [0.5] * 3, [0.5] * 3, net_ref.v3_forward_raw)
+
+
+@pytest.mark.parametrize("S", [300, 512])
+def test_v2_plan_reproduces_oracle(S):
+    model = demonet_b200.ssd_lite_mobilenet_v2(image_size=S)
+    sd = weights.seeded_state_dict(model.state_dict())
+    _check_plan(model, sd, weights.synthetic_images(1, S), [0.485, 0.456, 0.406], [0.229, 0.224, 0.225],
+                net_ref.v2_forward_raw)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads on a CPU-only box and exports everything include/*.h declares."""
+    header = open(os.path.join(ROOT, "include", "demonet_b200.h")).read()
+    declared = set(re.findall(r"\b(dn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    handle = ctypes.CDLL(_C.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), "missing export: " + name
+    assert declared == set(_C.EXPORTED_SYMBOLS)
+    assert _C.lib().dn_abi_version() == 1
+
+
+def test_c_abi_argument_validation_without_gpu():
+    lib = _C.lib()
+    assert lib.dn_dwconv(None, None, None, None, 1, 8, 8, 8, 3, 1, 0, None) == _C.DN_ERR_INVALID
+    assert b"NULL" in lib.dn_last_error()
+    assert lib.dn_batched_nms_workspace_bytes(36000) > 36000 * 8
+    with pytest.raises(RuntimeError):
+        demonet_b200.ops.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)       # CPU tensors: no fallback

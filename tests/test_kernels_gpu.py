@@ -1,0 +1,131 @@
+"""Each CUDA kernel against a plain PyTorch fp32 reference of the same op on the same bf16 inputs
+(C-ABI stage entry points, shapes from SURVEY.md Appendix C).  Tolerance: the output is bf16, so the
+bar is 1 bf16 ulp of the reference value (2^-8 relative) plus fp32 summation noise."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from demonet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+ACTS = {"none": lambda v: v, "relu": F.relu, "relu6": F.relu6, "hardswish": F.hardswish}
+
+
+def _close_bf16(got, want, extra_abs=1e-3):
+    got, want = got.float(), want.float()
+    tol = want.abs() * (2.0 ** -7) + extra_abs
+    bad = (got - want).abs() > tol
+    assert not bool(bad.any()), "max err %g at %d elements" % (float((got - want).abs().max()), int(bad.sum()))
+
+
+# (C, k, stride, H) from Appendix C.1 / C.3 plus ragged sizes
+DW_CASES = [(16, 3, 1, 160), (64, 3, 2, 160), (72, 5, 2, 80), (120, 5, 1, 40), (240, 3, 2, 40), (672, 3, 1, 20),
+            (672, 5, 2, 20), (480, 5, 1, 10), (256, 3, 2, 10), (128, 3, 2, 5), (128, 3, 2, 3), (64, 3, 2, 2),
+            (128, 3, 1, 1), (96, 3, 1, 19), (144, 3, 2, 75), (32, 3, 1, 150), (1280, 3, 1, 16), (8, 5, 2, 7)]
+
+
+@pytest.mark.parametrize("C,k,s,H", DW_CASES)
+@pytest.mark.parametrize("act", ["relu6", "hardswish"])
+def test_dwconv(C, k, s, H, act):
+    g = torch.Generator().manual_seed(C * 100 + k * 10 + s + H)
+    B = 3
+    x = (torch.randn(B, H, H, C, generator=g) * 2).bfloat16().cuda()
+    w = (torch.randn(k * k, C, generator=g) / k).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = ops.dwconv(x, w, b, k, s, act)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, k, k), b, s, (k - 1) // 2, 1, C)
+    ref = ACTS[act](ref).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    _close_bf16(y, ref)
+
+
+# (M, K, N): Appendix C GEMM shapes (per-image M times a small batch), incl. N not multiple of 16 / > 256
+PW_CASES = [(25600, 16, 16), (25600, 16, 64), (6400, 64, 24), (6400, 24, 72), (1600, 72, 40), (1600, 40, 240),
+            (400, 80, 184), (400, 200, 80), (400, 112, 672), (400, 672, 112), (400, 672, 546), (400, 672, 24),
+            (100, 480, 546), (100, 480, 256), (25, 512, 546), (9, 256, 128), (4, 256, 64), (1, 128, 546),
+            (1024, 96, 576), (256, 320, 1280), (256, 1280, 126), (1, 64, 24), (130, 8, 8), (257, 200, 1000)]
+
+
+@pytest.mark.parametrize("M,K,N", PW_CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_pwconv(M, K, N, impl):
+    g = torch.Generator().manual_seed(M + K * 7 + N * 13)
+    batch = 3 if M < 30000 else 1
+    Mt = M * batch
+    x = torch.randn(Mt, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = x.float() @ w.float().t() + b
+    for act, res, fp32 in (("none", False, False), ("hardswish", False, False), ("none", True, False), ("none", False, True),
+                           ("relu6", False, False)):
+        r = torch.randn(Mt, N, generator=g).bfloat16().cuda() if res else None
+        y = ops.pwconv(x, w, b, act, r, fp32, impl)
+        want = ACTS[act](ref) + (r.float() if res else 0)
+        if fp32:
+            assert y.dtype == torch.float32
+            assert float((y - want).abs().max()) < 2e-3
+        else:
+            _close_bf16(y, want)
+
+
+def test_pwconv_tc_equals_simt_large():
+    """tcgen05 kernel vs the independent SIMT kernel at a full config-2 layer size (B=256, cls head L0)."""
+    g = torch.Generator().manual_seed(0)
+    M, K, N = 256 * 400, 672, 546
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    b = torch.randn(N, generator=g).cuda()
+    y0 = ops.pwconv(x, w, b, "none", None, True, 0)
+    y1 = ops.pwconv(x, w, b, "none", None, True, 1)
+    assert float((y0 - y1).abs().max()) < 1e-3
+
+
+def test_pwconv_head_addressing():
+    """Strided fp32 output: row (b, hw) of a level lands at b*P*K + (off + hw*A)*K  (generalized_ssd.py:66-74)."""
+    from demonet_b200 import _C
+    g = torch.Generator().manual_seed(1)
+    B, HW, K, A, cols, P, off = 3, 25, 512, 6, 91, 3234, 3000
+    N = A * cols
+    x = torch.randn(B * HW, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    b = torch.randn(N, generator=g).cuda()
+    out = torch.zeros(B, P, cols, device="cuda")
+    base = out.data_ptr() + off * cols * 4
+    _C.check(_C.lib().dn_pwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, base, B * HW, K, N, 0, 1, HW, P * cols,
+                                N, 0, torch.cuda.current_stream().cuda_stream))
+    ref = (x.float() @ w.float().t() + b).view(B, HW * A, cols)
+    assert float((out[:, off:off + HW * A] - ref).abs().max()) < 2e-3
+    assert float(out[:, :off].abs().sum()) == 0 and float(out[:, off + HW * A:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("Cout,S,act", [(16, 320, "hardswish"), (32, 300, "relu6"), (32, 512, "relu6"), (16, 33, "hardswish")])
+def test_stem(Cout, S, act):
+    g = torch.Generator().manual_seed(S)
+    B = 2
+    img = torch.rand(B, 3, S, S, generator=g).cuda()
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) * 0.3).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    y = ops.stem_conv(img, w.permute(1, 2, 3, 0).reshape(27, Cout).contiguous(), b, mean, std, act)
+    m = torch.tensor(mean, device="cuda")[None, :, None, None]
+    s = torch.tensor(std, device="cuda")[None, :, None, None]
+    ref = ACTS[act](F.conv2d((img - m) / s, w, b, 2, 1)).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    _close_bf16(y, ref)
+
+
+@pytest.mark.parametrize("C,Cs,HW", [(72, 24, 1600), (120, 32, 1600), (480, 120, 400), (672, 168, 400), (672, 168, 100),
+                                     (480, 120, 100), (16, 8, 9)])
+def test_se(C, Cs, HW):
+    g = torch.Generator().manual_seed(C + HW)
+    B = 3
+    x = (torch.randn(B, HW, C, generator=g)).bfloat16().cuda()
+    w1 = (torch.randn(Cs, C, generator=g) / C ** 0.5).cuda()
+    b1 = torch.randn(Cs, generator=g).cuda() * 0.5
+    w2 = (torch.randn(C, Cs, generator=g) / Cs ** 0.5).cuda()
+    b2 = torch.randn(C, generator=g).cuda() * 0.5
+    xf = x.float()
+    scale = F.hardsigmoid(F.relu(xf.mean(1) @ w1.t() + b1) @ w2.t() + b2)
+    ref = xf * scale[:, None, :]
+    y = ops.se_inplace(x.clone(), w1, b1, w2.t().contiguous(), b2)
+    _close_bf16(y, ref, extra_abs=2e-3)
