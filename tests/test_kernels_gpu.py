@@ -47,8 +47,16 @@ PW_CASES = [(25600, 16, 16), (25600, 16, 64), (6400, 64, 24), (6400, 24, 72), (1
 
 
 @pytest.mark.parametrize("M,K,N", PW_CASES)
-@pytest.mark.parametrize("impl", [0, 1])
-def test_pwconv(M, K, N, impl):
+def test_pwconv_simt(M, K, N):
+    _check_pwconv(M, K, N, 1)
+
+
+@pytest.mark.parametrize("M,K,N", PW_CASES)
+def test_pwconv_tc(M, K, N):
+    _check_pwconv(M, K, N, 0)
+
+
+def _check_pwconv(M, K, N, impl):
     g = torch.Generator().manual_seed(M + K * 7 + N * 13)
     batch = 3 if M < 30000 else 1
     Mt = M * batch
