@@ -155,7 +155,7 @@ def layer_costs(plan, B):
             out.append(("pwconv_tc_kernel", B * hi * wi * (L.cin * 2 + L.cout * ob) + res + L.cin * L.cout * 2,
                         2 * B * hi * wi * L.cin * L.cout))
     out.append(("softmax_decode_kernel", B * (P * K * 4 + P * 16) + P * 16 + B * (P * (K - 1) * 4 + P * 16), 0))
-    out.append(("class_nms_kernel", B * (K - 1) * P * 4, 0))
+    out.append(("class_sort+select+nms kernels", B * (K - 1) * P * 4, 0))
     out.append(("merge_topd_kernel", B * plan_D(plan) * 28, 0))
     return out
 
@@ -256,7 +256,7 @@ def main():
 
     # per-launch device times, live, with CUDA events on the launching stream
     n_launch = eng.launches_per_forward
-    ms = (ctypes.c_float * n_launch)()
+    ms = (ctypes.c_float * (len(model.plan.layers) + 3))()
     with torch.cuda.device(dev):
         _C.check(lib.dn_engine_profile(eng._handle, imgs.data_ptr(), B, 10, ms, stream.cuda_stream))
     costs = layer_costs(model.plan, B)

@@ -2,16 +2,18 @@
 //
 //   D[M, N] = A[M, K] . W[N, K]^T     A = NHWC bf16 activations (K-major), W = bf16 weights (K-major)
 //
-// One CTA computes a 128 x BLOCK_N output tile (BLOCK_N is a runtime multiple of 16, <= 256):
+// Persistent CTAs (one to four per SM) walk 128 x BLOCK_N output tiles (BLOCK_N is a runtime multiple
+// of 16, <= 256); the smem ring and two TMEM accumulator buffers run continuously across tiles:
 //   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of the A and W k-blocks (64 bf16 = one
 //                              128-byte swizzle row) into a NUM_STAGES-deep shared-memory ring,
 //                              completion signalled on mbarriers (expect_tx)
 //   warp 1      MMA issuer   : allocates TMEM, one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //                              (UMMA 128 x BLOCK_N x 16, fp32 accumulator in TMEM), tcgen05.commit frees
 //                              the smem stage / publishes the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld the accumulator (thread = output row), add the folded-BN bias,
-//                              activation, residual add, convert, store with the head's strided
-//                              addressing (PwEpilogue)
+//   warps 2..5  epilogue     : tcgen05.ld the accumulator (thread = output row), add the folded-BN bias and
+//                              apply the activation, stage 32-column fp32 chunks through shared memory so
+//                              that the residual loads / output stores are row-contiguous (8 lanes per row),
+//                              add the residual, convert, store with the head's strided addressing
 // K and N tails are zero-filled by TMA (out-of-bounds box elements), M tails are masked in the epilogue.
 // Reference ops replaced: see dn_pwconv in include/demonet_b200.h.
 #include <cuda.h>
@@ -25,8 +27,11 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;      // 16 KiB
+constexpr int TC_STAGE_PITCH = 36;                                 // floats; 144-B rows keep 16-B smem accesses conflict-free
+constexpr int TC_STATIC_SMEM = 2 * 256 * 4 + TC_EPI_WARPS * 32 * TC_STAGE_PITCH * 4;      // bias staging + epilogue staging
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,18 +141,36 @@ __device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
 }
 
 struct __align__(8) TcBarriers {
-    uint64_t full[TC_MAX_STAGES];
-    uint64_t empty[TC_MAX_STAGES];
-    uint64_t tmem_full;
+    uint64_t full[TC_MAX_STAGES];        // TMA -> MMA: k-block landed in smem
+    uint64_t empty[TC_MAX_STAGES];       // MMA -> TMA: smem stage consumed
+    uint64_t tmem_full[2];               // MMA -> epilogue: accumulator buffer complete
+    uint64_t tmem_empty[2];              // epilogue -> MMA: accumulator buffer drained
     uint32_t tmem_base;
     uint32_t pad;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring and
+// the two TMEM accumulator buffers run continuously across tiles, so the TMA loads / MMAs of tile i+1
+// overlap the epilogue of tile i.
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+    if (ACT == DN_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == DN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    if (ACT == DN_ACT_HSWISH) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return v;
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS)
 pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, PwEpilogue ep,
-                 int M, int K, int N, int block_n, int n_tiles, int num_stages, int tmem_cols) {
+                 int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ float s_bias[256];
+    __shared__ float s_bias[2][256];
+    __shared__ __align__(16) float s_stage[TC_EPI_WARPS][32 * TC_STAGE_PITCH];      // per epilogue warp: 32 rows x 32 fp32 (+pad)
     // carve: [stages x A tile][stages x W tile][barriers]; tiles must be 1024-B aligned for SWIZZLE_128B
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = block_n * TC_BLOCK_K * 2;
@@ -156,8 +179,6 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_w + num_stages * w_stage_bytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x % n_tiles, m_tile = blockIdx.x / n_tiles;
-    const int m0 = m_tile * TC_BLOCK_M, n0 = n_tile * block_n;
     const int num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
 
     if (warp == 0 && lane == 0) {
@@ -167,118 +188,172 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
         }
-        mbar_init(&bars->tmem_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->tmem_full[b], 1);
+            mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS);          // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_d = bars->tmem_base;
+    const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
             const uint32_t stage_bytes = (uint32_t)(TC_A_STAGE_BYTES + w_stage_bytes);
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % num_stages;
-                const uint32_t round = (uint32_t)(kb / num_stages);
-                mbar_wait(&bars->empty[s], (round & 1u) ^ 1u);
-                mbar_expect_tx(&bars->full[s], stage_bytes);
-                tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
-                tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int s = it % num_stages;
+                    mbar_wait(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
+                    mbar_expect_tx(&bars->full[s], stage_bytes);
+                    tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
+                    tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(TC_BLOCK_M, block_n);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-            const int s = kb % num_stages;
-            const uint32_t round = (uint32_t)(kb / num_stages);
-            mbar_wait(&bars->full[s], round & 1u);
+        uint32_t it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            mbar_wait(&bars->tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
             tcgen05_fence_after();
-            if (elect_one()) {
-                const uint64_t da = make_smem_desc(smem_u32(smem_a + s * TC_A_STAGE_BYTES));
-                const uint64_t dw = make_smem_desc(smem_u32(smem_w + s * w_stage_bytes));
-#pragma unroll
-                for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-                    // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4) units
-                    umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n;
+            for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                const int s = it % num_stages;
+                mbar_wait(&bars->full[s], (it / num_stages) & 1u);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = make_smem_desc(smem_u32(smem_a + s * TC_A_STAGE_BYTES));
+                    const uint64_t dw = make_smem_desc(smem_u32(smem_w + s * w_stage_bytes));
+                    const int k_left = K - kb * TC_BLOCK_K;              // zero-filled K tail needs no MMA
+                    const int ksteps = k_left >= TC_BLOCK_K ? TC_BLOCK_K / TC_UMMA_K : (k_left + TC_UMMA_K - 1) / TC_UMMA_K;
+                    for (int k = 0; k < ksteps; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4) units
+                        umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&bars->empty[s]);                       // frees this smem stage when the MMAs retire
+                    if (kb == num_k_blocks - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete
                 }
-                umma_commit(&bars->empty[s]);                       // frees this smem stage when the MMAs retire
-                if (kb == num_k_blocks - 1) umma_commit(&bars->tmem_full);   // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column chunks interleaved between the
+        // two warps that share a quarter =====
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        const int m = m0 + row;
-        const int n_valid = min(block_n, N - n0);
-        for (int i = threadIdx.x - 64; i < block_n; i += 128) s_bias[i] = (i < n_valid) ? __ldg(ep.bias + n0 + i) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(&bars->tmem_full, 0);
-        tcgen05_fence_after();
-        const long long out_row = (m < M) ? ep.row_offset(m) : 0;
-        const __nv_bfloat16* res_row = ep.residual ? ep.residual + (long long)(m < M ? m : 0) * N : nullptr;
-        for (int c0 = 0; c0 < n_valid; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            tmem_ld_wait();
-            if (m < M) {
-                const int n = n0 + c0;
-                const int cnt = min(16, N - n);
-                float f[16];
+        const int et = threadIdx.x - 64;                                  // 0 .. 32*TC_EPI_WARPS-1
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+            const int m = m0 + row;
+            const int n_valid = min(block_n, N - n0);
+            float* sb = s_bias[buf];
+            for (int i = et; i < block_n; i += 32 * TC_EPI_WARPS) sb[i] = (i < n_valid) ? __ldg(ep.bias + n0 + i) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16);
+            const long long out_row = (m < M) ? ep.row_offset(m) : 0;     // this lane's own row; shared by shuffle below
+            float* stg = s_stage[warp - 2];
+            for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
+                uint32_t v[32];
+                const bool second = (c0 + 16 < block_n);                  // warp-uniform
+                tmem_ld16(tmem_d + (uint32_t)c0, v);
+                if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
+                tmem_ld_wait();
+                // residual tile of this chunk: issue all loads now, they complete behind the TMEM read / staging
+                const int cg = (lane & 7) * 4;
+                const int n = n0 + c0 + cg;
+                const int cnt = n0 + n_valid - n;                          // columns of THIS tile left in the row (>= 4: full vector)
+                const bool res_vec = ep.residual && cnt >= 4 && (N % 4 == 0);
+                uint2 rres[8];
+                if (res_vec) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = apply_act(__uint_as_float(v[i]) + s_bias[c0 + i], ep.act);
-                if (res_row) {
-                    const __nv_bfloat16* rp = res_row + n;
-                    if (cnt == 16 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                        float r[16];
-                        unpack8(__ldg(reinterpret_cast<const uint4*>(rp)), r);
-                        unpack8(__ldg(reinterpret_cast<const uint4*>(rp) + 1), r + 8);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] += r[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < cnt) f[i] += __bfloat162float(rp[i]);
+                    for (int it = 0; it < 8; ++it) {
+                        const int mr = m0 + quarter * 32 + it * 4 + (lane >> 3);
+                        rres[it] = (mr < M) ? __ldg(reinterpret_cast<const uint2*>(ep.residual + (long long)mr * N + n))
+                                            : make_uint2(0u, 0u);
                     }
                 }
-                if (ep.out_fp32) {
-                    float* dst = reinterpret_cast<float*>(ep.y) + out_row + n;
-                    if (cnt == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                // (1) thread = row: bias + activation in fp32, staged to shared memory (pitch 36 floats)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    } else if (cnt == 16 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = act_fn<ACT>(__uint_as_float(v[j + 0]) + sb[c0 + j + 0]);
+                    o.y = act_fn<ACT>(__uint_as_float(v[j + 1]) + sb[c0 + j + 1]);
+                    o.z = act_fn<ACT>(__uint_as_float(v[j + 2]) + sb[c0 + j + 2]);
+                    o.w = act_fn<ACT>(__uint_as_float(v[j + 3]) + sb[c0 + j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * TC_STAGE_PITCH + j) = o;
+                }
+                __syncwarp();
+                // (2) 8 lanes per row, 4 rows per instruction: coalesced output stores
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) reinterpret_cast<float2*>(dst)[i] = make_float2(f[2 * i], f[2 * i + 1]);
-                    } else {
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3);
+                    const long long orow = __shfl_sync(0xffffffffu, out_row, r);
+                    const int mr = m0 + quarter * 32 + r;
+                    if (mr < M && cnt > 0) {
+                        float4 o = *reinterpret_cast<const float4*>(stg + r * TC_STAGE_PITCH + cg);
+                        float f[4] = {o.x, o.y, o.z, o.w};
+                        if (res_vec) {
+                            const float2 r0 = bf16x2_to_float2(rres[it].x), r1 = bf16x2_to_float2(rres[it].y);
+                            f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                        } else if (ep.residual) {
+                            const __nv_bfloat16* rp = ep.residual + (long long)mr * N + n;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < cnt) dst[i] = f[i];
-                    }
-                } else {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.y) + out_row + n;
-                    if (cnt == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                        reinterpret_cast<uint4*>(dst)[0] = pack8(f);
-                        reinterpret_cast<uint4*>(dst)[1] = pack8(f + 8);
-                    } else {
+                            for (int i = 0; i < 4; ++i)
+                                if (i < cnt) f[i] += __bfloat162float(rp[i]);
+                        }
+                        if (ep.out_fp32) {
+                            float* dst = reinterpret_cast<float*>(ep.y) + orow + n;
+                            if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                                *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+                            } else if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                                reinterpret_cast<float2*>(dst)[0] = make_float2(f[0], f[1]);
+                                reinterpret_cast<float2*>(dst)[1] = make_float2(f[2], f[3]);
+                            } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < cnt) dst[i] = __float2bfloat16_rn(f[i]);
+                                for (int i = 0; i < 4; ++i)
+                                    if (i < cnt) dst[i] = f[i];
+                            }
+                        } else {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.y) + orow + n;
+                            if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                                uint2 pk;
+                                pk.x = float2_to_bf16x2(f[0], f[1]);
+                                pk.y = float2_to_bf16x2(f[2], f[3]);
+                                *reinterpret_cast<uint2*>(dst) = pk;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (i < cnt) dst[i] = __float2bfloat16_rn(f[i]);
+                            }
+                        }
                     }
                 }
+                __syncwarp();
             }
+            // all tcgen05.ld of this warp have completed (wait::ld above): hand the buffer back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
         }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }
 }
 
@@ -317,19 +392,27 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
     return DN_OK;
 }
 
+// Largest dynamic shared-memory request that still lets n CTAs co-reside on an SM (228 KiB per SM;
+// every CTA costs its dynamic request + the static staging buffers + 1 KiB reserved).
+static size_t smem_cap(int n) {
+    return n == 1 ? (size_t)(227 * 1024 - TC_STATIC_SMEM - 256) : (size_t)(228 * 1024) / n - TC_STATIC_SMEM - 1024 - 256;
+}
+
 void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
     const int nt = (N + 255) / 256;
     int bn = (N + nt - 1) / nt;
     bn = (bn + 15) & ~15;
-    const int kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
-    const int st = kb < TC_MAX_STAGES ? kb : TC_MAX_STAGES;
     int cols = 32;
-    while (cols < bn) cols <<= 1;
+    while (cols < 2 * bn) cols <<= 1;                  // two accumulator buffers
     *block_n = bn;
     *n_tiles = nt;
+    const int kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    int st = kb >= 3 ? TC_MAX_STAGES : kb + 1;            // short-K layers: fewer stages -> more CTAs per SM
+    auto need = [&](int stg) { return 1024 + (size_t)stg * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2) + sizeof(TcBarriers); };
+    while (st > 2 && need(st) > smem_cap(1)) --st;
     *stages = st;
     *tmem_cols = cols;
-    *smem_bytes = 1024 + (size_t)st * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2) + sizeof(TcBarriers);
+    *smem_bytes = need(st);
 }
 
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilogue& ep, int M, int K, int N,
@@ -337,14 +420,45 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilo
     int bn, nt, st, cols;
     size_t smem;
     pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        configured = 200 * 1024;
+    // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  An SM has 228 KiB
+    // of shared memory; every CTA costs its dynamic request + ~20 KiB static (bias / epilogue staging) + 1 KiB reserved.
+    // The dynamic request is padded up to the largest size that still lets `per_sm` CTAs co-reside, so
+    // that the hardware cannot place one more (a CTA that cannot get its TMEM columns would spin until
+    // a neighbour exits).
+    auto cap = [](int n) -> size_t { return smem_cap(n); };
+    static bool configured = false;
+    if (!configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
+        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
+        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_RELU6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
+        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_HSWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
+        configured = true;
     }
+    int per_sm = 1;
+    for (int n = 4; n >= 1; --n)
+        if (smem <= cap(n) && n * cols <= 512) {
+            per_sm = n;
+            break;
+        }
+    DN_REQUIRE(smem <= cap(1), DN_ERR_UNSUPPORTED, "GEMM tile does not fit in shared memory");
+    const size_t smem_req = cap(per_sm);
     const long long tiles = (long long)ceil_div(M, TC_BLOCK_M) * nt;
     DN_REQUIRE(tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "GEMM too large");
-    pwconv_tc_kernel<<<(unsigned)tiles, TC_THREADS, smem, stream>>>(ta, tw, ep, M, K, N, bn, nt, st, cols);
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > tiles) grid = tiles;
+    switch (ep.act) {
+        case DN_ACT_RELU:
+            pwconv_tc_kernel<DN_ACT_RELU><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
+            break;
+        case DN_ACT_RELU6:
+            pwconv_tc_kernel<DN_ACT_RELU6><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
+            break;
+        case DN_ACT_HSWISH:
+            pwconv_tc_kernel<DN_ACT_HSWISH><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
+            break;
+        default:
+            pwconv_tc_kernel<DN_ACT_NONE><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
+    }
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

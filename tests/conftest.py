@@ -10,7 +10,18 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _no_tf32():
+    # the torch fp32 references in the GPU tests must be real fp32: cuDNN convolutions default to TF32
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+
+
 def pytest_configure(config):
+    _no_tf32()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
