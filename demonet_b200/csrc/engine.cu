@@ -40,7 +40,8 @@ struct dn_engine {
     float* anchors_dev = nullptr;
     void* post_ws = nullptr;
     size_t post_ws_bytes = 0;
-    std::vector<CUtensorMap> tmap_a, tmap_w;       // per op (PW only)
+    std::vector<CUtensorMap> tmap_a, tmap_w, tmap_y;       // per op (PW only)
+    std::vector<char> has_tmap_y;
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
     cudaStream_t capture_stream = nullptr;
@@ -162,6 +163,8 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
     if (!e->tmaps_ready && e->desc.gemm_impl == 0) {
         e->tmap_a.resize(e->ops.size());
         e->tmap_w.resize(e->ops.size());
+        e->tmap_y.resize(e->ops.size());
+        e->has_tmap_y.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
             if (o.kind != DN_OP_PW) continue;
@@ -173,6 +176,13 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
             if (rc) return rc;
             rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn);
             if (rc) return rc;
+            // dense bf16 outputs without a residual are written by TMA (box 32 rows x 64 columns)
+            if (!o.out_fp32 && o.res_buf == DN_BUF_NONE && o.out_batch_stride == 0 && o.out_row_stride == 0 &&
+                o.out_offset == 0 && o.c_out % 8 == 0) {
+                rc = make_tmap_bf16_2d(&e->tmap_y[i], buf_ptr(e, o.out_buf), m_max, o.c_out, 32);
+                if (rc) return rc;
+                e->has_tmap_y[i] = 1;
+            }
         }
         e->tmaps_ready = true;
     }
@@ -207,7 +217,8 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 ep.out_row_stride = o.out_row_stride ? o.out_row_stride : o.c_out;
                 const int M = B * hw;
                 if (e->desc.gemm_impl == 0)
-                    rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], ep, M, o.c_in, o.c_out, s);
+                    rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], e->has_tmap_y[i] ? &e->tmap_y[i] : nullptr, ep, M, o.c_in,
+                                          o.c_out, s);
                 else
                     rc = pwconv_simt(buf_ptr(e, o.in_buf), W + o.w_off, ep, M, o.c_in, o.c_out, s);
                 break;

@@ -31,7 +31,8 @@ constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quart
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;      // 16 KiB
 constexpr int TC_STAGE_PITCH = 36;                                 // floats; 144-B rows keep 16-B smem accesses conflict-free
-constexpr int TC_STATIC_SMEM = 2 * 256 * 4 + TC_EPI_WARPS * 32 * TC_STAGE_PITCH * 4;      // bias staging + epilogue staging
+constexpr int TC_STAGE_BYTES = 5120;                               // >= 32*36*4 and a multiple of 1024
+constexpr int TC_STATIC_SMEM = 2 * 256 * 4 + TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // bias + epilogue staging (+ alignment)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +84,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -160,17 +166,20 @@ template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
     if (ACT == DN_ACT_RELU) return fmaxf(v, 0.f);
     if (ACT == DN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
-    if (ACT == DN_ACT_HSWISH) return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    if (ACT == DN_ACT_HSWISH) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));      // x * relu6(x + 3) / 6
     return v;
 }
 
-template <int ACT>
+template <int ACT, bool TMA_STORE>
 __global__ void __launch_bounds__(TC_THREADS)
-pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, PwEpilogue ep,
+pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
                  int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ float s_bias[2][256];
-    __shared__ __align__(16) float s_stage[TC_EPI_WARPS][32 * TC_STAGE_PITCH];      // per epilogue warp: 32 rows x 32 fp32 (+pad)
+    // per epilogue warp: 32 rows x 32 fp32 (+pad) for the staged stores, or a 32 x 64 bf16 SWIZZLE_128B tile
+    // for the TMA store
+    __shared__ __align__(1024) uint8_t s_stage_raw[TC_EPI_WARPS][TC_STAGE_BYTES];
     // carve: [stages x A tile][stages x W tile][barriers]; tiles must be 1024-B aligned for SWIZZLE_128B
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int w_stage_bytes = block_n * TC_BLOCK_K * 2;
@@ -184,6 +193,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_w);
+        if (TMA_STORE) prefetch_tmap(&tmap_y);
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
@@ -263,8 +273,43 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16);
+            if constexpr (TMA_STORE) {
+                // bf16 output, no residual: pack the tile into a SWIZZLE_128B staging buffer (thread = row,
+                // 16-byte chunk c of row r lives at chunk position c ^ (r & 7)) and let the TMA engine write
+                // it out; M / N tails are clipped by the tensor map.
+                uint8_t* obuf = s_stage_raw[warp - 2];
+                for (int g0 = half * 64; g0 < n_valid; g0 += 128) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c0 = g0 + 32 * h;
+                        if (c0 < block_n) {                                   // warp-uniform
+                            uint32_t v[32];
+                            const bool second = (c0 + 16 < block_n);
+                            tmem_ld16(tmem_d + (uint32_t)c0, v);
+                            if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                float f[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) f[i] = act_fn<ACT>(__uint_as_float(v[q * 8 + i]) + sb[c0 + q * 8 + i]);
+                                const int chunk = h * 4 + q;
+                                *reinterpret_cast<uint4*>(obuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pack8(f);
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_y, obuf, n0 + g0, m0 + quarter * 32);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
             const long long out_row = (m < M) ? ep.row_offset(m) : 0;     // this lane's own row; shared by shuffle below
-            float* stg = s_stage[warp - 2];
+            float* stg = reinterpret_cast<float*>(s_stage_raw[warp - 2]);
             for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
                 uint32_t v[32];
                 const bool second = (c0 + 16 < block_n);                  // warp-uniform
@@ -343,11 +388,13 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 __syncwarp();
             }
+            }
             // all tcgen05.ld of this warp have completed (wait::ld above): hand the buffer back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
         }
+        if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -401,7 +448,7 @@ static size_t smem_cap(int n) {
 void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
     const int nt = (N + 255) / 256;
     int bn = (N + nt - 1) / nt;
-    bn = (bn + 15) & ~15;
+    bn = nt > 1 ? (bn + 63) & ~63 : (bn + 15) & ~15;      // 64-column groups must not straddle two N tiles
     int cols = 32;
     while (cols < 2 * bn) cols <<= 1;                  // two accumulator buffers
     *block_n = bn;
@@ -415,64 +462,75 @@ void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* 
     *smem_bytes = need(st);
 }
 
-int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilogue& ep, int M, int K, int N,
-                     cudaStream_t stream) {
+template <int ACT, bool TMA_STORE>
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
+                          int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
+                          cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<ACT, TMA_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem_cap(1)));
+        configured = true;
+    }
+    pwconv_tc_kernel<ACT, TMA_STORE><<<grid, TC_THREADS, smem_req, stream>>>(ta, tw, ty, ep, M, K, N, bn, nt, tiles, st, cols);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+// ty: tensor map of the bf16 output ([rows, N], box 32 x 64) or nullptr.  The TMA-store epilogue is used when
+// ty is given and the layer has neither a residual nor fp32 / strided output.
+int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, int K,
+                     int N, cudaStream_t stream) {
     int bn, nt, st, cols;
     size_t smem;
     pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
-    // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  An SM has 228 KiB
-    // of shared memory; every CTA costs its dynamic request + ~20 KiB static (bias / epilogue staging) + 1 KiB reserved.
-    // The dynamic request is padded up to the largest size that still lets `per_sm` CTAs co-reside, so
-    // that the hardware cannot place one more (a CTA that cannot get its TMEM columns would spin until
-    // a neighbour exits).
-    auto cap = [](int n) -> size_t { return smem_cap(n); };
-    static bool configured = false;
-    if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_RELU6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<DN_ACT_HSWISH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap(1)));
-        configured = true;
-    }
+    // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
+    // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
+    // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).
+    DN_REQUIRE(smem <= smem_cap(1), DN_ERR_UNSUPPORTED, "GEMM tile does not fit in shared memory");
     int per_sm = 1;
     for (int n = 4; n >= 1; --n)
-        if (smem <= cap(n) && n * cols <= 512) {
+        if (smem <= smem_cap(n) && n * cols <= 512) {
             per_sm = n;
             break;
         }
-    DN_REQUIRE(smem <= cap(1), DN_ERR_UNSUPPORTED, "GEMM tile does not fit in shared memory");
-    const size_t smem_req = cap(per_sm);
+    const size_t smem_req = smem_cap(per_sm);
     const long long tiles = (long long)ceil_div(M, TC_BLOCK_M) * nt;
     DN_REQUIRE(tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "GEMM too large");
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
+    const bool tma_store = ty != nullptr && ep.residual == nullptr && !ep.out_fp32;
+    const CUtensorMap& tyr = tma_store ? *ty : ta;
+#define DN_PW_CASE(ACT)                                                                                                   \
+    return tma_store ? launch_variant<ACT, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid,  \
+                                                 smem_req, stream)                                                        \
+                     : launch_variant<ACT, false>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid, \
+                                                  smem_req, stream)
     switch (ep.act) {
-        case DN_ACT_RELU:
-            pwconv_tc_kernel<DN_ACT_RELU><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
-            break;
-        case DN_ACT_RELU6:
-            pwconv_tc_kernel<DN_ACT_RELU6><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
-            break;
-        case DN_ACT_HSWISH:
-            pwconv_tc_kernel<DN_ACT_HSWISH><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
-            break;
-        default:
-            pwconv_tc_kernel<DN_ACT_NONE><<<(unsigned)grid, TC_THREADS, smem_req, stream>>>(ta, tw, ep, M, K, N, bn, nt, (int)tiles, st, cols);
+        case DN_ACT_RELU: DN_PW_CASE(DN_ACT_RELU);
+        case DN_ACT_RELU6: DN_PW_CASE(DN_ACT_RELU6);
+        case DN_ACT_HSWISH: DN_PW_CASE(DN_ACT_HSWISH);
+        default: DN_PW_CASE(DN_ACT_NONE);
     }
-    DN_CHECK_LAUNCH();
-    return DN_OK;
+#undef DN_PW_CASE
 }
 
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream) {
     int bn, nt, st, cols;
     size_t smem;
     pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
-    CUtensorMap ta, tw;
+    CUtensorMap ta, tw, ty;
     int rc = make_tmap_bf16_2d(&ta, x, M, K, TC_BLOCK_M);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tw, w, N, K, bn);
     if (rc) return rc;
-    return pwconv_tc_launch(ta, tw, ep, M, K, N, stream);
+    const bool dense = !ep.out_fp32 && !ep.residual && N % 8 == 0 && ep.out_row_stride == N &&
+                       (ep.hw >= M || ep.out_batch_stride == (long long)ep.hw * N);
+    if (dense) {
+        rc = make_tmap_bf16_2d(&ty, ep.y, M, N, 32);
+        if (rc) return rc;
+    }
+    return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, K, N, stream);
 }
 
 }  // namespace dn
