@@ -14,23 +14,31 @@ namespace dn {
 // between neighbouring threads is served by L1.
 // Reference: ConvBNActivation(groups=C), demonet/models/mobilenetv2.py:32-55.
 // ---------------------------------------------------------------------------------------------
-template <int KS, int S, int TW>
+template <int ACT>
+__device__ __forceinline__ float dw_act(float v) {
+    if (ACT == DN_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == DN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    if (ACT == DN_ACT_HSWISH) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));      // x * relu6(x + 3) / 6
+    return v;
+}
+
+template <int KS, int S, int TW, int ACT>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-              uint4* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, int act) {
+              uint4* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
     constexpr int PAD = (KS - 1) / 2;
     constexpr int NV = (TW - 1) * S + KS;
     const int CV = C >> 3;
     const int WT = (Wo + TW - 1) / TW;
-    const long long total = (long long)B * Ho * WT * CV;
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const unsigned total = (unsigned)B * Ho * WT * CV;          // < 2^31, checked on the host
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
-    const int cv = (int)(tid % CV);
-    long long r = tid / CV;
-    const int wt = (int)(r % WT);
-    r /= WT;
-    const int oh = (int)(r % Ho);
-    const int b = (int)(r / Ho);
+    const int cv = (int)(tid % (unsigned)CV);
+    unsigned r = tid / (unsigned)CV;
+    const int wt = (int)(r % (unsigned)WT);
+    r /= (unsigned)WT;
+    const int oh = (int)(r % (unsigned)Ho);
+    const int b = (int)(r / (unsigned)Ho);
     const int ow0 = wt * TW;
     const int iw0 = ow0 * S - PAD;
 
@@ -45,28 +53,34 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
         }
     }
     const uint4* xb = x + (long long)b * H * W * CV + cv;
+    const bool interior_w = (iw0 >= 0) && (iw0 + NV <= W);      // no column of the window is padding
 #pragma unroll
     for (int kh = 0; kh < KS; ++kh) {
         const int ih = oh * S - PAD + kh;
         if (ih < 0 || ih >= H) continue;
-        const uint4* xr = xb + (long long)ih * W * CV;
-        uint4 raw[NV];
+        const uint4* xr = xb + (long long)(ih * W + iw0) * CV;
+        // one load + one bf16->fp32 unpack per input vector of the row window; every vector then feeds up to
+        // KS taps x TW outputs from registers
+        float in[NV][8];
+        if (interior_w) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int iw = iw0 + i;
-            raw[i] = (iw >= 0 && iw < W) ? __ldg(xr + (long long)iw * CV) : make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < NV; ++i) unpack8(__ldg(xr + i * CV), in[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int iw = iw0 + i;
+                unpack8((iw >= 0 && iw < W) ? __ldg(xr + i * CV) : make_uint4(0u, 0u, 0u, 0u), in[i]);
+            }
         }
 #pragma unroll
         for (int kw = 0; kw < KS; ++kw) {
-            const float4* wp = reinterpret_cast<const float4*>(w + (long long)(kh * KS + kw) * C) + cv * 2;
+            const float4* wp = reinterpret_cast<const float4*>(w + (kh * KS + kw) * C) + cv * 2;
             const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
             const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int t = 0; t < TW; ++t) {
-                float f[8];
-                unpack8(raw[t * S + kw], f);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[t][q] = fmaf(f[q], wv[q], acc[t][q]);
+                for (int q = 0; q < 8; ++q) acc[t][q] = fmaf(in[t * S + kw][q], wv[q], acc[t][q]);
             }
         }
     }
@@ -75,7 +89,7 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
     for (int t = 0; t < TW; ++t) {
         if (ow0 + t < Wo) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[t][q] = apply_act(acc[t][q], act);
+            for (int q = 0; q < 8; ++q) acc[t][q] = dw_act<ACT>(acc[t][q]);
             yo[(long long)t * CV] = pack8(acc[t]);
         }
     }
@@ -85,10 +99,17 @@ template <int KS, int S, int TW>
 static int launch_dw(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int Ho,
                      int Wo, int act, cudaStream_t stream) {
     const long long total = (long long)B * Ho * ((Wo + TW - 1) / TW) * (C / 8);
-    const long long blocks = (total + 255) / 256;
-    DN_REQUIRE(blocks < (1ll << 31), DN_ERR_UNSUPPORTED, "depthwise problem too large");
-    dwconv_kernel<KS, S, TW><<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)x, w, bias, (uint4*)y, B, H, W, C, Ho,
-                                                                  Wo, act);
+    DN_REQUIRE(total < (1ll << 31) && (long long)B * H * W * (C / 8) < (1ll << 31), DN_ERR_UNSUPPORTED,
+               "depthwise problem too large");
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const uint4* xi = (const uint4*)x;
+    uint4* yo = (uint4*)y;
+    switch (act) {
+        case DN_ACT_RELU: dwconv_kernel<KS, S, TW, DN_ACT_RELU><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        case DN_ACT_RELU6: dwconv_kernel<KS, S, TW, DN_ACT_RELU6><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        case DN_ACT_HSWISH: dwconv_kernel<KS, S, TW, DN_ACT_HSWISH><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        default: dwconv_kernel<KS, S, TW, DN_ACT_NONE><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo);
+    }
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

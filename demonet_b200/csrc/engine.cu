@@ -172,14 +172,14 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
             size_t smem;
             pwconv_tc_plan(o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
             const long long m_max = (long long)e->max_batch * o.h_in * o.w_in;
-            int rc = make_tmap_bf16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128);
+            int rc = make_tmap_bf16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128, 64);
             if (rc) return rc;
-            rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn);
+            rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn, 64);
             if (rc) return rc;
-            // dense bf16 outputs without a residual are written by TMA (box 32 rows x 64 columns)
+            // dense bf16 outputs without a residual are written by TMA (box 32 rows x 32 columns)
             if (!o.out_fp32 && o.res_buf == DN_BUF_NONE && o.out_batch_stride == 0 && o.out_row_stride == 0 &&
                 o.out_offset == 0 && o.c_out % 8 == 0) {
-                rc = make_tmap_bf16_2d(&e->tmap_y[i], buf_ptr(e, o.out_buf), m_max, o.c_out, 32);
+                rc = make_tmap_bf16_2d(&e->tmap_y[i], buf_ptr(e, o.out_buf), m_max, o.c_out, 32, 32);
                 if (rc) return rc;
                 e->has_tmap_y[i] = 1;
             }

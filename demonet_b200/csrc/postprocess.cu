@@ -172,12 +172,27 @@ __device__ unsigned int nms_consume_chunk(NmsState& st, int cand_cnt, float thr_
 // ---------------------------------------------------------------------------------------------
 constexpr int P1_ROWS = 32;
 constexpr int P1_THREADS = 256;
+// Per-image histogram of the foreground scores over a monotone key (float bits >> 17: 64 bins per
+// binade, from 2^-24 up to 1.0).  It only steers how deep the lazy NMS rounds go -- any threshold is
+// exact -- so the resolution (1.5 % in score) is irrelevant for correctness.
+constexpr int HIST_SHIFT = 17;
+constexpr int HIST_BASE = 0x33800000 >> HIST_SHIFT;
+constexpr int HIST_BINS = (0x3F800000 >> HIST_SHIFT) - HIST_BASE + 2;
+__device__ __forceinline__ int hist_bin(float s) {
+    int b = (int)(__float_as_uint(s) >> HIST_SHIFT) - HIST_BASE;
+    return b < 0 ? 0 : (b >= HIST_BINS ? HIST_BINS - 1 : b);
+}
+__device__ __forceinline__ float hist_bin_lower_edge(int b) {
+    return b <= 0 ? 0.f : __uint_as_float((uint32_t)(b + HIST_BASE) << HIST_SHIFT);
+}
 
 __global__ void __launch_bounds__(P1_THREADS)
 softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict__ bbox,
                       const float* __restrict__ anchors, float* __restrict__ scores_t,
-                      float4* __restrict__ boxes, int P, int K, dn_postprocess_params prm) {
+                      float4* __restrict__ boxes, int* __restrict__ hist, int P, int K, dn_postprocess_params prm) {
     extern __shared__ float s_tile[];                    // [P1_ROWS][K + 1]
+    __shared__ int s_hist[HIST_BINS];
+    for (int i = threadIdx.x; i < HIST_BINS; i += P1_THREADS) s_hist[i] = 0;
     const int ld = K + 1;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * P1_ROWS;
@@ -228,9 +243,63 @@ softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict_
         for (int k = lane; k < K; k += 32) dst[k] = __fdiv_rn(dst[k], s);
     }
     __syncthreads();
-    // transposed, coalesced store of classes 1..K-1
+    // transposed, coalesced store of classes 1..K-1 (+ histogram of the scores above the threshold)
     for (int k = 1 + warp; k < K; k += P1_THREADS / 32) {
-        if (lane < rows) scores_t[((size_t)b * (K - 1) + (k - 1)) * P + p0 + lane] = s_tile[lane * ld + k];
+        if (lane < rows) {
+            const float sv = s_tile[lane * ld + k];
+            scores_t[((size_t)b * (K - 1) + (k - 1)) * P + p0 + lane] = sv;
+            if (sv > prm.score_thresh) atomicAdd(&s_hist[hist_bin(sv)], 1);
+        }
+    }
+    __syncthreads();
+    int* gh = hist + (size_t)b * HIST_BINS;
+    for (int i = threadIdx.x; i < HIST_BINS; i += P1_THREADS) {
+        const int c = s_hist[i];
+        if (c) atomicAdd(gh + i, c);
+    }
+}
+
+// One warp per image: score thresholds of the lazy-NMS rounds.  Round r processes every candidate whose
+// score is >= thr[b][r], chosen so that about targets[r] candidates qualify (0 = everything).
+constexpr int NMS_ROUNDS = 3;
+struct RoundTargets {
+    int t[NMS_ROUNDS];
+};
+__global__ void __launch_bounds__(32)
+pick_thresholds_kernel(const int* __restrict__ hist, float* __restrict__ thr, RoundTargets targets) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int* gh = hist + (size_t)b * HIST_BINS;
+    constexpr int PER = (HIST_BINS + 31) / 32;
+    // lane l owns bins [l*PER, (l+1)*PER); suffix = candidates in all higher lanes
+    int mine = 0;
+    for (int i = 0; i < PER; ++i) {
+        const int bin = lane * PER + i;
+        if (bin < HIST_BINS) mine += gh[bin];
+    }
+    int above = 0;
+    for (int l = 31; l >= 0; --l) {
+        const int v = __shfl_sync(0xffffffffu, mine, l);
+        if (l > lane) above += v;
+    }
+    for (int r = 0; r < NMS_ROUNDS; ++r) {
+        const int target = targets.t[r];
+        float t = 0.f;                                   // everything
+        const bool here = target > 0 && above < target && above + mine >= target;
+        if (here) {
+            int acc = above;
+            for (int i = PER - 1; i >= 0; --i) {
+                const int bin = lane * PER + i;
+                if (bin >= HIST_BINS) continue;
+                acc += gh[bin];
+                if (acc >= target) {
+                    t = hist_bin_lower_edge(bin);
+                    break;
+                }
+            }
+        }
+        // at most one lane found a crossing; otherwise fewer than `target` candidates exist -> 0
+        for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (lane == 0) thr[b * NMS_ROUNDS + r] = t;
     }
 }
 
@@ -248,14 +317,17 @@ struct Entry {                        // one kept detection of a class list
 __global__ void __launch_bounds__(P2_THREADS)
 class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__ boxes,
                   unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_counts, int P, int K, int cap,
-                  float score_thresh, int topk, float min_box_size) {
+                  float score_thresh, int topk, float min_box_size, const float* __restrict__ thr,
+                  const int* __restrict__ done, int round) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_raw);              // [next_pow2(P)]
     __shared__ int s_n;
     const int c = blockIdx.x, b = blockIdx.y;
+    if (round > 0 && done[b]) return;
     const int lane = threadIdx.x & 31;
     const float* sc = scores_t + ((size_t)b * (K - 1) + c) * P;
     const float4* bx = boxes + (size_t)b * P;
+    const float round_thr = thr[b * NMS_ROUNDS + round];      // lazy NMS: only the top of the image this round
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // threshold (fp32 compare, generalized_ssd.py:371) [+ legacy remove_small_boxes, box_head.py:370]
@@ -265,7 +337,7 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
         bool pass = false;
         if (p < P) {
             s = sc[p];
-            pass = s > score_thresh;
+            pass = (s > score_thresh) && (s >= round_thr);
             if (pass && min_box_size >= 0.f) {
                 const float4 q = bx[p];
                 pass = (__fsub_rn(q.z, q.x) >= min_box_size) && (__fsub_rn(q.w, q.y) >= min_box_size);
@@ -296,79 +368,17 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// P2t: one CTA per image picks how deep each class list has to be processed in this round.
-// All candidates of the image whose score is >= T are processed, T chosen by bisection so that about
-// `target` candidates qualify (target < 0: everything).  Because every class list is sorted, the
-// qualifying candidates are a PREFIX of each list, greedy NMS on a prefix equals the full greedy NMS
-// restricted to it, and any unprocessed candidate scores strictly below every processed one -- so
-// once D detections survive among the processed ones, they are exactly the reference's
-// keep[:detections_per_img].  (If fewer survive, the next round goes deeper.)
+// Lazy NMS.  Round r only looks at the candidates of an image whose score is >= thr[b][r] (see
+// pick_thresholds_kernel).  Those candidates are a PREFIX of every class's full sorted top-k list,
+// greedy NMS on a prefix equals the full greedy NMS restricted to it, and every unprocessed candidate
+// scores strictly below every processed one -- so once D detections survive among the processed ones
+// they are exactly the reference's keep[:detections_per_img].  If fewer survive, the next round goes
+// deeper (the last round processes everything).
 // ---------------------------------------------------------------------------------------------
-constexpr int SEL_THREADS = 256;      // >= K-1
-
-__device__ __forceinline__ int prefix_leq(const unsigned long long* keys, int n, uint32_t u) {
-    int lo = 0, hi = n;                // first index whose score-key exceeds u
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((uint32_t)(keys[mid] >> 32) <= u) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ long long block_sum_ll(long long v, long long* s_tmp) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    long long t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_tmp[w];
-    return t;
-}
-
-__global__ void __launch_bounds__(SEL_THREADS)
-select_prefix_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ cand_counts,
-                     int* __restrict__ prefix, const int* __restrict__ done, int K, int cap, int target, int round) {
-    const int b = blockIdx.x, c = threadIdx.x;
-    if (round > 0 && done[b]) return;
-    __shared__ long long s_tmp[SEL_THREADS / 32];
-    __shared__ unsigned int s_lo, s_hi;
-    const int nc = K - 1;
-    const size_t slot = (size_t)b * nc + c;
-    const int m = (c < nc) ? cand_counts[slot] : 0;
-    const unsigned long long* keys = cand_keys + slot * cap;
-    const long long total = block_sum_ll(m, s_tmp);
-    if (target < 0 || total <= target) {
-        if (c < nc) prefix[slot] = m;
-        return;
-    }
-    if (threadIdx.x == 0) {
-        s_lo = 0xffffffffu;
-        s_hi = 0u;
-    }
-    __syncthreads();
-    if (m > 0) {
-        atomicMin(&s_lo, (uint32_t)(keys[0] >> 32));
-        atomicMax(&s_hi, (uint32_t)(keys[m - 1] >> 32));
-    }
-    __syncthreads();
-    uint32_t lo = s_lo, hi = s_hi;             // answer U lies in [lo, hi]; count(U = hi) = total > target
-    for (int it = 0; it < 24 && lo < hi; ++it) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const long long cnt = block_sum_ll(m > 0 ? prefix_leq(keys, m, mid) : 0, s_tmp);
-        if (cnt >= target) {
-            hi = mid;
-            if (cnt <= 2ll * target) break;    // close enough: any threshold is exact, only the work differs
-        } else {
-            lo = mid + 1;
-        }
-    }
-    if (c < nc) prefix[slot] = m > 0 ? prefix_leq(keys, m, hi) : 0;
-}
+constexpr int SEL_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
-// P2b: greedy NMS, one WARP per (image, class) over the prefix chosen above; stops at D kept.
+// P2b: greedy NMS, one WARP per (image, class) over this round's candidate list; stops at D kept.
 // Lane = one candidate of the current 32-wide chunk; the kept list lives in this warp's slice of
 // shared memory.  A candidate is kept iff no earlier kept box of its class overlaps it by more than
 // the threshold (the greedy loop of the CPU kernel).
@@ -459,22 +469,22 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
 constexpr int P3_MAX_PER_LANE = 8;     // supports K-1 <= 256 classes
 
 __global__ void __launch_bounds__(32)
-merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts, const int* __restrict__ prefix,
-                  const int* __restrict__ cand_counts, const float4* __restrict__ boxes, float4* __restrict__ out_boxes,
-                  float* __restrict__ out_scores, long long* __restrict__ out_labels, int* __restrict__ out_counts,
-                  int* __restrict__ done, int P, int K, int D, int round) {
+merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts, const float* __restrict__ thr,
+                  const float4* __restrict__ boxes, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
+                  long long* __restrict__ out_labels, int* __restrict__ out_counts, int* __restrict__ done, int P, int K,
+                  int D, int round) {
     const int b = blockIdx.x, lane = threadIdx.x;
     if (round > 0 && done[b]) return;
     const int nc = K - 1;
     int pos[P3_MAX_PER_LANE], cnt[P3_MAX_PER_LANE];
     Entry head[P3_MAX_PER_LANE];
-    int total = 0, incomplete = 0;
+    int total = 0;
+    const int incomplete = thr[b * NMS_ROUNDS + round] > 0.f;      // candidates below the round threshold exist
 #pragma unroll
     for (int i = 0; i < P3_MAX_PER_LANE; ++i) {
         const int c = lane + 32 * i;
         pos[i] = 0;
         cnt[i] = (c < nc) ? counts[b * nc + c] : 0;
-        if (c < nc) incomplete |= (prefix[b * nc + c] < cand_counts[b * nc + c]) && (cnt[i] < D);
         total += cnt[i];
         head[i].score = 0.f;
         head[i].prior = 0;
@@ -482,7 +492,6 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    incomplete = __any_sync(0xffffffffu, incomplete);
     if (total < D && incomplete) {
         if (lane == 0) done[b] = 0;
         return;
@@ -559,11 +568,12 @@ static int next_pow2(int v) {
 
 // rounds of the lazy NMS: process about this many top-scoring candidates per image, go deeper only
 // for the images where fewer than D detections survived (-1 = everything)
-constexpr int NMS_ROUNDS = 3;
-static void round_targets(int D, int* t) {
-    t[0] = D * 8 > 2048 ? D * 8 : 2048;
-    t[1] = t[0] * 8;
-    t[2] = -1;
+static RoundTargets round_targets(int D) {
+    RoundTargets r;
+    r.t[0] = D * 8 > 2048 ? D * 8 : 2048;
+    r.t[1] = r.t[0] * 8;
+    r.t[2] = 0;               // everything
+    return r;
 }
 
 static int cand_cap(const dn_postprocess_params* p) {
@@ -571,7 +581,7 @@ static int cand_cap(const dn_postprocess_params* p) {
 }
 
 struct PostLayout {
-    size_t scores_off, boxes_off, cand_off, ccount_off, prefix_off, entries_off, counts_off, done_off, total;
+    size_t scores_off, boxes_off, cand_off, ccount_off, hist_off, thr_off, entries_off, counts_off, done_off, total;
 };
 static PostLayout post_layout(int B, const dn_postprocess_params* p) {
     PostLayout L;
@@ -582,7 +592,8 @@ static PostLayout post_layout(int B, const dn_postprocess_params* p) {
     L.boxes_off = off;  off = al(off + (size_t)B * P * sizeof(float4));
     L.cand_off = off;   off = al(off + (size_t)B * (K - 1) * cap * sizeof(unsigned long long));
     L.ccount_off = off; off = al(off + (size_t)B * (K - 1) * sizeof(int));
-    L.prefix_off = off; off = al(off + (size_t)B * (K - 1) * sizeof(int));
+    L.hist_off = off;   off = al(off + (size_t)B * HIST_BINS * sizeof(int));
+    L.thr_off = off;    off = al(off + (size_t)B * NMS_ROUNDS * sizeof(float));
     L.entries_off = off; off = al(off + (size_t)B * (K - 1) * D * sizeof(Entry));
     L.counts_off = off; off = al(off + (size_t)B * (K - 1) * sizeof(int));
     L.done_off = off;   off = al(off + (size_t)B * sizeof(int));
@@ -635,7 +646,8 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
     int* counts = (int*)(ws + L.counts_off);
     unsigned long long* cand = (unsigned long long*)(ws + L.cand_off);
     int* ccount = (int*)(ws + L.ccount_off);
-    int* prefix = (int*)(ws + L.prefix_off);
+    int* hist = (int*)(ws + L.hist_off);
+    float* thr = (float*)(ws + L.thr_off);
     int* done = (int*)(ws + L.done_off);
     const int cap = cand_cap(p);
     const size_t smem1 = (size_t)P1_ROWS * (K + 1) * sizeof(float);
@@ -654,43 +666,41 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
         cfg_nms = smem_nms;
     }
     const float thr_up = threshold_up(p->nms_thresh);
-    int targets[NMS_ROUNDS];
-    round_targets(D, targets);
+    const RoundTargets targets = round_targets(D);
     const long long problems = (long long)B * (K - 1);
     cudaEvent_t ev[2] = {nullptr, nullptr};
     if (ms3) {
         DN_CHECK_CUDA(cudaEventCreate(&ev[0]));
         DN_CHECK_CUDA(cudaEventCreate(&ev[1]));
     }
-    // phase 0: softmax + decode; phase 1: sort + per-round prefix selection and NMS; phase 2: merges.
+    // phase 0: softmax + decode (+ histogram, round thresholds); phase 1: per-round sort and NMS; phase 2: merges.
     // (the profiling variant re-runs each phase `iters` times, which is idempotent)
     for (int phase = 0; phase < 3; ++phase) {
         if (ms3) DN_CHECK_CUDA(cudaEventRecord(ev[0], stream));
         for (int it = 0; it < iters; ++it) {
             if (phase == 0 || !ms3) {
+                DN_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * HIST_BINS * sizeof(int), stream));
                 dim3 grid(ceil_div(P, P1_ROWS), B);
                 softmax_decode_kernel<<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors, scores_t,
-                                                                          boxes, P, K, *p);
+                                                                          boxes, hist, P, K, *p);
                 DN_CHECK_LAUNCH();
-            }
-            if (phase == 1 || !ms3) {
-                dim3 grid(K - 1, B);
-                class_sort_kernel<<<grid, P2_THREADS, smem_sort, stream>>>(scores_t, boxes, cand, ccount, P, K, cap,
-                                                                          p->score_thresh, p->topk_candidates,
-                                                                          p->min_box_size);
+                pick_thresholds_kernel<<<B, 32, 0, stream>>>(hist, thr, targets);
                 DN_CHECK_LAUNCH();
             }
             for (int r = 0; r < NMS_ROUNDS; ++r) {
                 if (phase == 1 || !ms3) {
-                    select_prefix_kernel<<<B, SEL_THREADS, 0, stream>>>(cand, ccount, prefix, done, K, cap, targets[r], r);
+                    dim3 grid(K - 1, B);
+                    class_sort_kernel<<<grid, P2_THREADS, smem_sort, stream>>>(scores_t, boxes, cand, ccount, P, K, cap,
+                                                                              p->score_thresh, p->topk_candidates,
+                                                                              p->min_box_size, thr, done, r);
                     DN_CHECK_LAUNCH();
                     class_nms_warp_kernel<<<(unsigned)ceil_div<long long>(problems, nms_warps), nms_warps * 32, smem_nms,
-                                            stream>>>(cand, prefix, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
+                                            stream>>>(cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
                     DN_CHECK_LAUNCH();
                 }
                 if (phase == 2 || !ms3) {
-                    merge_topd_kernel<<<B, 32, 0, stream>>>(entries, counts, prefix, ccount, boxes, (float4*)out_boxes,
-                                                            out_scores, (long long*)out_labels, out_counts, done, P, K, D, r);
+                    merge_topd_kernel<<<B, 32, 0, stream>>>(entries, counts, thr, boxes, (float4*)out_boxes, out_scores,
+                                                            (long long*)out_labels, out_counts, done, P, K, D, r);
                     DN_CHECK_LAUNCH();
                 }
             }

@@ -32,7 +32,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;      // 16 KiB
 constexpr int TC_STAGE_PITCH = 36;                                 // floats; 144-B rows keep 16-B smem accesses conflict-free
 constexpr int TC_STAGE_BYTES = 5120;                               // >= 32*36*4 and a multiple of 1024
-constexpr int TC_STATIC_SMEM = 2 * 256 * 4 + TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // bias + epilogue staging (+ alignment)
+constexpr int TC_STATIC_SMEM = TC_EPI_WARPS * 32 * 4 + TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // bias + epilogue staging (+ alignment)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -176,7 +176,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
                  int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ float s_bias[2][256];
+    __shared__ float s_bias[TC_EPI_WARPS][32];                         // warp-private bias slice of the current 32 columns
     // per epilogue warp: 32 rows x 32 fp32 (+pad) for the staged stores, or a 32 x 64 bf16 SWIZZLE_128B tile
     // for the TMA store
     __shared__ __align__(1024) uint8_t s_stage_raw[TC_EPI_WARPS][TC_STAGE_BYTES];
@@ -260,50 +260,45 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        const int et = threadIdx.x - 64;                                  // 0 .. 32*TC_EPI_WARPS-1
-        uint32_t lt = 0;
+        uint32_t lt = 0, stores = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1u;
             const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
             const int m = m0 + row;
             const int n_valid = min(block_n, N - n0);
-            float* sb = s_bias[buf];
-            for (int i = et; i < block_n; i += 32 * TC_EPI_WARPS) sb[i] = (i < n_valid) ? __ldg(ep.bias + n0 + i) : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+            float* sbw = s_bias[warp - 2];
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16);
             if constexpr (TMA_STORE) {
-                // bf16 output, no residual: pack the tile into a SWIZZLE_128B staging buffer (thread = row,
-                // 16-byte chunk c of row r lives at chunk position c ^ (r & 7)) and let the TMA engine write
-                // it out; M / N tails are clipped by the tensor map.
-                uint8_t* obuf = s_stage_raw[warp - 2];
-                for (int g0 = half * 64; g0 < n_valid; g0 += 128) {
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffer free again
+                // bf16 output, no residual: pack 32-column groups into SWIZZLE_64B staging tiles (thread = row;
+                // 16-byte chunk c of row r lives at chunk position c ^ ((r >> 1) & 3)) and let the TMA engine
+                // write them out; M / N tails are clipped by the tensor map.  Two staging tiles per warp.
+                uint8_t* obase = s_stage_raw[warp - 2];
+                for (int c0 = half * 32; c0 < n_valid; c0 += 64, ++stores) {
+                    uint8_t* obuf = obase + (stores & 1u) * 2048;
+                    const int nb = n0 + c0 + lane;
+                    const float bv = (nb < N) ? __ldg(ep.bias + nb) : 0.f;
+                    uint32_t v[32];
+                    const bool second = (c0 + 16 < block_n);              // warp-uniform
+                    tmem_ld16(tmem_d + (uint32_t)c0, v);
+                    if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this tile's previous store
                     __syncwarp();
+                    sbw[lane] = bv;
+                    __syncwarp();
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c0 = g0 + 32 * h;
-                        if (c0 < block_n) {                                   // warp-uniform
-                            uint32_t v[32];
-                            const bool second = (c0 + 16 < block_n);
-                            tmem_ld16(tmem_d + (uint32_t)c0, v);
-                            if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
-                            tmem_ld_wait();
+                    for (int q = 0; q < 4; ++q) {
+                        float f[8];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                float f[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) f[i] = act_fn<ACT>(__uint_as_float(v[q * 8 + i]) + sb[c0 + q * 8 + i]);
-                                const int chunk = h * 4 + q;
-                                *reinterpret_cast<uint4*>(obuf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = pack8(f);
-                            }
-                        }
+                        for (int i = 0; i < 8; ++i) f[i] = act_fn<ACT>(__uint_as_float(v[q * 8 + i]) + sbw[q * 8 + i]);
+                        *reinterpret_cast<uint4*>(obuf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pack8(f);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&tmap_y, obuf, n0 + g0, m0 + quarter * 32);
+                        tma_store_2d(&tmap_y, obuf, n0 + c0, m0 + quarter * 32);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -315,6 +310,11 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool second = (c0 + 16 < block_n);                  // warp-uniform
                 tmem_ld16(tmem_d + (uint32_t)c0, v);
                 if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
+                {
+                    const int nb = n0 + c0 + lane;
+                    sbw[lane] = (nb < N) ? __ldg(ep.bias + nb) : 0.f;
+                }
+                __syncwarp();
                 tmem_ld_wait();
                 // residual tile of this chunk: issue all loads now, they complete behind the TMEM read / staging
                 const int cg = (lane & 7) * 4;
@@ -334,10 +334,10 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o;
-                    o.x = act_fn<ACT>(__uint_as_float(v[j + 0]) + sb[c0 + j + 0]);
-                    o.y = act_fn<ACT>(__uint_as_float(v[j + 1]) + sb[c0 + j + 1]);
-                    o.z = act_fn<ACT>(__uint_as_float(v[j + 2]) + sb[c0 + j + 2]);
-                    o.w = act_fn<ACT>(__uint_as_float(v[j + 3]) + sb[c0 + j + 3]);
+                    o.x = act_fn<ACT>(__uint_as_float(v[j + 0]) + sbw[j + 0]);
+                    o.y = act_fn<ACT>(__uint_as_float(v[j + 1]) + sbw[j + 1]);
+                    o.z = act_fn<ACT>(__uint_as_float(v[j + 2]) + sbw[j + 2]);
+                    o.w = act_fn<ACT>(__uint_as_float(v[j + 3]) + sbw[j + 3]);
                     *reinterpret_cast<float4*>(stg + lane * TC_STAGE_PITCH + j) = o;
                 }
                 __syncwarp();
@@ -421,18 +421,22 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// 2D bf16 tensor map over a row-major [rows, cols] matrix, box = [box_rows, 64 cols], SWIZZLE_128B
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows) {
+// 2D bf16 tensor map over a row-major [rows, cols] matrix, box = [box_rows, box_cols]; the swizzle span equals
+// the box row (64 cols -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B)
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols) {
     PFN_encodeTiled fn = get_encode_fn();
     DN_REQUIRE(fn != nullptr, DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     DN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, DN_ERR_INVALID, "GEMM operand must be 16-byte aligned");
     DN_REQUIRE(cols % 8 == 0, DN_ERR_UNSUPPORTED, "GEMM K must be a multiple of 8 (got %lld)", cols);
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
+    DN_REQUIRE(box_cols == 16 || box_cols == 32 || box_cols == 64, DN_ERR_INVALID, "box_cols must be 16, 32 or 64");
+    const CUtensorMapSwizzle swz = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DN_REQUIRE(r == CUDA_SUCCESS, DN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r,
                rows, cols, box_rows);
@@ -520,14 +524,14 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
     size_t smem;
     pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
     CUtensorMap ta, tw, ty;
-    int rc = make_tmap_bf16_2d(&ta, x, M, K, TC_BLOCK_M);
+    int rc = make_tmap_bf16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tw, w, N, K, bn);
+    rc = make_tmap_bf16_2d(&tw, w, N, K, bn, TC_BLOCK_K);
     if (rc) return rc;
     const bool dense = !ep.out_fp32 && !ep.residual && N % 8 == 0 && ep.out_row_stride == N &&
                        (ep.hw >= M || ep.out_batch_stride == (long long)ep.hw * N);
     if (dense) {
-        rc = make_tmap_bf16_2d(&ty, ep.y, M, N, 32);
+        rc = make_tmap_bf16_2d(&ty, ep.y, M, N, 32, 32);
         if (rc) return rc;
     }
     return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, K, N, stream);

@@ -267,6 +267,26 @@ def fold_layer(sd, layer: Layer, eps: float):
     return wf, bf
 
 
+def pw_pack_factor(L: Layer) -> int:
+    """Pixel packing for pointwise layers with very few input channels.
+
+    A [M, K] NHWC activation with K <= 32 is also a [M/p, p*K] matrix (p consecutive pixels per row), and
+    the [M, N] output is a [M/p, p*N] matrix, so the 1x1 conv equals one GEMM with the block-diagonal
+    weight diag(W, ..., W).  The tensor cores do p times the MACs (irrelevant: these layers are
+    bandwidth-bound) but every TMA row becomes a dense 128-byte line and there are p times fewer tiles.
+    """
+    if L.kind != "pw" or L.head or L.cin > 96:
+        return 1
+    hw = L.h_in * L.w_in
+
+    def k_waste(k):            # padded K (64-wide k-blocks) per useful K
+        return ((k + 63) // 64 * 64) / k
+    for p in (4, 2):
+        if p * L.cout <= 256 and hw % p == 0 and p * L.cin <= 192 and k_waste(p * L.cin) <= k_waste(L.cin):
+            return p
+    return 1
+
+
 def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
     """Fold + lay out every layer.  Returns (blob, per-layer offsets dict(w, b[, w2, b2]))."""
     chunks, offs, pos = [], [], 0
@@ -297,8 +317,13 @@ def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
             w = wf.float().permute(1, 2, 3, 0).reshape(27, L.cout).contiguous().numpy()
         elif L.kind == "dw":      # [C,1,k,k] -> [k*k][C] fp32
             w = wf.float().reshape(L.cout, L.k * L.k).t().contiguous().numpy()
-        else:                     # pw: [N,K,1,1] -> [N][K] bf16
-            w = wf.float().reshape(L.cout, L.cin).to(torch.bfloat16).contiguous().view(torch.int16).numpy()
+        else:                     # pw: [N,K,1,1] -> [N][K] bf16 (block-diagonal when pixels are packed)
+            w2 = wf.float().reshape(L.cout, L.cin).to(torch.bfloat16)
+            pf = pw_pack_factor(L)
+            if pf > 1:
+                w2 = torch.block_diag(*([w2.float()] * pf)).to(torch.bfloat16)
+                bias = np.tile(bias, pf)
+            w = w2.contiguous().view(torch.int16).numpy()
         offs.append({"w": put(w), "b": put(bias)})
     return b"".join(chunks), offs
 
@@ -361,6 +386,10 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf):
         op.res_buf = t2b[L.res] if L.res else _C.BUF_NONE
         op.h_in, op.w_in, op.c_in = L.h_in, L.w_in, L.cin
         op.h_out, op.w_out, op.c_out = L.h_out, L.w_out, L.cout
+        pf = pw_pack_factor(L)
+        if pf > 1:                # [M, K] x [K, N]  ==  [M/p, pK] x diag(W..W)  (same memory)
+            op.h_in, op.w_in, op.c_in = (L.h_in * L.w_in) // pf, 1, pf * L.cin
+            op.h_out, op.w_out, op.c_out = op.h_in, 1, pf * L.cout
         op.ksize, op.stride, op.c_mid = L.k, L.stride, L.se_mid
         op.w_off, op.b_off = off["w"], off["b"]
         op.w2_off, op.b2_off = off.get("w2", 0), off.get("b2", 0)
