@@ -42,14 +42,15 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
     const int ow0 = wt * TW;
     const int iw0 = ow0 * S - PAD;
 
-    float acc[TW][8];
+    // packed fp32 math (sm_100 FFMA2: two fp32 FMAs per instruction), channel pairs (2q, 2q+1)
+    float2 acc[TW][4];
     {
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2);
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + cv * 2 + 1);
 #pragma unroll
         for (int t = 0; t < TW; ++t) {
-            acc[t][0] = b0.x; acc[t][1] = b0.y; acc[t][2] = b0.z; acc[t][3] = b0.w;
-            acc[t][4] = b1.x; acc[t][5] = b1.y; acc[t][6] = b1.z; acc[t][7] = b1.w;
+            acc[t][0] = make_float2(b0.x, b0.y); acc[t][1] = make_float2(b0.z, b0.w);
+            acc[t][2] = make_float2(b1.x, b1.y); acc[t][3] = make_float2(b1.z, b1.w);
         }
     }
     const uint4* xb = x + (long long)b * H * W * CV + cv;
@@ -61,26 +62,26 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
         const uint4* xr = xb + (long long)(ih * W + iw0) * CV;
         // one load + one bf16->fp32 unpack per input vector of the row window; every vector then feeds up to
         // KS taps x TW outputs from registers
-        float in[NV][8];
-        if (interior_w) {
+        float2 in[NV][4];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) unpack8(__ldg(xr + i * CV), in[i]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int iw = iw0 + i;
-                unpack8((iw >= 0 && iw < W) ? __ldg(xr + i * CV) : make_uint4(0u, 0u, 0u, 0u), in[i]);
-            }
+        for (int i = 0; i < NV; ++i) {
+            const int iw = iw0 + i;
+            const uint4 v = (interior_w || (iw >= 0 && iw < W)) ? __ldg(xr + i * CV) : make_uint4(0u, 0u, 0u, 0u);
+            in[i][0] = bf16x2_to_float2(v.x);
+            in[i][1] = bf16x2_to_float2(v.y);
+            in[i][2] = bf16x2_to_float2(v.z);
+            in[i][3] = bf16x2_to_float2(v.w);
         }
 #pragma unroll
         for (int kw = 0; kw < KS; ++kw) {
             const float4* wp = reinterpret_cast<const float4*>(w + (kh * KS + kw) * C) + cv * 2;
             const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                                  make_float2(w1.z, w1.w)};
 #pragma unroll
             for (int t = 0; t < TW; ++t) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[t][q] = fmaf(in[t * S + kw][q], wv[q], acc[t][q]);
+                for (int q = 0; q < 4; ++q) acc[t][q] = __ffma2_rn(in[t * S + kw][q], wv[q], acc[t][q]);
             }
         }
     }
@@ -88,9 +89,12 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
 #pragma unroll
     for (int t = 0; t < TW; ++t) {
         if (ow0 + t < Wo) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[t][q] = dw_act<ACT>(acc[t][q]);
-            yo[(long long)t * CV] = pack8(acc[t]);
+            uint4 o;
+            o.x = float2_to_bf16x2(dw_act<ACT>(acc[t][0].x), dw_act<ACT>(acc[t][0].y));
+            o.y = float2_to_bf16x2(dw_act<ACT>(acc[t][1].x), dw_act<ACT>(acc[t][1].y));
+            o.z = float2_to_bf16x2(dw_act<ACT>(acc[t][2].x), dw_act<ACT>(acc[t][2].y));
+            o.w = float2_to_bf16x2(dw_act<ACT>(acc[t][3].x), dw_act<ACT>(acc[t][3].y));
+            yo[(long long)t * CV] = o;
         }
     }
 }
@@ -136,9 +140,9 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
     const int ow = (int)(tid % Wo);
     const int oh = (int)((tid / Wo) % Ho);
     const int b = (int)(tid / ((long long)Wo * Ho));
-    float acc[COUT];
+    float2 acc[COUT / 2];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+    for (int c = 0; c < COUT / 2; ++c) acc[c] = make_float2(sb[2 * c], sb[2 * c + 1]);
     const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
@@ -153,22 +157,26 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
                 if (ih >= 0 && ih < H && iw >= 0 && iw < W)
                     v = __fdiv_rn(__fsub_rn(__ldg(plane + (long long)ih * W + iw), mean[ci]), stdv[ci]);
                 const float4* wr = reinterpret_cast<const float4*>(sw + ((ci * 3 + kh) * 3 + kw) * COUT);
+                const float2 vv = make_float2(v, v);
 #pragma unroll
                 for (int c4 = 0; c4 < COUT / 4; ++c4) {
                     const float4 ww = wr[c4];
-                    acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
-                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
-                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
-                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                    acc[c4 * 2 + 0] = __ffma2_rn(vv, make_float2(ww.x, ww.y), acc[c4 * 2 + 0]);
+                    acc[c4 * 2 + 1] = __ffma2_rn(vv, make_float2(ww.z, ww.w), acc[c4 * 2 + 1]);
                 }
             }
         }
     }
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = apply_act(acc[c], act);
     uint4* yo = y + tid * (COUT / 8);
 #pragma unroll
-    for (int v = 0; v < COUT / 8; ++v) yo[v] = pack8(acc + v * 8);
+    for (int v = 0; v < COUT / 8; ++v) {
+        uint4 o;
+        o.x = float2_to_bf16x2(apply_act(acc[v * 4 + 0].x, act), apply_act(acc[v * 4 + 0].y, act));
+        o.y = float2_to_bf16x2(apply_act(acc[v * 4 + 1].x, act), apply_act(acc[v * 4 + 1].y, act));
+        o.z = float2_to_bf16x2(apply_act(acc[v * 4 + 2].x, act), apply_act(acc[v * 4 + 2].y, act));
+        o.w = float2_to_bf16x2(apply_act(acc[v * 4 + 3].x, act), apply_act(acc[v * 4 + 3].y, act));
+        yo[v] = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

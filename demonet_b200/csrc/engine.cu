@@ -45,8 +45,14 @@ struct dn_engine {
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
     cudaStream_t capture_stream = nullptr;
-    // staging for dn_engine_forward_host
-    float* stage_images = nullptr;
+    // staging for dn_engine_forward_host: two input buffers so that the H2D copy of call i+1 (on copy_stream)
+    // overlaps the forward of call i (on the caller's stream)
+    float* stage_images = nullptr;              // [2][max_batch,3,H,W]
+    size_t stage_image_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr};
+    bool fwd_recorded[2] = {false, false};
+    int host_parity = 0;
     unsigned char* stage_out = nullptr;
     size_t so_boxes = 0, so_scores = 0, so_labels = 0, so_counts = 0, so_total = 0;
     size_t device_bytes = 0;
@@ -118,11 +124,17 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     TRY(cudaMalloc(&e->anchors_dev, e->anchors_host.size() * sizeof(float)));
     TRY(cudaMemcpy(e->anchors_dev, e->anchors_host.data(), e->anchors_host.size() * sizeof(float), cudaMemcpyHostToDevice));
     TRY(cudaMalloc(&e->post_ws, e->post_ws_bytes));
-    TRY(cudaMalloc(&e->stage_images, img_bytes));
+    e->stage_image_bytes = (img_bytes + 255) & ~(size_t)255;
+    TRY(cudaMalloc(&e->stage_images, 2 * e->stage_image_bytes));
+    TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        TRY(cudaEventCreateWithFlags(&e->h2d_done[i], cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&e->fwd_done[i], cudaEventDisableTiming));
+    }
     TRY(cudaMalloc(&e->stage_out, e->so_total));
     TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
 #undef TRY
-    e->device_bytes = e->arena_bytes + e->post_ws_bytes + img_bytes + e->so_total + e->anchors_host.size() * 4;
+    e->device_bytes = e->arena_bytes + e->post_ws_bytes + 2 * e->stage_image_bytes + e->so_total + e->anchors_host.size() * 4;
     *out = e;
     return DN_OK;
 }
@@ -131,6 +143,11 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
     if (!e) return DN_OK;
     drop_graphs(e);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (e->h2d_done[i]) cudaEventDestroy(e->h2d_done[i]);
+        if (e->fwd_done[i]) cudaEventDestroy(e->fwd_done[i]);
+    }
     cudaFree(e->arena);
     cudaFree(e->weights);
     cudaFree(e->anchors_dev);
@@ -286,11 +303,21 @@ extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, in
     cudaStream_t s = (cudaStream_t)stream_;
     const size_t D = e->desc.post.detections_per_img;
     const size_t img_bytes = (size_t)B * 3 * e->desc.image_h * e->desc.image_w * sizeof(float);
-    DN_CHECK_CUDA(cudaMemcpyAsync(e->stage_images, images_host, img_bytes, cudaMemcpyHostToDevice, s));
+    // H2D on the copy stream into the staging buffer the previous-but-one call used; the forward on the
+    // caller's stream waits for it, so back-to-back calls overlap copy(i+1) with forward(i).
+    const int par = e->host_parity;
+    e->host_parity ^= 1;
+    float* stage = (float*)((unsigned char*)e->stage_images + (size_t)par * e->stage_image_bytes);
+    if (e->fwd_recorded[par]) DN_CHECK_CUDA(cudaStreamWaitEvent(e->copy_stream, e->fwd_done[par], 0));   // WAR on stage
+    DN_CHECK_CUDA(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    DN_CHECK_CUDA(cudaEventRecord(e->h2d_done[par], e->copy_stream));
+    DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->h2d_done[par], 0));
     unsigned char* so = e->stage_out;
-    int rc = dn_engine_forward(e, e->stage_images, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
+    int rc = dn_engine_forward(e, stage, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
                                (int64_t*)(so + e->so_labels), (int32_t*)(so + e->so_counts), s);
     if (rc) return rc;
+    DN_CHECK_CUDA(cudaEventRecord(e->fwd_done[par], s));
+    e->fwd_recorded[par] = true;
     DN_CHECK_CUDA(cudaMemcpyAsync(out_boxes_host, so + e->so_boxes, (size_t)B * D * 16, cudaMemcpyDeviceToHost, s));
     DN_CHECK_CUDA(cudaMemcpyAsync(out_scores_host, so + e->so_scores, (size_t)B * D * 4, cudaMemcpyDeviceToHost, s));
     DN_CHECK_CUDA(cudaMemcpyAsync(out_labels_host, so + e->so_labels, (size_t)B * D * 8, cudaMemcpyDeviceToHost, s));

@@ -175,7 +175,10 @@ int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes);
 /* images_dev: fp32 [B,3,H,W]; outputs as in dn_postprocess */
 int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
                       int64_t* out_labels, int32_t* out_counts, void* stream);
-/* same, taking PINNED HOST buffers: H2D copy, forward, D2H copy, all enqueued on `stream` */
+/* same, taking PINNED HOST buffers: H2D copy, forward, D2H copy.  The forward and the D2H copies are
+ * enqueued on `stream`; the H2D copy runs on an engine-owned stream that `stream` waits for, into one of two
+ * staging buffers, so back-to-back calls overlap the upload of call i+1 with the forward of call i.
+ * The results (and images_host) are safe to touch once `stream` has been synchronised. */
 int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
                            float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
                            void* stream);
