@@ -198,14 +198,10 @@ def main():
     imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
     imgs = imgs_host.to(dev)
     # one packed output buffer per rank so that the final gather is ONE collective
-    nb_boxes, nb_scores, nb_labels, nb_counts = B * D * 16, B * D * 4, B * D * 8, ((B * 4 + 7) // 8) * 8
-    packed = torch.zeros(nb_boxes + nb_scores + nb_labels + nb_counts, dtype=torch.uint8, device=dev)
-    o = 0
-    out_boxes = packed[o:o + nb_boxes].view(torch.float32).view(B, D, 4); o += nb_boxes
-    out_scores = packed[o:o + nb_scores].view(torch.float32).view(B, D); o += nb_scores
-    out_labels = packed[o:o + nb_labels].view(torch.int64).view(B, D); o += nb_labels
-    out_counts = packed[o:o + B * 4].view(torch.int32)
-    io = {"boxes": out_boxes, "scores": out_scores, "labels": out_labels, "counts": out_counts}
+    from demonet_b200 import dist as ddist
+    packed_det = ddist.PackedDetections(B, D, dev)
+    packed = packed_det.buffer
+    io = packed_det.as_io()
     gathered = torch.empty(world * packed.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
     host_out = {"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
                 "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
@@ -215,7 +211,7 @@ def main():
     def step_device():
         eng.forward(imgs, io)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, packed)
+            ddist.gather_detections(packed_det, gathered)
 
     def step_host():
         eng.forward_host(imgs_host, host_out)       # results land in each rank's own host memory: no gather

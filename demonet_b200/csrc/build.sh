@@ -6,11 +6,11 @@ OUT="$HERE/../lib"
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-SRCS="error.cu postprocess.cu dwconv.cu pwconv_simt.cu pwconv_tc.cu engine.cu"
+SRCS="error.cu postprocess.cu dwconv.cu dwconv_tma.cu pwconv_simt.cu pwconv_tc.cu engine.cu"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$HERE/$s" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/pwconv.cuh" -nt "$o" ] || [ "$HERE/../../include/demonet_b200.h" -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$HERE/$s" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/pwconv.cuh" -nt "$o" ] || [ "$HERE/dwconv.cuh" -nt "$o" ] || [ "$HERE/../../include/demonet_b200.h" -nt "$o" ]; then
     $NVCC $FLAGS -c "$HERE/$s" -o "$o" &
   fi
   OBJS="$OBJS $o"

@@ -4,6 +4,7 @@
 //   * squeeze-excitation, applied in place                                              (dn_se_inplace)
 // Activations are NHWC bf16, 8 channels (16 B) per thread access, fp32 accumulation.
 #include "common.cuh"
+#include "dwconv.cuh"
 
 namespace dn {
 
@@ -245,6 +246,12 @@ se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const flo
     }
 }
 
+// Tile strategy per layer shape (measured on B200, profiles/r01_dw_tma_vs_direct.txt): the TMA-fed
+// shared-memory tiles win on the large feature maps (>= 80x80 outputs: 2.8-5.8 TB/s vs 2.0-4.8 TB/s), where a
+// halo tile amortises over many outputs; on the small maps the register-tiled kernel (L1-served halos, no
+// per-tile barrier) is faster.
+bool dw_use_tma(int Ho, int Wo) { return (long long)Ho * Wo >= 3600; }
+
 }  // namespace dn
 
 using namespace dn;
@@ -259,6 +266,15 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
     const int pad = (k - 1) / 2;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t s = (cudaStream_t)stream_;
+    if (dw_use_tma(Ho, Wo)) {
+        DwTiling tl;
+        int rc = dw_plan(H, W, C, k, stride, &tl);
+        if (rc) return rc;
+        CUtensorMap tm;
+        rc = dw_make_tmap(&tm, x, B, H, W, C, tl);
+        if (rc) return rc;
+        return dwconv_tma_launch(tm, tl, w, bias, y, B, H, W, C, k, stride, act, s);
+    }
     if (k == 3 && stride == 1) return launch_dw<3, 1, 4>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
     if (k == 3 && stride == 2) return launch_dw<3, 2, 2>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
     if (k == 5 && stride == 1) return launch_dw<5, 1, 4>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);

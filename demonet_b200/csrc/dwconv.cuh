@@ -1,0 +1,25 @@
+// Tiling of the TMA-fed depthwise kernel (dwconv_tma.cu), shared with the engine.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dn {
+
+constexpr int DW_THREADS = 256;
+
+struct DwTiling {
+    int CB;                 // channels per CTA chunk (multiple of 8, divides C, <= 64)
+    int THo, TWo;           // output tile
+    int spr;                // strips (TW output columns) per tile row
+    int IHT, IWT;           // input halo tile
+    int tiles_x, tiles_y, chunks;
+};
+
+bool dw_use_tma(int Ho, int Wo);
+int dw_plan(int H, int W, int C, int k, int stride, DwTiling* tl);
+int dw_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, const DwTiling& tl);
+int dwconv_tma_launch(const CUtensorMap& tm, const DwTiling& tl, const float* w, const float* bias, void* y, int B, int H,
+                      int W, int C, int k, int stride, int act, cudaStream_t stream);
+
+}  // namespace dn

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dwconv.cuh"
 #include "pwconv.cuh"
 
 using namespace dn;
@@ -42,6 +43,10 @@ struct dn_engine {
     size_t post_ws_bytes = 0;
     std::vector<CUtensorMap> tmap_a, tmap_w, tmap_y;       // per op (PW only)
     std::vector<char> has_tmap_y;
+    std::vector<CUtensorMap> tmap_dw;               // per op (DW only)
+    std::vector<DwTiling> dw_tiling;
+    std::vector<char> dw_tma;                       // per op: TMA-tiled kernel selected
+    bool dw_ready = false;
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
     cudaStream_t capture_stream = nullptr;
@@ -177,6 +182,21 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
         e->tmaps_ready = false;
     }
     DN_CHECK_CUDA(cudaMemcpy(e->weights, blob_host, bytes, cudaMemcpyHostToDevice));
+    if (!e->dw_ready) {
+        e->tmap_dw.resize(e->ops.size());
+        e->dw_tiling.resize(e->ops.size());
+        e->dw_tma.assign(e->ops.size(), 0);
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            const dn_op& o = e->ops[i];
+            if (o.kind != DN_OP_DW || !dw_use_tma(o.h_out, o.w_out)) continue;
+            e->dw_tma[i] = 1;
+            int rc = dw_plan(o.h_in, o.w_in, o.c_in, o.ksize, o.stride, &e->dw_tiling[i]);
+            if (rc) return rc;
+            rc = dw_make_tmap(&e->tmap_dw[i], buf_ptr(e, o.in_buf), e->max_batch, o.h_in, o.w_in, o.c_in, e->dw_tiling[i]);
+            if (rc) return rc;
+        }
+        e->dw_ready = true;
+    }
     if (!e->tmaps_ready && e->desc.gemm_impl == 0) {
         e->tmap_a.resize(e->ops.size());
         e->tmap_w.resize(e->ops.size());
@@ -217,6 +237,11 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                                   e->desc.image_std, buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_out, o.act, s);
                 break;
             case DN_OP_DW:
+                if (e->dw_ready && e->dw_tma[i]) {
+                    rc = dwconv_tma_launch(e->tmap_dw[i], e->dw_tiling[i], (const float*)(W + o.w_off), (const float*)(W + o.b_off),
+                                           buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize, o.stride, o.act, s);
+                    break;
+                }
                 rc = dn_dwconv(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
                                buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize, o.stride, o.act, s);
                 break;
