@@ -271,8 +271,25 @@ def main():
         pass
     dk = per_kernel[dominant]
     achieved = dk["bytes"] / (dk["ms"] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel from the committed ncu launch list of this same command
+    # (profiles/r01_ncu_launches_*.json, dram__bytes_read.sum + dram__bytes_write.sum), per launch like `achieved`
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")))
+        if cands and B == 256:
+            nl = json.load(open(cands[-1]))["kernels"]
+            fam = {"dwconv_kernel": ["dn::dwconv_kernel", "dn::dwconv_tma_kernel"], "pwconv_tc_kernel": ["dn::pwconv_tc_kernel"]}
+            names = fam.get(dominant, ["dn::" + dominant])
+            tb = sum(nl[n]["dram_bytes"] for n in names if n in nl)
+            tl = sum(nl[n]["launches"] for n in names if n in nl)
+            if tl:
+                traffic, traffic_src = tb / tl, os.path.basename(cands[-1])
+    except Exception:
+        pass
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": dk["bytes"] / dk["launches"], "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
                 "launches_per_step": dk["launches"], "avg_launch_ms": dk["ms"] / dk["launches"],
                 "share_of_step": dk["ms"] / sum_ms,
                 "tensor_tflops": dk["flops"] / (dk["ms"] * 1e-3) / 1e12 if dk["flops"] else None,

@@ -202,6 +202,7 @@ se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const flo
     const int cv = threadIdx.x % CV, sl = threadIdx.x / CV;
     if (sl < slices) {
         float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int p = sl; p < HW; p += slices) {
             float f[8];
             unpack8(xb[(long long)p * CV + cv], f);
@@ -222,6 +223,7 @@ se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const flo
     for (int j = warp; j < Cs; j += SE_THREADS / 32) {
         const float* wr = w1 + (long long)j * C;
         float s = 0.f;
+#pragma unroll 4
         for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), pooled[c], s);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -230,12 +232,14 @@ se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const flo
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += SE_THREADS) {
         float s = __ldg(b2 + c);
+#pragma unroll 8
         for (int j = 0; j < Cs; ++j) s = fmaf(__ldg(w2t + (long long)j * C + c), hidden[j], s);
         // hardsigmoid(x) = relu6(x + 3) / 6
         scale[c] = __fdiv_rn(fminf(fmaxf(s + 3.f, 0.f), 6.f), 6.f);
     }
     __syncthreads();
     const int nvec = HW * CV;
+#pragma unroll 4
     for (int i = threadIdx.x; i < nvec; i += SE_THREADS) {
         const int c0 = (i % CV) * 8;
         float f[8];

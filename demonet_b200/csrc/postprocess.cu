@@ -71,6 +71,27 @@ __device__ __forceinline__ bool iou_exceeds_fast(const float4& a, float aarea, c
 
 // in-smem bitonic sort (ascending) of n_pad (power of two) 64-bit keys by the whole CTA
 __device__ void bitonic_sort_u64(unsigned long long* keys, int n_pad) {
+    if (n_pad <= 64) {                 // one warp is enough: no block-wide barriers
+        if (threadIdx.x < 32) {
+            for (int k = 2; k <= n_pad; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = threadIdx.x; t < (n_pad >> 1); t += 32) {
+                        int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        int hi = lo | j;
+                        unsigned long long a = keys[lo], b = keys[hi];
+                        bool up = ((lo & k) == 0);
+                        if ((a > b) == up) {
+                            keys[lo] = b;
+                            keys[hi] = a;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+        return;
+    }
     for (int k = 2; k <= n_pad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
@@ -234,13 +255,14 @@ softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict_
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         float s = 0.f;
         for (int k = lane; k < K; k += 32) {
-            float e = expf(dst[k] - m);
+            float e = __expf(dst[k] - m);             // ex2.approx: |rel err| <= 2^-21 * |x - m|, i.e. <= 1e-7 absolute on a score
             dst[k] = e;
             s += e;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        for (int k = lane; k < K; k += 32) dst[k] = __fdiv_rn(dst[k], s);
+        const float inv = __fdiv_rn(1.f, s);
+        for (int k = lane; k < K; k += 32) dst[k] *= inv;
     }
     __syncthreads();
     // transposed, coalesced store of classes 1..K-1 (+ histogram of the scores above the threshold)
@@ -331,12 +353,22 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // threshold (fp32 compare, generalized_ssd.py:371) [+ legacy remove_small_boxes, box_head.py:370]
-    for (int p0 = 0; p0 < P; p0 += P2_THREADS) {
+    for (int q0 = 0; q0 < P; q0 += 4 * P2_THREADS) {
+      float sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                     // four independent loads in flight per thread
+        const int p = q0 + u * P2_THREADS + threadIdx.x;
+        sv[u] = (p < P) ? sc[p] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p0 = q0 + u * P2_THREADS;
+        if (p0 >= P) break;
         const int p = p0 + threadIdx.x;
         float s = 0.f;
         bool pass = false;
         if (p < P) {
-            s = sc[p];
+            s = sv[u];
             pass = (s > score_thresh) && (s >= round_thr);
             if (pass && min_box_size >= 0.f) {
                 const float4 q = bx[p];
@@ -348,6 +380,7 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
         if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (pass) keys[base + __popc(m & ((1u << lane) - 1u))] = make_key(s, (uint32_t)p);
+      }
     }
     __syncthreads();
     const int n = s_n;
@@ -467,36 +500,69 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
 // otherwise done[b] stays 0 and the next round goes deeper.
 // ---------------------------------------------------------------------------------------------
 constexpr int P3_MAX_PER_LANE = 8;     // supports K-1 <= 256 classes
+constexpr int P3_THREADS = 128;
+constexpr int P3_SMEM_ENTRIES = 3840;  // 30 KiB of kept entries staged in shared memory
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(P3_THREADS)
 merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts, const float* __restrict__ thr,
                   const float4* __restrict__ boxes, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                   long long* __restrict__ out_labels, int* __restrict__ out_counts, int* __restrict__ done, int P, int K,
                   int D, int round) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+    const int b = blockIdx.x;
     if (round > 0 && done[b]) return;
+    __shared__ Entry s_ent[P3_SMEM_ENTRIES];
+    __shared__ int s_off[32 * P3_MAX_PER_LANE + 1];
     const int nc = K - 1;
+    const int lane = threadIdx.x & 31;
+    for (int c = threadIdx.x; c < nc; c += P3_THREADS) s_off[c + 1] = counts[b * nc + c];
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // exclusive scan of the per-class kept counts (nc <= 256)
+        int acc = 0;
+        s_off[0] = 0;
+        for (int c = 1; c <= nc; ++c) {
+            acc += s_off[c];
+            s_off[c] = acc;
+        }
+    }
+    __syncthreads();
+    const int total = s_off[nc];
+    const bool incomplete = thr[b * NMS_ROUNDS + round] > 0.f;      // candidates below the round threshold exist
+    if (total < D && incomplete) {
+        if (threadIdx.x == 0) done[b] = 0;
+        return;
+    }
+    // stage the kept lists of the image in shared memory (class-major, each list in descending order) so
+    // that the serial merge below reads shared memory instead of chasing L2 latency
+    const bool staged = total <= P3_SMEM_ENTRIES;
+    if (staged) {
+        for (int f = threadIdx.x; f < total; f += P3_THREADS) {
+            int lo = 0, hi = nc;                  // class whose [off, off + cnt) contains f
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= f) lo = mid;
+                else hi = mid;
+            }
+            s_ent[f] = entries[((size_t)b * nc + lo) * D + (f - s_off[lo])];
+        }
+    }
+    __syncthreads();
+    __shared__ int s_sel_prior[4096];       // detections_per_img <= 4096
+    __shared__ int s_nsel;
+    if (threadIdx.x < 32) {
+    if (lane == 0) done[b] = 1;
     int pos[P3_MAX_PER_LANE], cnt[P3_MAX_PER_LANE];
+    const Entry* list[P3_MAX_PER_LANE];
     Entry head[P3_MAX_PER_LANE];
-    int total = 0;
-    const int incomplete = thr[b * NMS_ROUNDS + round] > 0.f;      // candidates below the round threshold exist
 #pragma unroll
     for (int i = 0; i < P3_MAX_PER_LANE; ++i) {
         const int c = lane + 32 * i;
         pos[i] = 0;
-        cnt[i] = (c < nc) ? counts[b * nc + c] : 0;
-        total += cnt[i];
+        cnt[i] = (c < nc) ? s_off[c + 1] - s_off[c] : 0;
+        list[i] = (c < nc) ? (staged ? s_ent + s_off[c] : entries + ((size_t)b * nc + c) * D) : entries;
         head[i].score = 0.f;
         head[i].prior = 0;
-        if (cnt[i] > 0) head[i] = entries[((size_t)b * nc + c) * D];
+        if (cnt[i] > 0) head[i] = list[i][0];
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (total < D && incomplete) {
-        if (lane == 0) done[b] = 0;
-        return;
-    }
-    if (lane == 0) done[b] = 1;
     int d = 0;
     for (; d < D; ++d) {
         unsigned long long best = 0ull;
@@ -524,21 +590,31 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
                 if (q == i) e = head[q];
             out_scores[(size_t)b * D + d] = e.score;
             out_labels[(size_t)b * D + d] = (long long)(cls + 1);
-            out_boxes[(size_t)b * D + d] = boxes[(size_t)b * P + e.prior];
+            s_sel_prior[d] = e.prior;              // the box gather happens after the serial loop, in parallel
 #pragma unroll
             for (int q = 0; q < P3_MAX_PER_LANE; ++q) {
                 if (q == i) {
                     pos[q] += 1;
-                    if (pos[q] < cnt[q]) head[q] = entries[((size_t)b * nc + cls) * D + pos[q]];
+                    if (pos[q] < cnt[q]) head[q] = list[q][pos[q]];
                 }
             }
         }
     }
-    if (lane == 0) out_counts[b] = d;
-    for (int i = d + lane; i < D; i += 32) {
-        out_scores[(size_t)b * D + i] = 0.f;
-        out_labels[(size_t)b * D + i] = 0;
-        out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) {
+        out_counts[b] = d;
+        s_nsel = d;
+    }
+    }
+    __syncthreads();
+    const int nsel = s_nsel;
+    for (int i = threadIdx.x; i < D; i += P3_THREADS) {
+        if (i < nsel) {
+            out_boxes[(size_t)b * D + i] = boxes[(size_t)b * P + s_sel_prior[i]];
+        } else {
+            out_scores[(size_t)b * D + i] = 0.f;
+            out_labels[(size_t)b * D + i] = 0;
+            out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
 }
 
@@ -699,7 +775,7 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
                     DN_CHECK_LAUNCH();
                 }
                 if (phase == 2 || !ms3) {
-                    merge_topd_kernel<<<B, 32, 0, stream>>>(entries, counts, thr, boxes, (float4*)out_boxes, out_scores,
+                    merge_topd_kernel<<<B, P3_THREADS, 0, stream>>>(entries, counts, thr, boxes, (float4*)out_boxes, out_scores,
                                                             (long long*)out_labels, out_counts, done, P, K, D, r);
                     DN_CHECK_LAUNCH();
                 }
