@@ -47,8 +47,8 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_rate(n_images, steps, warmup):
     import torch
-    from oracle import boxes_np, net_ref, weights
-    from demonet_b200 import plan as dplan
+    from oracle import net_ref              # the CPU leg is the one place bench.py executes oracle/
+    from demonet_b200 import plan as dplan, seeded as weights
     import demonet_b200
     cores = os.cpu_count() or 1
     try:
@@ -173,7 +173,7 @@ def main():
     import torch.distributed as dist
     import demonet_b200
     from demonet_b200 import _C
-    from oracle import weights            # seeded re-init recipe + synthetic images (bench infrastructure)
+    from demonet_b200 import seeded as weights      # seeded re-init recipe + synthetic images
     import ctypes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -310,7 +310,7 @@ def main():
             "config": {"workload": "ssdlite320_mobilenet_v3_large, 91 classes, 320x320, batch %d per GPU, bf16 activations, "
                                    "forward + softmax/decode/top-k/NMS/top-300 (BASELINE.json configs[1])" % B,
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (image shards, final NCCL "
-                       "all-gather of detections)" % world, "weights": "seeded re-init 1234 (oracle/weights.py)",
+                       "all-gather of detections)" % world, "weights": "seeded re-init 1234 (demonet_b200/seeded.py)",
                        "images": "torch.rand seed 1+rank", "l2": "inputs larger than L2 (%.0f MB fp32 images per step; "
                        "activation arena %.1f GB)" % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
                        "cuda_graph": True},

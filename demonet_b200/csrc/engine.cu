@@ -408,6 +408,6 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
     return rc;
 }
 
-// layers + softmax/decode + class sort + 3 rounds x (prefix select, NMS, merge)
-extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 11 : 0; }
+// layers + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS, CTA NMS, merge)
+extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 14 : 0; }
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) { return e ? e->device_bytes : 0; }

@@ -409,6 +409,7 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
 // deeper (the last round processes everything).
 // ---------------------------------------------------------------------------------------------
 constexpr int SEL_THREADS = 256;
+constexpr int NMS_WARP_MAX = 96;       // class lists up to this length run on one warp, longer ones on a CTA
 
 // ---------------------------------------------------------------------------------------------
 // P2b: greedy NMS, one WARP per (image, class) over this round's candidate list; stops at D kept.
@@ -438,6 +439,7 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
     const float4* bx = boxes + (size_t)b * P;
     Entry* dst = out_entries + (size_t)prob * D;
     const int q = prefix[prob];
+    if (q > NMS_WARP_MAX) return;                     // long lists are handled by class_nms_cta_kernel
     int nk = 0;
     for (int c0 = 0; c0 < q && nk < D; c0 += 32) {
         const int cnt = min(32, q - c0);
@@ -491,6 +493,63 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
         __syncwarp();
     }
     if (lane == 0) out_counts[prob] = nk;
+}
+
+// Long class lists (a dominant class easily holds a few hundred candidates) would make their warp the
+// straggler of the whole launch, so they get a full CTA: every warp tests the 32-candidate chunk against a
+// slice of the kept list (nms_consume_chunk), warp 0 resolves the chunk.
+constexpr int NMS_CTA_THREADS = 256;
+__global__ void __launch_bounds__(NMS_CTA_THREADS)
+class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ prefix,
+                     const float4* __restrict__ boxes, Entry* __restrict__ out_entries, int* __restrict__ out_counts,
+                     const int* __restrict__ done, int P, int K, int cap, float thr_up, int D, int round) {
+    const int nc = K - 1;
+    const int prob = blockIdx.x;
+    const int b = prob / nc;
+    if (round > 0 && done[b]) return;
+    const int q = prefix[prob];
+    if (q <= NMS_WARP_MAX) return;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float4* kept_box = reinterpret_cast<float4*>(s_raw);               // [D]
+    float* kept_area = reinterpret_cast<float*>(kept_box + D);         // [D]
+    __shared__ int s_nkept;
+    __shared__ unsigned int s_dead;
+    __shared__ float4 s_chunk_box[32];
+    __shared__ float s_chunk_area[32];
+    __shared__ unsigned long long s_chunk_key[32];
+    if (threadIdx.x == 0) {
+        s_nkept = 0;
+        s_dead = 0u;
+    }
+    __syncthreads();
+    NmsState st{kept_box, kept_area, s_chunk_box, s_chunk_area, &s_dead, &s_nkept};
+    const unsigned long long* keys = cand_keys + (size_t)prob * cap;
+    const float4* bx = boxes + (size_t)b * P;
+    Entry* dst = out_entries + (size_t)prob * D;
+    const int lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < q; c0 += 32) {
+        const int cnt = min(32, q - c0);
+        if (threadIdx.x < cnt) {
+            const unsigned long long kk = keys[c0 + threadIdx.x];
+            const float4 v = bx[key_index(kk)];
+            s_chunk_key[threadIdx.x] = kk;
+            s_chunk_box[threadIdx.x] = v;
+            s_chunk_area[threadIdx.x] = box_area(v);
+        }
+        __syncthreads();
+        const int nk_before = s_nkept;
+        const unsigned int taken = nms_consume_chunk(st, cnt, thr_up, D);
+        if (threadIdx.x < 32 && ((taken >> lane) & 1u)) {
+            const unsigned long long kk = s_chunk_key[lane];
+            Entry e;
+            e.score = key_score(kk);
+            e.prior = (int)key_index(kk);
+            dst[nk_before + __popc(taken & ((1u << lane) - 1u))] = e;
+        }
+        if (s_nkept >= D) break;             // uniform: written before the closing barrier of the consumer
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_counts[prob] = s_nkept;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,7 +705,7 @@ static int next_pow2(int v) {
 // for the images where fewer than D detections survived (-1 = everything)
 static RoundTargets round_targets(int D) {
     RoundTargets r;
-    r.t[0] = D * 8 > 2048 ? D * 8 : 2048;
+    r.t[0] = D * 4 > 1024 ? D * 4 : 1024;
     r.t[1] = r.t[0] * 8;
     r.t[2] = 0;               // everything
     return r;
@@ -737,6 +796,11 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
         DN_CHECK_CUDA(cudaFuncSetAttribute(class_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
         cfg_sort = smem_sort;
     }
+    static size_t cfg_cta = 48 * 1024;
+    if ((size_t)D * 20 > cfg_cta) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(class_nms_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 20));
+        cfg_cta = (size_t)D * 20;
+    }
     if (smem_nms > cfg_nms) {
         DN_CHECK_CUDA(cudaFuncSetAttribute(class_nms_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
         cfg_nms = smem_nms;
@@ -772,6 +836,9 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
                     DN_CHECK_LAUNCH();
                     class_nms_warp_kernel<<<(unsigned)ceil_div<long long>(problems, nms_warps), nms_warps * 32, smem_nms,
                                             stream>>>(cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
+                    DN_CHECK_LAUNCH();
+                    class_nms_cta_kernel<<<(unsigned)problems, NMS_CTA_THREADS, (size_t)D * 20, stream>>>(
+                        cand, ccount, boxes, entries, counts, done, P, K, cap, thr_up, D, r);
                     DN_CHECK_LAUNCH();
                 }
                 if (phase == 2 || !ms3) {

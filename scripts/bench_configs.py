@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 import demonet_b200                                   # noqa: E402
 from demonet_b200 import _C, plan as dplan            # noqa: E402
 from demonet_b200.module import make_post_params      # noqa: E402
-from oracle import weights                            # noqa: E402
+from demonet_b200 import seeded as weights            # noqa: E402
 
 
 def timed(fn, steps, warmup):
