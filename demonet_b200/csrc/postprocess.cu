@@ -193,6 +193,7 @@ __device__ unsigned int nms_consume_chunk(NmsState& st, int cand_cnt, float thr_
 // ---------------------------------------------------------------------------------------------
 constexpr int P1_ROWS = 32;
 constexpr int P1_THREADS = 256;
+constexpr int P1_MAX_PER_LANE = 3;     // register path of the softmax covers K <= 96 (91 COCO / 21 VOC classes)
 // Per-image histogram of the foreground scores over a monotone key (float bits >> 17: 64 bins per
 // binade, from 2^-24 up to 1.0).  It only steers how deep the lazy NMS rounds go -- any threshold is
 // exact -- so the resolution (1.5 % in score) is irrelevant for correctness.
@@ -211,10 +212,10 @@ __global__ void __launch_bounds__(P1_THREADS)
 softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict__ bbox,
                       const float* __restrict__ anchors, float* __restrict__ scores_t,
                       float4* __restrict__ boxes, int* __restrict__ hist, int P, int K, dn_postprocess_params prm) {
-    extern __shared__ float s_tile[];                    // [P1_ROWS][K + 1]
+    extern __shared__ float s_tile[];                    // [P1_ROWS][ld], ld odd -> conflict-free column reads
     __shared__ int s_hist[HIST_BINS];
     for (int i = threadIdx.x; i < HIST_BINS; i += P1_THREADS) s_hist[i] = 0;
-    const int ld = K + 1;
+    const int ld = K | 1;
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * P1_ROWS;
     const int rows = min(P1_ROWS, P - p0);
@@ -241,28 +242,55 @@ softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict_
         boxes[(size_t)b * P + p] = o;
     }
 
-    // softmax, one warp per row
+    // softmax, one warp per row; a lane keeps its (up to P1_MAX_PER_LANE) elements in registers and writes
+    // the finished probabilities to shared memory once
     for (int r = warp; r < rows; r += P1_THREADS / 32) {
         const float* src = logits + ((size_t)b * P + p0 + r) * K;
         float* dst = s_tile + r * ld;
-        float m = -FLT_MAX;
-        for (int k = lane; k < K; k += 32) {
-            float v = src[k];
-            dst[k] = v;
-            m = fmaxf(m, v);
-        }
+        if (K <= 32 * P1_MAX_PER_LANE) {
+            float v[P1_MAX_PER_LANE];
+            float m = -FLT_MAX;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        float s = 0.f;
-        for (int k = lane; k < K; k += 32) {
-            float e = __expf(dst[k] - m);             // ex2.approx: |rel err| <= 2^-21 * |x - m|, i.e. <= 1e-7 absolute on a score
-            dst[k] = e;
-            s += e;
-        }
+            for (int i = 0; i < P1_MAX_PER_LANE; ++i) {
+                const int k = lane + 32 * i;
+                v[i] = (k < K) ? src[k] : -FLT_MAX;
+                m = fmaxf(m, v[i]);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const float inv = __fdiv_rn(1.f, s);
-        for (int k = lane; k < K; k += 32) dst[k] *= inv;
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < P1_MAX_PER_LANE; ++i) {
+                // ex2.approx: |rel err| <= 2^-21 * |x - m|, i.e. <= 1e-7 absolute on a score
+                v[i] = (lane + 32 * i < K) ? __expf(v[i] - m) : 0.f;
+                s += v[i];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = __fdiv_rn(1.f, s);
+#pragma unroll
+            for (int i = 0; i < P1_MAX_PER_LANE; ++i)
+                if (lane + 32 * i < K) dst[lane + 32 * i] = v[i] * inv;
+        } else {
+            float m = -FLT_MAX;
+            for (int k = lane; k < K; k += 32) {
+                float v = src[k];
+                dst[k] = v;
+                m = fmaxf(m, v);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float s = 0.f;
+            for (int k = lane; k < K; k += 32) {
+                float e = __expf(dst[k] - m);
+                dst[k] = e;
+                s += e;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = __fdiv_rn(1.f, s);
+            for (int k = lane; k < K; k += 32) dst[k] *= inv;
+        }
     }
     __syncthreads();
     // transposed, coalesced store of classes 1..K-1 (+ histogram of the scores above the threshold)
