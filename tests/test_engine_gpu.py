@@ -201,3 +201,36 @@ def test_v2_legacy_hub_entry():
                                     scores=torch.softmax(cls[0].cpu(), -1).numpy())
     same = (d["labels"].cpu().numpy() == o["labels"]) & (np.abs(d["scores"].cpu().numpy() - o["scores"]) < 3e-6)
     assert same.mean() >= 0.97
+
+
+def test_no_detections_and_batch_growth():
+    """score_thresh = 1.0 can never be exceeded by a softmax score -> empty results (test_onnx.py:125-133
+    'image with no detections'); a larger batch afterwards re-creates the engine transparently."""
+    model, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large, score_thresh=1.0)
+    x = weights.synthetic_images(7, 320).cuda()
+    out = model([x[0], x[1]])
+    assert len(out) == 2
+    for d in out:
+        assert d["boxes"].shape == (0, 4) and d["scores"].shape == (0,) and d["labels"].shape == (0,)
+        assert d["labels"].dtype == torch.int64
+    model2, _ = _model(demonet_b200.ssdlite320_mobilenet_v3_large)
+    a = model2([x[0]])
+    b = model2(list(x))                              # max batch grows 1 -> 7
+    assert len(b) == 7 and torch.equal(a[0]["scores"], b[0]["scores"]) and torch.equal(a[0]["boxes"], b[0]["boxes"])
+    c = model2(x)                                    # a batched 4-D tensor is accepted like a list
+    assert torch.equal(c[6]["labels"], b[6]["labels"])
+    assert model2([]) == []
+
+
+def test_default_box_generator_op():
+    from demonet_b200 import ops
+
+    class _IL:                                        # minimal ImageList stand-in (tensors, image_sizes)
+        def __init__(self, t):
+            self.tensors, self.image_sizes = t, [tuple(t.shape[-2:])] * t.shape[0]
+    gen = ops.DefaultBoxGenerator([[2, 3]] * 6, min_ratio=0.2, max_ratio=0.95)
+    feats = [torch.zeros(2, 8, s, s, device="cuda") for s in (20, 10, 5, 3, 2, 1)]
+    out = gen(_IL(torch.zeros(2, 3, 320, 320, device="cuda")), feats)
+    want = boxes_np.default_boxes([(s, s) for s in (20, 10, 5, 3, 2, 1)], (320, 320))
+    assert len(out) == 2 and np.array_equal(out[0].cpu().numpy(), want)
+    assert gen.num_anchors_per_location() == [6] * 6

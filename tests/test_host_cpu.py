@@ -123,3 +123,22 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.dn_batched_nms_workspace_bytes(36000) > 36000 * 8
     with pytest.raises(RuntimeError):
         demonet_b200.ops.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)       # CPU tensors: no fallback
+
+
+def test_default_box_generator_table_cpu():
+    from demonet_b200 import ops
+    gen = ops.DefaultBoxGenerator([[2, 3]] * 6, min_ratio=0.2, max_ratio=0.95)
+    grids = [(19, 19), (10, 10), (5, 5), (3, 3), (2, 2), (1, 1)]
+    t = gen.table(grids, (300, 300), "cpu")
+    assert np.array_equal(t.numpy(), boxes_np.default_boxes(grids, (300, 300)))
+    assert gen.table(grids, (300, 300), "cpu") is t          # cached
+
+
+def test_pixel_packing_rule():
+    p = dplan.plan_ssdlite320_mobilenet_v3_large()
+    packed = {i: dplan.pw_pack_factor(L) for i, L in enumerate(p.layers) if L.kind == "pw"}
+    assert packed[2] == 4 and packed[3] == 4          # 160x160, 16 input channels
+    assert all(f == 1 for i, f in packed.items() if p.layers[i].head)       # strided head outputs are never packed
+    for i, f in packed.items():
+        L = p.layers[i]
+        assert (L.h_in * L.w_in) % f == 0 and (f == 1 or f * L.cout <= 256)
