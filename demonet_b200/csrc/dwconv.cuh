@@ -22,4 +22,11 @@ int dw_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, co
 int dwconv_tma_launch(const CUtensorMap& tm, const DwTiling& tl, const float* w, const float* bias, void* y, int B, int H,
                       int W, int C, int k, int stride, int act, cudaStream_t stream);
 
+// TMA-tiled stem (stem_tma.cu)
+bool stem_can_tma(const void* images, int W);
+bool stem_norm_ok(const float* std3);
+int stem_make_tmap(CUtensorMap* map, const float* images, int B, int H, int W);
+int stem_tma_launch(const CUtensorMap& tm, const float* w, const float* bias, const float* mean3, const float* std3, void* y,
+                    int B, int H, int W, int Cout, int act, cudaStream_t stream);
+
 }  // namespace dn

@@ -282,7 +282,7 @@ def pw_pack_factor(L: Layer) -> int:
     def k_waste(k):            # padded K (64-wide k-blocks) per useful K
         return ((k + 63) // 64 * 64) / k
     for p in (4, 2):
-        if p * L.cout <= 256 and hw % p == 0 and p * L.cin <= 192 and k_waste(p * L.cin) <= k_waste(L.cin):
+        if p * L.cout <= (256 if p == 4 else 512) and hw % p == 0 and p * L.cin <= 192 and k_waste(p * L.cin) <= k_waste(L.cin):
             return p
     return 1
 

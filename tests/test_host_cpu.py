@@ -141,4 +141,23 @@ def test_pixel_packing_rule():
     assert all(f == 1 for i, f in packed.items() if p.layers[i].head)       # strided head outputs are never packed
     for i, f in packed.items():
         L = p.layers[i]
-        assert (L.h_in * L.w_in) % f == 0 and (f == 1 or f * L.cout <= 256)
+        assert (L.h_in * L.w_in) % f == 0 and (f == 1 or f * L.cout <= 512)
+
+
+def test_stem_division_shortcut_is_exact():
+    """stem_tma.cu replaces (x - mean) / std by q0 = RN(d * r), e = fma(-q0, std, d), q = fma(e, r, q0) with
+    r = RN(1 / std).  Emulated here with exact float64 / long double intermediates: bit-identical to the
+    float32 division the reference performs (transform.py:137)."""
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.random(400_000, dtype=np.float32), (np.arange(256) / 255).astype(np.float32),
+                         (rng.standard_normal(100_000) * 3).astype(np.float32)])
+    for m, s in [(0.485, 0.229), (0.456, 0.224), (0.406, 0.225), (0.5, 0.5), (0.3, 0.77777)]:
+        m, s = np.float32(m), np.float32(s)
+        r = np.float32(1.0 / np.float64(s))
+        d = (xs - m).astype(np.float32)
+        q0 = (d * r).astype(np.float32)
+        e = np.float64(d) - np.float64(q0) * np.float64(s)
+        e32 = e.astype(np.float32)
+        assert np.all(e32.astype(np.float64) == e)                    # the remainder is exactly representable
+        q = (np.longdouble(q0) + np.longdouble(e32) * np.longdouble(r)).astype(np.float32)
+        assert np.array_equal(q.view(np.int32), (d / s).astype(np.float32).view(np.int32))
