@@ -3,6 +3,8 @@
 //   * stem: input normalisation + dense 3x3 stride-2 conv + folded BN + activation     (dn_stem_conv)
 //   * squeeze-excitation, applied in place                                              (dn_se_inplace)
 // Activations are NHWC bf16, 8 channels (16 B) per thread access, fp32 accumulation.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dwconv.cuh"
 
@@ -250,11 +252,24 @@ se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const flo
     }
 }
 
-// Tile strategy per layer shape (measured on B200, profiles/r01_dw_tma_vs_direct.txt): the TMA-fed
-// shared-memory tiles win on the large feature maps (>= 80x80 outputs: 2.8-5.8 TB/s vs 2.0-4.8 TB/s), where a
-// halo tile amortises over many outputs; on the small maps the register-tiled kernel (L1-served halos, no
-// per-tile barrier) is faster.
-bool dw_use_tma(int Ho, int Wo) { return (long long)Ho * Wo >= 3600; }
+// Kernel per layer shape (measured on B200, profiles/r01_dw_*.txt): stride-1 layers with at least 8 rows run on the
+// TMA-fed row stream (dwconv_stream.cu, 3.0-4.0 TB/s); of the rest, the TMA-fed shared-memory tiles win on the
+// large maps (>= 60x60 outputs) and the register-tiled direct kernel on the small ones.
+DwImpl dw_choose(int H, int W, int C, int k, int stride) {
+    static const int forced = [] {                  // measurement aid: DN_DW_IMPL=1|2|4 forces one kernel where it applies
+        const char* e = getenv("DN_DW_IMPL");
+        return e ? atoi(e) : 0;
+    }();
+    const int pad = (k - 1) / 2;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    DwStream sp;
+    const bool stream_ok = H >= 8 && dw_stream_plan(H, W, C, k, stride, &sp);
+    const DwImpl tiled = (long long)Ho * Wo >= 3600 ? DW_TMA : DW_DIRECT;
+    if (forced == DW_DIRECT) return DW_DIRECT;
+    if (forced == DW_TMA) return DW_TMA;
+    if (forced == DW_STREAM) return stream_ok ? DW_STREAM : tiled;
+    return stream_ok ? DW_STREAM : tiled;
+}
 
 }  // namespace dn
 
@@ -270,7 +285,16 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
     const int pad = (k - 1) / 2;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t s = (cudaStream_t)stream_;
-    if (dw_use_tma(Ho, Wo)) {
+    const DwImpl impl = dw_choose(H, W, C, k, stride);
+    if (impl == DW_STREAM) {
+        DwStream sp;
+        DN_REQUIRE(dw_stream_plan(H, W, C, k, stride, &sp), DN_ERR_UNSUPPORTED, "no stream plan");
+        CUtensorMap tm;
+        int rc = dw_stream_make_tmap(&tm, x, B, H, W, C, k, sp);
+        if (rc) return rc;
+        return dwconv_stream_launch(tm, sp, w, bias, y, B, H, W, C, k, act, s);
+    }
+    if (impl == DW_TMA) {
         DwTiling tl;
         int rc = dw_plan(H, W, C, k, stride, &tl);
         if (rc) return rc;

@@ -16,11 +16,30 @@ struct DwTiling {
     int tiles_x, tiles_y, chunks;
 };
 
-bool dw_use_tma(int Ho, int Wo);
 int dw_plan(int H, int W, int C, int k, int stride, DwTiling* tl);
 int dw_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, const DwTiling& tl);
 int dwconv_tma_launch(const CUtensorMap& tm, const DwTiling& tl, const float* w, const float* bias, void* y, int B, int H,
                       int W, int C, int k, int stride, int act, cudaStream_t stream);
+
+// TMA-fed row stream (dwconv_stream.cu), stride 1
+constexpr int DWS_MAX_THREADS = 288;        // producer warp + up to 8 consumer warps
+struct DwStream {
+    int CB;                 // channels per block (multiple of 8, divides C)
+    int ncb;                // column blocks (TW output columns each) across the width
+    int IW;                 // staged row width in pixels (ncb * TW + k - 1)
+    int ncblk;              // channel blocks
+    int nst;                // ring stages (k input rows each)
+    int stage_bytes, stage_stride;
+    int threads;
+    size_t smem;
+};
+bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp);
+int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
+int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
+                         int W, int C, int k, int act, cudaStream_t stream);
+// which depthwise kernel a layer shape runs on
+enum DwImpl { DW_DIRECT = 1, DW_TMA = 2, DW_STREAM = 4 };
+DwImpl dw_choose(int H, int W, int C, int k, int stride);
 
 // TMA-tiled stem (stem_tma.cu)
 bool stem_can_tma(const void* images, int W);

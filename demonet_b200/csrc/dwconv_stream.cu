@@ -1,0 +1,303 @@
+// Depthwise k x k stride-1 stencil as a TMA-fed ROW STREAM for sm_100a.
+// Reference: ConvBNActivation(groups=C), demonet/models/mobilenetv2.py:32-55 (see dn_dwconv).
+//
+// CTA c works on channel block c % ncblk for its whole life (taps and bias staged once); the output rows of all
+// images form one long stream per channel block and the CTAs of a block own equal contiguous shares of it, so the
+// GPU is balanced to within one row, a CTA pays the k-1 halo rows once per image it touches, and the CTAs of the
+// different channel blocks walk the same images at the same time (their interleaved reads meet in L2).  Inside a CTA, warp 0 is the producer: one thread issues cp.async.bulk.tensor.4d loads of k input
+// rows x the full padded width x CB channels into a ring of shared-memory stages (zero padding = the tensor
+// map's out-of-bounds fill, no boundary branches), running ahead of the consumers by the depth of the ring, so
+// the bytes in flight are set by shared memory rather than by registers.  Consumer thread = 4 channels x TW
+// output columns, walking down the rows: each staged input vector is read and unpacked to fp32 once and
+// scattered into a ring of k output-row accumulators in registers (packed FFMA2); the row whose last input row
+// just arrived is activated, packed to bf16 and stored, and its slot restarts from the bias.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "dwconv.cuh"
+
+namespace dn {
+
+__device__ __forceinline__ uint32_t dws_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int ACT>
+__device__ __forceinline__ float dws_act(float v) {
+    if (ACT == DN_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == DN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    if (ACT == DN_ACT_HSWISH) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));      // x * relu6(x + 3) / 6
+    return v;
+}
+
+__device__ __forceinline__ void dws_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+// taps are re-read from shared memory at every use: `volatile` keeps ptxas from hoisting all k*k of them into
+// registers (25 x 4 for a 5x5), which costs the occupancy this kernel lives on
+__device__ __forceinline__ float4 dws_lds128(uint32_t addr) {
+    float4 f;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(addr));
+    return f;
+}
+
+__device__ __forceinline__ uint2 dws_lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+constexpr int DWS_MAX_STAGES = 8;
+
+template <int KS, int TW, int ACT, int NT>
+__global__ void __launch_bounds__(NT, NT <= 160 ? 3 : 1)
+dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w, const float* __restrict__ bias,
+                     uint2* __restrict__ y, DwStream sp, int B, int H, int W, int C) {
+    constexpr int P = KS / 2, TWIN = TW + KS - 1;
+    extern __shared__ __align__(128) unsigned char dws_smem[];
+    __shared__ uint64_t full[DWS_MAX_STAGES], empty[DWS_MAX_STAGES];
+    unsigned char* stages = dws_smem;
+    float* wsm = reinterpret_cast<float*>(dws_smem + (size_t)sp.nst * sp.stage_stride);     // [KS*KS][CB]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_cons_warps = (blockDim.x >> 5) - 1;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < sp.nst; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dws_u32(&full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dws_u32(&empty[s])), "r"(n_cons_warps) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // this CTA's channel block and its share of that block's output-row stream (B * H rows)
+    const int cblk = blockIdx.x % sp.ncblk;
+    const long long T = (long long)B * H;
+    const int part = blockIdx.x / sp.ncblk, parts = gridDim.x / sp.ncblk;
+    const long long g_begin = T * part / parts, g_end = T * (part + 1) / parts;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t seq = 0;
+            for (long long g = g_begin; g < g_end;) {
+                const int b = (int)(g / H), o0 = (int)(g - (long long)b * H);
+                const int o1 = (int)min((long long)H, o0 + (g_end - g));
+                const int groups = (o1 - o0 + 2 * P + KS - 1) / KS;
+                for (int gi = 0; gi < groups; ++gi, ++seq) {
+                    const uint32_t slot = seq % sp.nst, round = seq / sp.nst;
+                    if (round > 0) dws_wait(dws_u32(&empty[slot]), (round - 1) & 1u);
+                    const uint32_t bar = dws_u32(&full[slot]);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sp.stage_bytes)
+                                 : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+                        "[%2];" ::"r"(dws_u32(stages + (size_t)slot * sp.stage_stride)),
+                        "l"(&tmap_x), "r"(bar), "r"(cblk * sp.CB), "r"(-P), "r"(o0 - P + gi * KS), "r"(b)
+                        : "memory");
+                }
+                g += o1 - o0;
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    const int ct = threadIdx.x - 32;
+    const int nqb = sp.CB >> 2;                      // channel quads per block
+    const int q = ct % nqb, cb = ct / nqb;
+    const bool active = cb < sp.ncb;
+    const int ow0 = cb * TW;
+    const int nq = C >> 2;
+    const int row_bytes = sp.IW * sp.CB * 2;
+    const int n_cons = n_cons_warps * 32;
+
+    // taps and bias of this channel block, staged once
+    // smem layout [channel quad][tap][4]: a thread's k*k taps are contiguous, so every tap is base + immediate offset
+    // (no per-tap address registers); lanes are k*k*16 bytes apart = 4 banks mod 32, conflict-free for LDS.128
+    for (int i = ct; i < KS * KS * sp.CB; i += n_cons) {
+        const int c = i % sp.CB, t = i / sp.CB;
+        wsm[((c >> 2) * (KS * KS) + t) * 4 + (c & 3)] = __ldg(w + t * C + cblk * sp.CB + c);
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
+    const uint32_t wq = dws_u32(wsm + q * (KS * KS) * 4);
+    float2 b01, b23;
+    {
+        const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + cblk * sp.CB + (active ? q : 0) * 4));
+        b01 = make_float2(bs.x, bs.y), b23 = make_float2(bs.z, bs.w);
+    }
+    const uint32_t stage0 = dws_u32(stages) + (uint32_t)((ow0 * sp.CB + q * 4) * 2);
+    const uint32_t cstep = (uint32_t)sp.CB * 2;     // bytes between staged pixels
+    float2 acc[KS][TW][2];                          // ring of k output rows (slot = row mod k)
+#pragma unroll
+    for (int s2 = 0; s2 < KS; ++s2)
+#pragma unroll
+        for (int p = 0; p < TW; ++p) acc[s2][p][0] = b01, acc[s2][p][1] = b23;
+    uint32_t seq = 0;
+    for (long long g = g_begin; g < g_end;) {
+        const int b = (int)(g / H), o0 = (int)(g - (long long)b * H);
+        const int o1 = (int)min((long long)H, o0 + (g_end - g));
+        const int n_steps = o1 - o0 + 2 * P;
+        const int groups = (n_steps + KS - 1) / KS;
+        uint2* yrow = y + ((long long)b * H * W) * nq + (cblk * nqb + q) + ((long long)o0 * W + ow0) * nq;
+
+        for (int gi = 0; gi < groups; ++gi, ++seq) {
+            const uint32_t slot = seq % sp.nst, round = seq / sp.nst;
+            dws_wait(dws_u32(&full[slot]), round & 1u);
+            if (active) {
+                const uint32_t st = stage0 + slot * (uint32_t)sp.stage_stride;
+                uint2 raw[TWIN];
+#pragma unroll
+                for (int j = 0; j < TWIN; ++j) raw[j] = dws_lds64(st + j * cstep);
+#pragma unroll
+                for (int u = 0; u < KS; ++u) {
+                    const int i = gi * KS + u;
+                    if (i < n_steps) {
+                        const int ih = o0 - P + i;
+                        float2 in[TWIN][2];
+#pragma unroll
+                        for (int j = 0; j < TWIN; ++j) in[j][0] = bf16x2_to_float2(raw[j].x), in[j][1] = bf16x2_to_float2(raw[j].y);
+                        if (u + 1 < KS) {                              // next staged row, in flight during this row's math
+#pragma unroll
+                            for (int j = 0; j < TWIN; ++j) raw[j] = dws_lds64(st + (u + 1) * (uint32_t)row_bytes + j * cstep);
+                        }
+                        constexpr int NEWEST = KS - 1;                 // output row that receives its first contribution
+                        if ((unsigned)ih < (unsigned)H) {
+#pragma unroll
+                            for (int m = 0; m < KS; ++m) {             // output row o0 + i - 2P + m takes kernel row 2P - m
+                                const int kh = 2 * P - m;
+                                const int sl = (u + 1 + m) % KS;
+#pragma unroll
+                                for (int kw = 0; kw < KS; ++kw) {
+                                    const float4 f = dws_lds128(wq + (kh * KS + kw) * 16);
+                                    const float2 w0 = make_float2(f.x, f.y), w1 = make_float2(f.z, f.w);
+#pragma unroll
+                                    for (int p = 0; p < TW; ++p) {
+                                        const bool first = (m == NEWEST) && (kw == 0);      // starts from the bias
+                                        acc[sl][p][0] = __ffma2_rn(in[p + kw][0], w0, first ? b01 : acc[sl][p][0]);
+                                        acc[sl][p][1] = __ffma2_rn(in[p + kw][1], w1, first ? b23 : acc[sl][p][1]);
+                                    }
+                                }
+                            }
+                        } else {                                       // a row above / below the image contributes nothing
+#pragma unroll
+                            for (int p = 0; p < TW; ++p) acc[(u + 1 + NEWEST) % KS][p][0] = b01, acc[(u + 1 + NEWEST) % KS][p][1] = b23;
+                        }
+                        if (i >= 2 * P) {                              // output row o0 + i - 2P is complete
+                            const int sl = (u + 1) % KS;
+#pragma unroll
+                            for (int p = 0; p < TW; ++p) {
+                                if (ow0 + p < W) {
+                                    uint2 v;
+                                    v.x = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][0].x), dws_act<ACT>(acc[sl][p][0].y));
+                                    v.y = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][1].x), dws_act<ACT>(acc[sl][p][1].y));
+                                    yrow[(long long)p * nq] = v;
+                                }
+                            }
+                            yrow += (long long)W * nq;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dws_u32(&empty[slot])) : "memory");
+        }
+        g += o1 - o0;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+template <int KS>
+static constexpr int dws_tw() { return KS == 3 ? 4 : 2; }
+
+bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
+    if (stride != 1 || (k != 3 && k != 5) || C % 8 != 0 || H < 4) return false;
+    const int TW = (k == 3) ? dws_tw<3>() : dws_tw<5>();
+    const int P = k / 2;
+    const int ncb = (W + TW - 1) / TW;
+    const int IW = ncb * TW + 2 * P;
+    if (IW > 256) return false;
+    // channel block: consumers (CB/4 x ncb threads) should fill about four warps -- small CTAs, several per SM
+    int best = 0, best_thr = 0;
+    for (int cb = 8; cb <= C; cb += 8) {
+        if (C % cb) continue;
+        const int thr = (cb / 4) * ncb;
+        if (thr > DWS_MAX_THREADS - 32) break;
+        const bool good = thr >= 96 && thr <= 128, best_good = best_thr >= 96 && best_thr <= 128;
+        if (!best || (good && !best_good) || (good == best_good)) best = cb, best_thr = thr;     // later (larger) wins ties
+    }
+    if (!best) return false;
+    sp->CB = best;
+    sp->ncb = ncb;
+    sp->IW = IW;
+    sp->ncblk = C / best;
+    sp->stage_bytes = k * IW * best * 2;
+    sp->stage_stride = (sp->stage_bytes + 127) & ~127;
+    int nst = (60 * 1024) / sp->stage_stride;             // ~60 KB of ring per CTA, three CTAs per SM
+    nst = nst < 3 ? 3 : (nst > DWS_MAX_STAGES ? DWS_MAX_STAGES : nst);
+    sp->nst = nst;
+    sp->threads = 32 + (((best / 4) * ncb + 31) / 32) * 32;
+    sp->smem = (size_t)nst * sp->stage_stride + (size_t)k * k * best * 4;
+    return sp->smem <= 200 * 1024;
+}
+
+int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp) {
+    DwTiling tl{};
+    tl.CB = sp.CB, tl.IWT = sp.IW, tl.IHT = k;
+    return dw_make_tmap(map, x, B, H, W, C, tl);
+}
+
+template <int KS, int ACT, int NT>
+static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, cudaStream_t stream) {
+    auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), ACT, NT>;
+    static size_t configured = 0;
+    if (sp.smem > configured) {
+        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    int per_sm = 0;
+    DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, sp.smem));
+    if (per_sm < 1) per_sm = 1;
+    // a multiple of the channel-block count, at most one CTA per output row of a block
+    long long parts = (long long)per_sm * sm_count() / sp.ncblk;
+    if (parts < 1) parts = 1;
+    if (parts > (long long)B * H) parts = (long long)B * H;
+    const long long grid = parts * sp.ncblk;
+    kern<<<(unsigned)grid, sp.threads, sp.smem, stream>>>(tm, w, bias, (uint2*)y, sp, B, H, W, C);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+template <int KS, int ACT>
+static int dws_launch_a(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, cudaStream_t stream) {
+    // small CTAs (<= 4 consumer warps) are compiled for three per SM; wide rows with few channels need up to 8
+    if (sp.threads <= 160) return dws_launch_n<KS, ACT, 160>(tm, sp, w, bias, y, B, H, W, C, stream);
+    return dws_launch_n<KS, ACT, DWS_MAX_THREADS>(tm, sp, w, bias, y, B, H, W, C, stream);
+}
+
+template <int KS>
+static int dws_launch_k(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, int act, cudaStream_t stream) {
+    switch (act) {
+        case DN_ACT_NONE: return dws_launch_a<KS, DN_ACT_NONE>(tm, sp, w, bias, y, B, H, W, C, stream);
+        case DN_ACT_RELU: return dws_launch_a<KS, DN_ACT_RELU>(tm, sp, w, bias, y, B, H, W, C, stream);
+        case DN_ACT_RELU6: return dws_launch_a<KS, DN_ACT_RELU6>(tm, sp, w, bias, y, B, H, W, C, stream);
+        case DN_ACT_HSWISH: return dws_launch_a<KS, DN_ACT_HSWISH>(tm, sp, w, bias, y, B, H, W, C, stream);
+    }
+    DN_REQUIRE(false, DN_ERR_INVALID, "bad activation %d", act);
+}
+
+int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
+                         int W, int C, int k, int act, cudaStream_t stream) {
+    DN_REQUIRE((long long)sp.ncblk * B * H < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
+    if (k == 3) return dws_launch_k<3>(tm, sp, w, bias, y, B, H, W, C, act, stream);
+    return dws_launch_k<5>(tm, sp, w, bias, y, B, H, W, C, act, stream);
+}
+
+}  // namespace dn

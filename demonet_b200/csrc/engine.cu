@@ -45,6 +45,7 @@ struct dn_engine {
     std::vector<char> has_tmap_y;
     std::vector<CUtensorMap> tmap_dw;               // per op (DW only)
     std::vector<DwTiling> dw_tiling;
+    std::vector<DwStream> dw_stream;
     std::vector<char> dw_tma;                       // per op: TMA-tiled kernel selected
     bool dw_ready = false;
     bool tmaps_ready = false;
@@ -185,10 +186,21 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
     if (!e->dw_ready) {
         e->tmap_dw.resize(e->ops.size());
         e->dw_tiling.resize(e->ops.size());
+        e->dw_stream.resize(e->ops.size());
         e->dw_tma.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
-            if (o.kind != DN_OP_DW || !dw_use_tma(o.h_out, o.w_out)) continue;
+            if (o.kind != DN_OP_DW) continue;
+            const DwImpl impl = dw_choose(o.h_in, o.w_in, o.c_in, o.ksize, o.stride);
+            if (impl == DW_STREAM) {
+                e->dw_tma[i] = 2;
+                if (!dw_stream_plan(o.h_in, o.w_in, o.c_in, o.ksize, o.stride, &e->dw_stream[i])) return DN_ERR_UNSUPPORTED;
+                int rc = dw_stream_make_tmap(&e->tmap_dw[i], buf_ptr(e, o.in_buf), e->max_batch, o.h_in, o.w_in, o.c_in, o.ksize,
+                                             e->dw_stream[i]);
+                if (rc) return rc;
+                continue;
+            }
+            if (impl != DW_TMA) continue;
             e->dw_tma[i] = 1;
             int rc = dw_plan(o.h_in, o.w_in, o.c_in, o.ksize, o.stride, &e->dw_tiling[i]);
             if (rc) return rc;
@@ -237,7 +249,13 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                                   e->desc.image_std, buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_out, o.act, s);
                 break;
             case DN_OP_DW:
-                if (e->dw_ready && e->dw_tma[i]) {
+                if (e->dw_ready && e->dw_tma[i] == 2) {
+                    rc = dwconv_stream_launch(e->tmap_dw[i], e->dw_stream[i], (const float*)(W + o.w_off),
+                                              (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
+                                              o.act, s);
+                    break;
+                }
+                if (e->dw_ready && e->dw_tma[i] == 1) {
                     rc = dwconv_tma_launch(e->tmap_dw[i], e->dw_tiling[i], (const float*)(W + o.w_off), (const float*)(W + o.b_off),
                                            buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize, o.stride, o.act, s);
                     break;

@@ -21,7 +21,8 @@ def _close_bf16(got, want, extra_abs=1e-3):
 # (C, k, stride, H) from Appendix C.1 / C.3 plus ragged sizes
 DW_CASES = [(16, 3, 1, 160), (64, 3, 2, 160), (72, 5, 2, 80), (120, 5, 1, 40), (240, 3, 2, 40), (672, 3, 1, 20),
             (672, 5, 2, 20), (480, 5, 1, 10), (256, 3, 2, 10), (128, 3, 2, 5), (128, 3, 2, 3), (64, 3, 2, 2),
-            (128, 3, 1, 1), (96, 3, 1, 19), (144, 3, 2, 75), (32, 3, 1, 150), (1280, 3, 1, 16), (8, 5, 2, 7)]
+            (128, 3, 1, 1), (96, 3, 1, 19), (144, 3, 2, 75), (32, 3, 1, 150), (1280, 3, 1, 16), (8, 5, 2, 7),
+            (200, 3, 1, 20), (72, 3, 1, 80), (24, 5, 1, 33), (8, 3, 1, 9), (184, 3, 1, 20)]
 
 
 @pytest.mark.parametrize("C,k,s,H", DW_CASES)
@@ -37,6 +38,19 @@ def test_dwconv(C, k, s, H, act):
     ref = ACTS[act](ref).permute(0, 2, 3, 1)
     assert y.shape == ref.shape
     _close_bf16(y, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C,k", [(37, 12, 27, 40, 3), (37, 12, 27, 40, 5), (300, 8, 8, 64, 3), (5, 64, 9, 16, 5)])
+def test_dwconv_rect_many_images(B, H, W, C, k):
+    """Non-square maps and enough images that a CTA's share of the row stream (dwconv_stream.cu) starts and ends
+    in the middle of images and spans several of them."""
+    g = torch.Generator().manual_seed(B + H * 3 + W * 5 + C * 7 + k)
+    x = (torch.randn(B, H, W, C, generator=g) * 2).bfloat16().cuda()
+    w = (torch.randn(k * k, C, generator=g) / k).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = ops.dwconv(x, w, b, k, 1, "hardswish")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, k, k), b, 1, (k - 1) // 2, 1, C)
+    _close_bf16(y, ACTS["hardswish"](ref).permute(0, 2, 3, 1))
 
 
 # (M, K, N): Appendix C GEMM shapes (per-image M times a small batch), incl. N not multiple of 16 / > 256
