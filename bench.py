@@ -95,14 +95,57 @@ def run_reference(args):
 # clocks sampler (nvidia-smi, during the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  NVML is polled in-process every 2 ms (a timed
+    region of a few tens of milliseconds still gets samples); `nvidia-smi -lms` is the fallback when the NVML
+    binding is not importable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown")
+                else n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.handle))
+                for nm, b in bits.items():
+                    if b and (r & b):
+                        self.reasons.add(nm)
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -116,6 +159,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in ln.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "power_w_max": round(max(self.power), 1) if self.power else None,
+                    "source": "nvml, 2 ms poll inside the timed region"}
         if self.proc:
             self.proc.terminate()
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
@@ -128,7 +179,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ class Op(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("act", c_int32), ("in_buf", c_int32), ("out_buf", c_int32), ("res_buf", c_int32),
                 ("h_in", c_int32), ("w_in", c_int32), ("c_in", c_int32), ("h_out", c_int32), ("w_out", c_int32),
                 ("c_out", c_int32), ("ksize", c_int32), ("stride", c_int32), ("c_mid", c_int32), ("out_fp32", c_int32),
-                ("reserved", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
+                ("lane", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
                 ("out_batch_stride", c_int64), ("out_row_stride", c_int64), ("out_offset", c_int64)]
 
 

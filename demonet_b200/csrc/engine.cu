@@ -2,6 +2,7 @@
 // as a pre-planned launch sequence over a device arena, replayed from a CUDA graph.
 // The layer list (dn_op[]) is produced by the Python host side from the reference's module
 // structure (demonet_b200/plan.py); this file only owns memory, tensor maps and launch order.
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -51,6 +52,14 @@ struct dn_engine {
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
     cudaStream_t capture_stream = nullptr;
+    // side lanes (dn_op.lane > 0): head branches forked off the main chain.  lane_stream[l-1] carries lane l;
+    // op_done[j] is recorded after op j when an op of another lane reads its output (deps[i] lists those j)
+    int n_lanes = 0;                                // highest lane id in use (0 = everything on one stream)
+    std::vector<cudaStream_t> lane_stream;
+    std::vector<cudaEvent_t> lane_joined;           // recorded at the end of each side lane
+    std::vector<cudaEvent_t> op_done;               // per op, nullptr when nobody waits for it
+    std::vector<std::vector<int>> deps;             // per op: producers on other lanes
+    cudaEvent_t fork_ev = nullptr;
     // staging for dn_engine_forward_host: two input buffers so that the H2D copy of call i+1 (on copy_stream)
     // overlaps the forward of call i (on the caller's stream)
     float* stage_images = nullptr;              // [2][max_batch,3,H,W]
@@ -95,6 +104,39 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     e->desc.bufs_host = nullptr;
     e->desc.anchors_host = nullptr;
     e->max_batch = max_batch;
+    {
+        static const bool lanes_off = [] {          // measurement aid: DN_LANES=0 keeps every op on the caller's stream
+            const char* v = getenv("DN_LANES");
+            return v && atoi(v) == 0;
+        }();
+        for (auto& o : e->ops) {
+            if (lanes_off || o.lane < 0 || o.lane > 64) o.lane = 0;
+            if (o.lane > e->n_lanes) e->n_lanes = o.lane;
+        }
+        e->deps.resize(e->ops.size());
+        std::vector<char> need(e->ops.size(), 0);
+        for (size_t i = 0; i < e->ops.size() && e->n_lanes > 0; ++i) {
+            const int ins[2] = {e->ops[i].in_buf, e->ops[i].res_buf};
+            for (int b : ins) {
+                if (b < 0) continue;
+                for (int j = (int)i - 1; j >= 0; --j) {
+                    if (e->ops[j].out_buf != b && !(e->ops[j].kind == DN_OP_SE && e->ops[j].in_buf == b)) continue;
+                    if (e->ops[j].lane != e->ops[i].lane) {
+                        e->deps[i].push_back(j);
+                        need[j] = 1;
+                    }
+                    break;                          // the latest writer orders everything before it on its own lane
+                }
+            }
+        }
+        e->op_done.assign(e->ops.size(), nullptr);
+        for (size_t j = 0; j < e->ops.size(); ++j)
+            if (need[j] && cudaEventCreateWithFlags(&e->op_done[j], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("cudaEventCreate failed");
+                dn_engine_destroy(e);
+                return DN_ERR_CUDA;
+            }
+    }
     auto fail = [&](int rc) {
         dn_engine_destroy(e);
         return rc;
@@ -139,6 +181,13 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     }
     TRY(cudaMalloc(&e->stage_out, e->so_total));
     TRY(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+    e->lane_stream.assign(e->n_lanes, nullptr);
+    e->lane_joined.assign(e->n_lanes, nullptr);
+    for (int l = 0; l < e->n_lanes; ++l) {
+        TRY(cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking));
+        TRY(cudaEventCreateWithFlags(&e->lane_joined[l], cudaEventDisableTiming));
+    }
+    TRY(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
 #undef TRY
     e->device_bytes = e->arena_bytes + e->post_ws_bytes + 2 * e->stage_image_bytes + e->so_total + e->anchors_host.size() * 4;
     *out = e;
@@ -150,6 +199,13 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
     drop_graphs(e);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (auto st : e->lane_stream)
+        if (st) cudaStreamDestroy(st);
+    for (auto ev : e->lane_joined)
+        if (ev) cudaEventDestroy(ev);
+    for (auto ev : e->op_done)
+        if (ev) cudaEventDestroy(ev);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
     for (int i = 0; i < 2; ++i) {
         if (e->h2d_done[i]) cudaEventDestroy(e->h2d_done[i]);
         if (e->fwd_done[i]) cudaEventDestroy(e->fwd_done[i]);
@@ -295,9 +351,30 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
 
 static int enqueue_forward(dn_engine* e, const float* images, int B, float* out_boxes, float* out_scores,
                            int64_t* out_labels, int32_t* out_counts, cudaStream_t s) {
+    // Lane 0 runs on the caller's stream; a side lane starts behind everything already enqueued there (fork_ev),
+    // waits for the producers it reads from (op_done) and is joined again before the post-processing.  Under
+    // stream capture the same event calls turn into parallel branches of the graph.
+    std::vector<char> lane_used(e->n_lanes, 0);
+    if (e->n_lanes > 0) DN_CHECK_CUDA(cudaEventRecord(e->fork_ev, s));
     for (size_t i = 0; i < e->ops.size(); ++i) {
-        int rc = enqueue_op(e, i, images, B, s);
+        const int lane = e->ops[i].lane;
+        cudaStream_t ls = s;
+        if (lane > 0) {
+            ls = e->lane_stream[lane - 1];
+            if (!lane_used[lane - 1]) {
+                lane_used[lane - 1] = 1;
+                DN_CHECK_CUDA(cudaStreamWaitEvent(ls, e->fork_ev, 0));
+            }
+        }
+        for (int j : e->deps[i]) DN_CHECK_CUDA(cudaStreamWaitEvent(ls, e->op_done[j], 0));
+        int rc = enqueue_op(e, i, images, B, ls);
         if (rc) return rc;
+        if (e->op_done[i]) DN_CHECK_CUDA(cudaEventRecord(e->op_done[i], ls));
+    }
+    for (int l = 0; l < e->n_lanes; ++l) {
+        if (!lane_used[l]) continue;
+        DN_CHECK_CUDA(cudaEventRecord(e->lane_joined[l], e->lane_stream[l]));
+        DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->lane_joined[l], 0));
     }
     return dn_postprocess((const float*)buf_ptr(e, e->desc.logits_buf), (const float*)buf_ptr(e, e->desc.bbox_buf),
                           e->anchors_dev, B, &e->desc.post, e->post_ws, e->post_ws_bytes, out_boxes, out_scores, out_labels,

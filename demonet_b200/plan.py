@@ -331,14 +331,39 @@ def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
 # ---------------------------------------------------------------------------------------------
 # arena buffers (liveness-based reuse) and the dn_op array
 # ---------------------------------------------------------------------------------------------
+def layer_lanes(plan: Plan) -> List[int]:
+    """Launch lane of every layer: 0 = the backbone / extras chain, 1 + 2*level (+1) = the classification
+    (regression) head of one feature level.  The 12 head branches (depthwise + 1x1 each) depend only on their
+    feature map, so the engine runs them on side streams that fork off the main chain -- inside the CUDA graph
+    they become parallel branches that overlap the tail of the backbone and each other."""
+    lanes = [0] * len(plan.layers)
+    by_dst = {L.dst: i for i, L in enumerate(plan.layers) if L.dst and L.kind != "se"}
+    for i, L in enumerate(plan.layers):
+        if L.head:
+            kind, lvl = L.head
+            lanes[i] = 1 + 2 * lvl + (0 if kind == "cls" else 1)
+            j = by_dst.get(L.src)
+            if j is not None and plan.layers[j].kind == "dw" and L.src not in plan.feature_names:
+                lanes[j] = lanes[i]
+    return lanes
+
+
 def assign_buffers(plan: Plan, reuse: bool = True):
     """Returns (tensor -> buffer id, [(elems_per_image, elem_bytes)], logits_buf, bbox_buf).
-    reuse=False gives every tensor its own buffer (used by the per-layer parity tests)."""
+    reuse=False gives every tensor its own buffer (used by the per-layer parity tests).
+    Tensors written or read on a side lane (layer_lanes) keep a buffer of their own for the whole forward:
+    list order is not execution order across lanes, so they can neither take over nor hand on a buffer."""
+    lanes = layer_lanes(plan)
+    pinned = set()
     last_use = {}
     for i, L in enumerate(plan.layers):
         for t in (L.src, L.res):
             if t and t != "images":
                 last_use[t] = i
+                if lanes[i]:
+                    pinned.add(t)
+        if lanes[i] and L.dst:
+            pinned.add(L.dst)
     bufs: List[List[int]] = []      # [elems, bytes]
     free: List[int] = []
     t2b: Dict[str, int] = {}
@@ -347,11 +372,12 @@ def assign_buffers(plan: Plan, reuse: bool = True):
             h, w, c = plan.tensors[L.dst]
             need = h * w * c
             best = None
-            for bid in free:
+            avail = [] if L.dst in pinned else free
+            for bid in avail:
                 if bufs[bid][0] >= need and (best is None or bufs[bid][0] < bufs[best][0]):
                     best = bid
-            if best is None and free:          # grow the largest free buffer instead of adding one
-                best = max(free, key=lambda q: bufs[q][0])
+            if best is None and avail:         # grow the largest free buffer instead of adding one
+                best = max(avail, key=lambda q: bufs[q][0])
                 bufs[best][0] = need
             if best is None:
                 bufs.append([need, 2])
@@ -360,7 +386,7 @@ def assign_buffers(plan: Plan, reuse: bool = True):
                 free.remove(best)
             t2b[L.dst] = best
         for t in {L.src, L.res}:
-            if reuse and t and t != "images" and last_use.get(t) == i and t in t2b:
+            if reuse and t and t != "images" and last_use.get(t) == i and t in t2b and t not in pinned:
                 free.append(t2b[t])
     P, K = plan.num_priors, plan.num_classes
     bufs.append([P * K, 4])
@@ -378,6 +404,7 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf):
         o += h * w * plan.anchors_per_loc
     P, K = plan.num_priors, plan.num_classes
     ops = (_C.Op * len(plan.layers))()
+    lanes = layer_lanes(plan)
     kinds = {"stem": _C.OP_STEM, "dw": _C.OP_DW, "pw": _C.OP_PW, "se": _C.OP_SE}
     for i, (L, off) in enumerate(zip(plan.layers, offsets)):
         op = ops[i]
@@ -391,6 +418,7 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf):
             op.h_in, op.w_in, op.c_in = (L.h_in * L.w_in) // pf, 1, pf * L.cin
             op.h_out, op.w_out, op.c_out = op.h_in, 1, pf * L.cout
         op.ksize, op.stride, op.c_mid = L.k, L.stride, L.se_mid
+        op.lane = lanes[i]
         op.w_off, op.b_off = off["w"], off["b"]
         op.w2_off, op.b2_off = off.get("w2", 0), off.get("b2", 0)
         if L.head:

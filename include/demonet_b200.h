@@ -142,7 +142,8 @@ typedef struct {
     int32_t ksize, stride;
     int32_t c_mid;                         /* SE squeeze width                              */
     int32_t out_fp32;
-    int32_t reserved;
+    int32_t lane;                          /* launch lane: 0 = main chain, > 0 = a side branch (head) that may run
+                                              concurrently; its tensors never share arena buffers with other lanes */
     int64_t w_off, b_off, w2_off, b2_off;  /* byte offsets into the weight blob             */
     int64_t out_batch_stride, out_row_stride, out_offset;   /* PW output addressing (elements) */
 } dn_op;

@@ -161,3 +161,30 @@ def test_stem_division_shortcut_is_exact():
         assert np.all(e32.astype(np.float64) == e)                    # the remainder is exactly representable
         q = (np.longdouble(q0) + np.longdouble(e32) * np.longdouble(r)).astype(np.float32)
         assert np.array_equal(q.view(np.int32), (d / s).astype(np.float32).view(np.int32))
+
+
+@pytest.mark.parametrize("make", [dplan.plan_ssdlite320_mobilenet_v3_large, lambda: dplan.plan_ssd_lite_mobilenet_v2(21, 512)])
+def test_side_lanes_never_share_buffers(make):
+    """Head branches run on side streams (plan.layer_lanes): every tensor they read or write must own its arena
+    buffer for the whole forward, and the main chain must not depend on a side lane."""
+    p = make()
+    lanes = dplan.layer_lanes(p)
+    t2b, bufs, lb, bb = dplan.assign_buffers(p)
+    assert lanes.count(0) == len(p.layers) - sum(1 for L in p.layers if L.head) - sum(
+        1 for i, L in enumerate(p.layers) if L.kind == "dw" and lanes[i])
+    assert len({lanes[i] for i, L in enumerate(p.layers) if L.head}) == 12       # one lane per (head, level)
+    producer = {L.dst: i for i, L in enumerate(p.layers) if L.dst and L.kind != "se"}
+    touched = set()
+    for i, L in enumerate(p.layers):
+        if lanes[i]:
+            touched.update(t for t in (L.src, L.res, L.dst) if t and t != "images")
+            if L.src in producer:                       # a side lane reads the main chain or itself, never another lane
+                assert lanes[producer[L.src]] in (0, lanes[i])
+        else:
+            assert all(lanes[producer[t]] == 0 for t in (L.src, L.res) if t in producer)
+    owners = {}
+    for t, b in t2b.items():
+        owners.setdefault(b, []).append(t)
+    for t in touched:
+        assert owners[t2b[t]] == [t], "buffer of %s is shared: %s" % (t, owners[t2b[t]])
+    assert set(p.feature_names) <= touched
