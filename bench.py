@@ -198,7 +198,7 @@ def layer_costs(plan, B):
             out.append(("dwconv_kernel", B * (hi * wi + ho * wo) * L.cin * 2 + L.k * L.k * L.cin * 4,
                         2 * B * ho * wo * L.cin * L.k * L.k))
         elif L.kind == "se":
-            out.append(("se_inplace_kernel", B * hi * wi * L.cin * 2 * 2 + 2 * L.cin * L.se_mid * 4,
+            out.append(("se_pool+fc1+fc2+scale kernels", B * hi * wi * L.cin * 2 * 2 + 2 * L.cin * L.se_mid * 4,
                         2 * B * 2 * L.cin * L.se_mid))
         else:
             ob = 4 if L.head else 2

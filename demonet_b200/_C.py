@@ -57,7 +57,9 @@ _SIGNATURES = {
                           c_int64, c_int64, c_int, c_void_p]),
     "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "dn_se_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_se_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dn_se_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                              c_size_t, c_void_p]),
     "dn_postprocess_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(PostprocessParams)]),
     "dn_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p, c_size_t,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

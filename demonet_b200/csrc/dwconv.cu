@@ -1,7 +1,6 @@
 // Bandwidth-bound CUDA-core kernels of the SSDLite backbone for sm_100a:
 //   * depthwise k x k stencil (k in {3,5}, stride in {1,2}) + folded BN + activation   (dn_dwconv)
 //   * stem: input normalisation + dense 3x3 stride-2 conv + folded BN + activation     (dn_stem_conv)
-//   * squeeze-excitation, applied in place                                              (dn_se_inplace)
 // Activations are NHWC bf16, 8 channels (16 B) per thread access, fp32 accumulation.
 #include <cstdlib>
 
@@ -182,76 +181,6 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Squeeze-Excitation, one CTA per image, in place:  x *= hardsigmoid(fc2(relu(fc1(mean_hw(x))))).
-// Reference: SqueezeExcitation, demonet/models/mobilenetv3.py:22-40.
-// w1: fp32 [Cs][C]; w2t: fp32 [Cs][C] (fc2 weight TRANSPOSED so that threads read it coalesced).
-// ---------------------------------------------------------------------------------------------
-constexpr int SE_THREADS = 512;
-
-__global__ void __launch_bounds__(SE_THREADS)
-se_inplace_kernel(uint4* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
-                  const float* __restrict__ w2t, const float* __restrict__ b2, int HW, int C, int Cs) {
-    extern __shared__ float s_se[];
-    float* pooled = s_se;              // [C]
-    float* hidden = pooled + C;        // [Cs]
-    float* scale = hidden + Cs;        // [C]
-    float* part = scale + C;           // [slices][C]
-    const int CV = C >> 3;
-    const int b = blockIdx.x;
-    uint4* xb = x + (long long)b * HW * CV;
-    const int slices = SE_THREADS / CV;          // >= 1 because C <= 8 * SE_THREADS is checked on the host
-    const int cv = threadIdx.x % CV, sl = threadIdx.x / CV;
-    if (sl < slices) {
-        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int p = sl; p < HW; p += slices) {
-            float f[8];
-            unpack8(xb[(long long)p * CV + cv], f);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s[q] += f[q];
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) part[sl * C + cv * 8 + q] = s[q];
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += SE_THREADS) {
-        float s = 0.f;
-        for (int i = 0; i < slices; ++i) s += part[i * C + c];
-        pooled[c] = __fdiv_rn(s, (float)HW);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = warp; j < Cs; j += SE_THREADS / 32) {
-        const float* wr = w1 + (long long)j * C;
-        float s = 0.f;
-#pragma unroll 4
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), pooled[c], s);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hidden[j] = fmaxf(s + __ldg(b1 + j), 0.f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += SE_THREADS) {
-        float s = __ldg(b2 + c);
-#pragma unroll 8
-        for (int j = 0; j < Cs; ++j) s = fmaf(__ldg(w2t + (long long)j * C + c), hidden[j], s);
-        // hardsigmoid(x) = relu6(x + 3) / 6
-        scale[c] = __fdiv_rn(fminf(fmaxf(s + 3.f, 0.f), 6.f), 6.f);
-    }
-    __syncthreads();
-    const int nvec = HW * CV;
-#pragma unroll 4
-    for (int i = threadIdx.x; i < nvec; i += SE_THREADS) {
-        const int c0 = (i % CV) * 8;
-        float f[8];
-        unpack8(xb[i], f);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] *= scale[c0 + q];
-        xb[i] = pack8(f);
-    }
-}
-
 // Kernel per layer shape (measured on B200, profiles/r01_dw_*.txt): stride-1 layers with at least 8 rows run on the
 // TMA-fed row stream (dwconv_stream.cu, 3.0-4.0 TB/s); of the rest, the TMA-fed shared-memory tiles win on the
 // large maps (>= 60x60 outputs) and the register-tiled direct kernel on the small ones.
@@ -330,25 +259,6 @@ extern "C" int dn_stem_conv(const float* images, const float* w, const float* bi
     else
         stem_conv_kernel<32><<<blocks, 128, 0, s>>>(images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0], mean3_host[1],
                                                    mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
-    DN_CHECK_LAUNCH();
-    return DN_OK;
-}
-
-extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
-                             int C, int Cs, void* stream_) {
-    DN_REQUIRE(x && w1 && b1 && w2t && b2, DN_ERR_INVALID, "NULL tensor pointer");
-    DN_REQUIRE(B > 0 && HW > 0 && C > 0 && Cs > 0, DN_ERR_INVALID, "bad shape");
-    DN_REQUIRE(C % 8 == 0 && C / 8 <= SE_THREADS, DN_ERR_UNSUPPORTED, "SE channels must be a multiple of 8 and <= %d",
-               8 * SE_THREADS);
-    const int slices = SE_THREADS / (C / 8);
-    const size_t smem = ((size_t)2 * C + Cs + (size_t)slices * C) * sizeof(float);
-    DN_REQUIRE(smem <= 200 * 1024, DN_ERR_UNSUPPORTED, "SE block too large for shared memory");
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(se_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    se_inplace_kernel<<<B, SE_THREADS, smem, (cudaStream_t)stream_>>>((uint4*)x, w1, b1, w2t, b2, HW, C, Cs);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

@@ -2,6 +2,7 @@
 // as a pre-planned launch sequence over a device arena, replayed from a CUDA graph.
 // The layer list (dn_op[]) is produced by the Python host side from the reference's module
 // structure (demonet_b200/plan.py); this file only owns memory, tensor maps and launch order.
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <tuple>
@@ -42,6 +43,9 @@ struct dn_engine {
     float* anchors_dev = nullptr;
     void* post_ws = nullptr;
     size_t post_ws_bytes = 0;
+    void* se_ws = nullptr;                          // scratch of the squeeze-excitation layers (largest of them)
+    size_t se_ws_bytes = 0;
+    int n_se = 0;
     std::vector<CUtensorMap> tmap_a, tmap_w, tmap_y;       // per op (PW only)
     std::vector<char> has_tmap_y;
     std::vector<CUtensorMap> tmap_dw;               // per op (DW only)
@@ -154,6 +158,11 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     }
     e->arena_bytes = off;
     e->post_ws_bytes = dn_postprocess_workspace_bytes(max_batch, &e->desc.post);
+    for (const auto& o : e->ops)
+        if (o.kind == DN_OP_SE) {
+            e->se_ws_bytes = std::max(e->se_ws_bytes, dn_se_workspace_bytes(max_batch, o.h_in * o.w_in, o.c_in));
+            ++e->n_se;
+        }
     const size_t D = e->desc.post.detections_per_img;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     e->so_boxes = 0;
@@ -172,6 +181,7 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     TRY(cudaMalloc(&e->anchors_dev, e->anchors_host.size() * sizeof(float)));
     TRY(cudaMemcpy(e->anchors_dev, e->anchors_host.data(), e->anchors_host.size() * sizeof(float), cudaMemcpyHostToDevice));
     TRY(cudaMalloc(&e->post_ws, e->post_ws_bytes));
+    if (e->se_ws_bytes) TRY(cudaMalloc(&e->se_ws, e->se_ws_bytes));
     e->stage_image_bytes = (img_bytes + 255) & ~(size_t)255;
     TRY(cudaMalloc(&e->stage_images, 2 * e->stage_image_bytes));
     TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -189,7 +199,7 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     }
     TRY(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
 #undef TRY
-    e->device_bytes = e->arena_bytes + e->post_ws_bytes + 2 * e->stage_image_bytes + e->so_total + e->anchors_host.size() * 4;
+    e->device_bytes = e->arena_bytes + e->post_ws_bytes + e->se_ws_bytes + 2 * e->stage_image_bytes + e->so_total + e->anchors_host.size() * 4;
     *out = e;
     return DN_OK;
 }
@@ -214,6 +224,7 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
     cudaFree(e->weights);
     cudaFree(e->anchors_dev);
     cudaFree(e->post_ws);
+    cudaFree(e->se_ws);
     cudaFree(e->stage_images);
     cudaFree(e->stage_out);
     delete e;
@@ -342,7 +353,7 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
             case DN_OP_SE:
                 rc = dn_se_inplace(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
                                    (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
-                                   o.c_mid, s);
+                                   o.c_mid, e->se_ws, e->se_ws_bytes, s);
                 break;
         }
         return rc;
@@ -503,6 +514,7 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
     return rc;
 }
 
-// layers + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS, CTA NMS, merge)
-extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 14 : 0; }
+// layers (a squeeze-excitation is 4 launches) + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS,
+// CTA NMS, merge)
+extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 3 * e->n_se + 14 : 0; }
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) { return e ? e->device_bytes : 0; }

@@ -18,6 +18,8 @@
 // Reference ops replaced: see dn_pwconv in include/demonet_b200.h.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "pwconv.cuh"
 
@@ -450,7 +452,12 @@ static size_t smem_cap(int n) {
 }
 
 void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
-    const int nt = (N + 255) / 256;
+    static const int bn_max = [] {                     // measurement aid: DN_PW_BN_MAX=64|128 caps the tile width
+        const char* v = getenv("DN_PW_BN_MAX");
+        const int x = v ? atoi(v) : 256;
+        return (x == 64 || x == 128) ? x : 256;
+    }();
+    const int nt = (N + bn_max - 1) / bn_max;
     int bn = (N + nt - 1) / nt;
     bn = nt > 1 ? (bn + 63) & ~63 : (bn + 15) & ~15;      // 64-column groups must not straddle two N tiles
     int cols = 32;

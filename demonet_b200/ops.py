@@ -219,8 +219,10 @@ def se_inplace(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor) -> Te
     """x bf16 [B,HW,C] scaled in place; w1 fp32 [Cs,C]; w2t fp32 [Cs,C] (fc2 transposed)."""
     _require_cuda(x, w1, b1, w2t, b2)
     B, HW, C = x.shape
+    ws_bytes = _C.lib().dn_se_workspace_bytes(B, HW, C)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         _C.check(_C.lib().dn_se_inplace(x.data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
                                         w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(), B, HW, C, w1.shape[0],
-                                        _stream(x)))
+                                        ws.data_ptr(), ws_bytes, _stream(x)))
     return x

@@ -75,9 +75,11 @@ int dn_stem_conv(const float* images, const float* w, const float* bias, const f
 /* Squeeze-Excitation applied in place: x *= hardsigmoid(fc2(relu(fc1(avgpool(x))))).
  * Replaces SqueezeExcitation.forward, mobilenetv3.py:22-40.
  * x: bf16 [B,HW,C] (in/out); w1: fp32 [Cs,C] (fc1); b1: fp32 [Cs]; w2t: fp32 [Cs,C] (fc2 weight
- * TRANSPOSED); b2: fp32 [C]. */
+ * TRANSPOSED); b2: fp32 [C].  workspace: device scratch of dn_se_workspace_bytes(B, HW, C) bytes
+ * (per-chunk channel sums and the [B,C] scales), 16-byte aligned. */
+size_t dn_se_workspace_bytes(int B, int HW, int C);
 int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
-                  int C, int Cs, void* stream);
+                  int C, int Cs, void* workspace, size_t workspace_bytes, void* stream);
 
 typedef struct {
     int32_t num_priors;          /* P                                                          */
