@@ -267,6 +267,11 @@ def main():
     def step_host():
         eng.forward_host(imgs_host, host_out)       # results land in each rank's own host memory: no gather
 
+    imgs_u8_host = (imgs_host * 255).round().to(torch.uint8).pin_memory()      # what an image decoder hands over
+
+    def step_host_u8():
+        eng.forward_host_u8(imgs_u8_host, host_out)
+
     def timed(fn, steps, warmup, sampler=None):
         for _ in range(warmup):
             fn()
@@ -300,6 +305,8 @@ def main():
     e2e_ms, _ = timed(step_host, args.steps, warm)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     counts_ok = int(host_out["counts"].min()) >= 0
+    u8_ms, _ = timed(step_host_u8, args.steps, warm)
+    u8_value = world * B * args.steps / (u8_ms * 1e-3)
 
     # per-launch device times, live, with CUDA events on the launching stream
     n_launch = eng.launches_per_forward
@@ -369,6 +376,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
                     "api": "dn_engine_forward_host (pinned fp32 images in, detections out)", "ok": counts_ok},
+            "e2e_u8": {"value": u8_value, "unit": UNIT, "ms_per_step": u8_ms / args.steps,
+                       "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                       "api": "dn_engine_forward_host_u8 (pinned uint8 pixels in, x/255 on the device, detections out); "
+                              "the e2e entry above keeps the reference's fp32 input contract and is PCIe-bound"},
             "gpu_launches": n_launch * args.steps,
             "gpu_launches_per_step": n_launch,
             "roofline": roofline}

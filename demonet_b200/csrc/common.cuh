@@ -18,6 +18,8 @@ int dn_postprocess_timed(const float* cls_logits, const float* bbox_regression, 
 namespace dn {
 
 void set_error(const char* fmt, ...);
+// uint8 -> fp32 / 255 (transform.cu), used by the engine's uint8 ingest
+int u8_to_f32_launch(const unsigned char* src, float* dst, size_t n, cudaStream_t s);
 
 #define DN_CHECK_CUDA(expr)                                                                      \
     do {                                                                                         \

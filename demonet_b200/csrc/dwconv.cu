@@ -183,7 +183,7 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 
 // Kernel per layer shape (measured on B200, profiles/r01_dw_*.txt): stride-1 layers with at least 8 rows run on the
 // TMA-fed row stream (dwconv_stream.cu, 3.0-4.0 TB/s); of the rest, the TMA-fed shared-memory tiles win on the
-// large maps (>= 60x60 outputs) and the register-tiled direct kernel on the small ones.
+// large maps (>= 40x40 outputs) and the register-tiled direct kernel on the small ones.
 DwImpl dw_choose(int H, int W, int C, int k, int stride) {
     static const int forced = [] {                  // measurement aid: DN_DW_IMPL=1|2|4 forces one kernel where it applies
         const char* e = getenv("DN_DW_IMPL");
@@ -193,7 +193,7 @@ DwImpl dw_choose(int H, int W, int C, int k, int stride) {
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     DwStream sp;
     const bool stream_ok = H >= 8 && dw_stream_plan(H, W, C, k, stride, &sp);
-    const DwImpl tiled = (long long)Ho * Wo >= 3600 ? DW_TMA : DW_DIRECT;
+    const DwImpl tiled = (long long)Ho * Wo >= 1600 ? DW_TMA : DW_DIRECT;      // 40x40 outputs and up (r01 A/B table)
     if (forced == DW_DIRECT) return DW_DIRECT;
     if (forced == DW_TMA) return DW_TMA;
     if (forced == DW_STREAM) return stream_ok ? DW_STREAM : tiled;

@@ -68,6 +68,8 @@ struct dn_engine {
     // overlaps the forward of call i (on the caller's stream)
     float* stage_images = nullptr;              // [2][max_batch,3,H,W]
     size_t stage_image_bytes = 0;
+    unsigned char* stage_u8 = nullptr;          // [2][max_batch,3,H,W] uint8, allocated on the first uint8 call
+    size_t stage_u8_bytes = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, fwd_done[2] = {nullptr, nullptr};
     bool fwd_recorded[2] = {false, false};
@@ -226,6 +228,7 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
     cudaFree(e->post_ws);
     cudaFree(e->se_ws);
     cudaFree(e->stage_images);
+    cudaFree(e->stage_u8);
     cudaFree(e->stage_out);
     delete e;
     return DN_OK;
@@ -424,25 +427,40 @@ extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, f
     return DN_OK;
 }
 
-extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
-                                      float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
-                                      void* stream_) {
+// Host-buffer forward, shared by the fp32 and the uint8 entry points.
+static int forward_host_impl(dn_engine* e, const void* images_host, bool u8, int B, float* out_boxes_host,
+                             float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
     DN_REQUIRE(B > 0 && B <= e->max_batch, DN_ERR_INVALID, "batch %d outside [1, %d]", B, e->max_batch);
     DN_REQUIRE(images_host && out_boxes_host && out_scores_host && out_labels_host && out_counts_host, DN_ERR_INVALID,
                "NULL host pointer");
     cudaStream_t s = (cudaStream_t)stream_;
     const size_t D = e->desc.post.detections_per_img;
-    const size_t img_bytes = (size_t)B * 3 * e->desc.image_h * e->desc.image_w * sizeof(float);
+    const size_t n_px = (size_t)B * 3 * e->desc.image_h * e->desc.image_w;
+    const size_t img_bytes = n_px * sizeof(float);
+    if (u8 && !e->stage_u8) {
+        e->stage_u8_bytes = ((size_t)e->max_batch * 3 * e->desc.image_h * e->desc.image_w + 255) & ~(size_t)255;
+        DN_CHECK_CUDA(cudaMalloc(&e->stage_u8, 2 * e->stage_u8_bytes));
+        e->device_bytes += 2 * e->stage_u8_bytes;
+    }
     // H2D on the copy stream into the staging buffer the previous-but-one call used; the forward on the
     // caller's stream waits for it, so back-to-back calls overlap copy(i+1) with forward(i).
     const int par = e->host_parity;
     e->host_parity ^= 1;
     float* stage = (float*)((unsigned char*)e->stage_images + (size_t)par * e->stage_image_bytes);
     if (e->fwd_recorded[par]) DN_CHECK_CUDA(cudaStreamWaitEvent(e->copy_stream, e->fwd_done[par], 0));   // WAR on stage
-    DN_CHECK_CUDA(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, e->copy_stream));
-    DN_CHECK_CUDA(cudaEventRecord(e->h2d_done[par], e->copy_stream));
-    DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->h2d_done[par], 0));
+    if (u8) {       // a quarter of the PCIe bytes; ToTensor's x / 255 runs on the device in front of the stem
+        unsigned char* su8 = e->stage_u8 + (size_t)par * e->stage_u8_bytes;
+        DN_CHECK_CUDA(cudaMemcpyAsync(su8, images_host, n_px, cudaMemcpyHostToDevice, e->copy_stream));
+        DN_CHECK_CUDA(cudaEventRecord(e->h2d_done[par], e->copy_stream));
+        DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->h2d_done[par], 0));
+        int rc = u8_to_f32_launch(su8, stage, n_px, s);
+        if (rc) return rc;
+    } else {
+        DN_CHECK_CUDA(cudaMemcpyAsync(stage, images_host, img_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        DN_CHECK_CUDA(cudaEventRecord(e->h2d_done[par], e->copy_stream));
+        DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->h2d_done[par], 0));
+    }
     unsigned char* so = e->stage_out;
     int rc = dn_engine_forward(e, stage, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
                                (int64_t*)(so + e->so_labels), (int32_t*)(so + e->so_counts), s);
@@ -454,6 +472,18 @@ extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, in
     DN_CHECK_CUDA(cudaMemcpyAsync(out_labels_host, so + e->so_labels, (size_t)B * D * 8, cudaMemcpyDeviceToHost, s));
     DN_CHECK_CUDA(cudaMemcpyAsync(out_counts_host, so + e->so_counts, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     return DN_OK;
+}
+
+extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
+                                      float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
+                                      void* stream_) {
+    return forward_host_impl(e, images_host, false, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
+}
+
+extern "C" int dn_engine_forward_host_u8(dn_engine* e, const uint8_t* images_host, int B, float* out_boxes_host,
+                                         float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
+                                         void* stream_) {
+    return forward_host_impl(e, images_host, true, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
 }
 
 extern "C" int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out) {

@@ -83,6 +83,14 @@ class _Engine:
                                                     out["scores"].data_ptr(), out["labels"].data_ptr(),
                                                     out["counts"].data_ptr(), stream))
 
+    def forward_host_u8(self, images_u8: Tensor, out):
+        B = images_u8.shape[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_forward_host_u8(self._handle, images_u8.data_ptr(), B, out["boxes"].data_ptr(),
+                                                       out["scores"].data_ptr(), out["labels"].data_ptr(),
+                                                       out["counts"].data_ptr(), stream))
+
     def buffer(self, tensor_name: str, batch: int) -> Tensor:
         """Copy of an intermediate activation as fp32 NCHW (for stage-by-stage parity tests)."""
         h, w, c = self.plan.tensors[tensor_name]
@@ -134,6 +142,55 @@ def make_post_params(P, K, image_h, image_w, score_thresh, nms_thresh, topk_cand
     p.box_weights = (ctypes.c_float * 4)(10.0, 10.0, 5.0, 5.0)      # generalized_ssd.py:170
     p.bbox_xform_clip = math.log(1000.0 / 16)                        # _utils.py:135
     return p
+
+
+def resize_bilinear(image: Tensor, size: Tuple[int, int], out: Optional[Tensor] = None) -> Tensor:
+    """Fixed-size bilinear resize of one CUDA [C,H,W] image (fp32 in [0,1], or uint8 -> x / 255 first) to fp32
+    [C,size[0],size[1]] -- the interpolate call of _resize_image_and_masks (transform.py:27-53) on the device."""
+    if not image.is_cuda:
+        raise RuntimeError("demonet_b200 operators run on CUDA tensors only (no CPU fallback)")
+    if image.dim() != 3:
+        raise ValueError("expected a [C, H, W] image, got {}".format(tuple(image.shape)))
+    if image.dtype not in (torch.float32, torch.uint8):
+        image = image.float()
+    image = image.contiguous()
+    C, H, W = image.shape
+    if out is None:
+        out = torch.empty(C, size[0], size[1], dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        _C.check(_C.lib().dn_resize_bilinear(image.data_ptr(), int(image.dtype == torch.uint8), C, H, W, out.data_ptr(),
+                                             size[0], size[1], torch.cuda.current_stream(image.device).cuda_stream))
+    return out
+
+
+def u8_to_f32(src: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """ToTensor's conversion on the device: uint8 -> fp32 / 255 (exact fp32 division)."""
+    if not src.is_cuda or src.dtype != torch.uint8:
+        raise RuntimeError("u8_to_f32 takes a CUDA uint8 tensor (no CPU fallback)")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    if src.numel() == 0:
+        return out
+    with torch.cuda.device(src.device):
+        _C.check(_C.lib().dn_u8_to_f32(src.data_ptr(), out.data_ptr(), src.numel(),
+                                       torch.cuda.current_stream(src.device).cuda_stream))
+    return out
+
+
+def rescale_boxes_(boxes: Tensor, original_sizes: List[Tuple[int, int]], new_size: Tuple[int, int]) -> Tensor:
+    """In place boxes[b] *= (rw, rh, rw, rh) for a padded CUDA [B,D,4] batch: resize_boxes (transform.py:278-292) with
+    the ratios formed in fp32 exactly as the reference forms them (orig / new as float32 tensors)."""
+    if not boxes.is_cuda:
+        raise RuntimeError("demonet_b200 operators run on CUDA tensors only (no CPU fallback)")
+    B, D = boxes.shape[0], boxes.shape[1]
+    orig = torch.tensor(original_sizes, dtype=torch.float32)
+    ratios = (orig / torch.tensor(new_size, dtype=torch.float32)).contiguous()        # [B,2] = (rh, rw)
+    ratios = ratios.to(boxes.device, non_blocking=False)
+    with torch.cuda.device(boxes.device):
+        _C.check(_C.lib().dn_rescale_boxes(boxes.data_ptr(), ratios.data_ptr(), B, D,
+                                           torch.cuda.current_stream(boxes.device).cuda_stream))
+    return boxes
 
 
 class SSDLiteB200(nn.Module):
@@ -271,32 +328,65 @@ class SSDLiteB200(nn.Module):
         host = in_dev.type != "cuda"
         device = torch.device("cuda", torch.cuda.current_device()) if host else in_dev
         eng = self._engine_for(device, B)
-        io = self._io_buffers(device, B, host)
+        resized = any(sz != (S, S) for sz in original_sizes)
+        # images that need the fixed-size resize (transform.py:27-53) go through the device kernel, so a host batch
+        # with such images is assembled on the device; an all-S x S host batch takes the pinned-staging path
+        io = self._io_buffers(device, B, host and not resized)
         batch = io["images"]
         for i, img in enumerate(images):
             if tuple(img.shape[-2:]) != (S, S):
-                # fixed-size bilinear resize, transform.py:27-53 (next-row f1: done with torch here)
-                img = torch.nn.functional.interpolate(img[None].float(), size=(S, S), mode="bilinear",
-                                                      align_corners=False)[0]
-            batch[i].copy_(img)
-        if host:
+                resize_bilinear(img.to(device), (S, S), out=batch[i])
+            else:
+                batch[i].copy_(img)
+        if host and not resized:
             eng.forward_host(batch, io)
             torch.cuda.current_stream(device).synchronize()
         else:
             eng.forward(batch, io)
+            if resized:                           # transform.postprocess / resize_boxes, transform.py:228-292
+                rescale_boxes_(io["boxes"], original_sizes, (S, S))
+        return self._detections(io, B, in_dev if host else None)
+
+    def _detections(self, io, B, to_device=None):
         counts = io["counts"].tolist()            # the one host sync: data-dependent output shapes
         detections = []
         for i in range(B):
             n = counts[i]
-            boxes = io["boxes"][i, :n].clone()
-            oh, ow = original_sizes[i]
-            if (oh, ow) != (S, S):                # transform.postprocess / resize_boxes, transform.py:228-292
-                rh = torch.tensor(oh, dtype=torch.float32) / torch.tensor(S, dtype=torch.float32)
-                rw = torch.tensor(ow, dtype=torch.float32) / torch.tensor(S, dtype=torch.float32)
-                boxes = boxes * torch.stack([rw, rh, rw, rh]).to(boxes.device)
-            detections.append({"boxes": boxes, "scores": io["scores"][i, :n].clone(),
-                               "labels": io["labels"][i, :n].clone()})
+            det = {"boxes": io["boxes"][i, :n].clone(), "scores": io["scores"][i, :n].clone(),
+                   "labels": io["labels"][i, :n].clone()}
+            if to_device is not None:
+                det = {k: v.to(to_device) for k, v in det.items()}
+            detections.append(det)
         return detections
+
+    def forward_uint8(self, images: Tensor):
+        """uint8 ingest: `images` is a [B,3,S,S] uint8 batch as a decoder produces it; the ToTensor
+        conversion x / 255 runs on the device (exact fp32 division), so the result equals
+        `self(list(images.float() / 255))`.  A pinned host batch crosses PCIe at one byte per sample."""
+        if images.dtype != torch.uint8 or images.dim() != 4 or tuple(images.shape[1:]) != (3, self.plan.size, self.plan.size):
+            raise ValueError("forward_uint8 expects a uint8 [B,3,{0},{0}] batch, got {1} {2}".format(
+                self.plan.size, images.dtype, tuple(images.shape)))
+        if not torch.cuda.is_available():
+            raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        B = images.shape[0]
+        if B == 0:
+            return []
+        host = not images.is_cuda
+        device = torch.device("cuda", torch.cuda.current_device()) if host else images.device
+        eng = self._engine_for(device, B)
+        io = self._io_buffers(device, B, host)
+        if host:
+            key = (str(device) + "/host_u8", B)
+            stage = self._io.get(key)
+            if stage is None:
+                stage = self._io[key] = {"images": torch.empty(images.shape, dtype=torch.uint8, pin_memory=True)}
+            stage["images"].copy_(images)
+            eng.forward_host_u8(stage["images"], io)
+            torch.cuda.current_stream(device).synchronize()
+        else:
+            u8_to_f32(images, out=io["images"])
+            eng.forward(io["images"], io)
+        return self._detections(io, B, images.device if host else None)
 
     def head_outputs(self, images: Tensor):
         """(cls_logits [B,P,K], bbox_regression [B,P,4]) of a [B,3,S,S] CUDA batch -- parity hook."""

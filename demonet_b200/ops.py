@@ -7,6 +7,7 @@ They keep the reference's names / argument meaning where the reference has a cou
   postprocess_detections(head_outputs, anchors, image_shape, ...)   SSD.postprocess_detections
   PostProcess(...)                                   box_head.PostProcess (legacy V2 flavour)
   DefaultBoxGenerator                                anchor_utils.DefaultBoxGenerator (table)
+  resize_bilinear / u8_to_f32 / rescale_boxes_       GeneralizedRCNNTransform resize, ToTensor, resize_boxes (transform.py)
 Everything raises if the CUDA library is missing or the tensors are not on a CUDA device.
 """
 import ctypes
@@ -17,7 +18,7 @@ import torch
 from torch import Tensor
 
 from . import _C
-from .module import make_post_params
+from .module import make_post_params, rescale_boxes_, resize_bilinear, u8_to_f32      # noqa: F401 (re-exported)
 
 
 def _stream(t: Tensor):

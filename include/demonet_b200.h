@@ -81,6 +81,24 @@ size_t dn_se_workspace_bytes(int B, int HW, int C);
 int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
                   int C, int Cs, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Transforms either side of the path (GeneralizedRCNNTransform, demonet/models/transform.py)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Fixed-size bilinear resize of ONE image, = torch.nn.functional.interpolate(image[None], size=(Ho,Wo),
+ * mode='bilinear', align_corners=False) as called by _resize_image_and_masks (transform.py:27-53).
+ * src: CHW, fp32 in [0,1] (src_is_u8 = 0) or uint8 (src_is_u8 = 1: converted like ToTensor, x / 255, first);
+ * dst: fp32 [C,Ho,Wo] (e.g. row b of the engine's [B,3,S,S] input batch). */
+int dn_resize_bilinear(const void* src, int src_is_u8, int C, int H, int W, float* dst, int Ho, int Wo, void* stream);
+
+/* dst[i] = src[i] / 255 in fp32 (ToTensor), n elements. */
+int dn_u8_to_f32(const uint8_t* src, float* dst, size_t n, void* stream);
+
+/* boxes[b,d,:] *= (rw, rh, rw, rh) with ratio_hw[b] = (rh, rw) = original size / network size, computed by the
+ * caller in fp32 exactly as resize_boxes does (transform.py:278-292; applied by postprocess, transform.py:228-247).
+ * boxes: fp32 [B,D,4] in place; ratio_hw: fp32 [B,2] device. */
+int dn_rescale_boxes(float* boxes, const float* ratio_hw, int B, int D, void* stream);
+
 typedef struct {
     int32_t num_priors;          /* P                                                          */
     int32_t num_classes;         /* K, including background column 0                           */
@@ -185,6 +203,11 @@ int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_b
 int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
                            float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
                            void* stream);
+/* same with uint8 [B,3,H,W] pixels (0..255) in pinned host memory: a quarter of the PCIe bytes; the ToTensor
+ * conversion x / 255 (exact in fp32) runs on the device in front of the stem (dn_u8_to_f32). */
+int dn_engine_forward_host_u8(dn_engine* e, const uint8_t* images_host, int B, float* out_boxes_host,
+                              float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
+                              void* stream);
 /* device pointers of intermediate arena buffers (valid after a forward), for stage-by-stage parity */
 int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out);
 /* enqueue a device-to-device copy of the first `bytes` bytes of an arena buffer into dst_dev */
