@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/demonet_b200.h"
 
@@ -57,6 +58,41 @@ inline int sm_count() {
     }
     return n;
 }
+
+// ---- programmatic dependent launch ----------------------------------------------------------
+// Every kernel of the forward is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_trigger() + pdl_wait(): its CTAs may become resident (and run whatever comes before the wait: barrier
+// setup, TMEM allocation, descriptor prefetch) while the previous kernel drains, but touch no activation memory
+// before that kernel has completed and flushed.  Inside the CUDA graph these become programmatic edges.
+// A kernel launched through launch_pdl MUST execute pdl_wait() before its first global access to data another
+// kernel writes, and before its first global write.  DN_PDL=0 turns the attribute off (measurement aid).
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("DN_PDL");
+        return !(v && atoi(v) == 0);
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);          // errors surface in DN_CHECK_LAUNCH
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) {

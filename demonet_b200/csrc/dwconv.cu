@@ -34,6 +34,8 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
     const int WT = (Wo + TW - 1) / TW;
     const unsigned total = (unsigned)B * Ho * WT * CV;          // < 2^31, checked on the host
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (tid >= total) return;
     const int cv = (int)(tid % (unsigned)CV);
     unsigned r = tid / (unsigned)CV;
@@ -111,10 +113,10 @@ static int launch_dw(const void* x, const float* w, const float* bias, void* y, 
     const uint4* xi = (const uint4*)x;
     uint4* yo = (uint4*)y;
     switch (act) {
-        case DN_ACT_RELU: dwconv_kernel<KS, S, TW, DN_ACT_RELU><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
-        case DN_ACT_RELU6: dwconv_kernel<KS, S, TW, DN_ACT_RELU6><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
-        case DN_ACT_HSWISH: dwconv_kernel<KS, S, TW, DN_ACT_HSWISH><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
-        default: dwconv_kernel<KS, S, TW, DN_ACT_NONE><<<blocks, 256, 0, stream>>>(xi, w, bias, yo, B, H, W, C, Ho, Wo);
+        case DN_ACT_RELU: launch_pdl(dwconv_kernel<KS, S, TW, DN_ACT_RELU>, blocks, 256, 0, stream, xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        case DN_ACT_RELU6: launch_pdl(dwconv_kernel<KS, S, TW, DN_ACT_RELU6>, blocks, 256, 0, stream, xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        case DN_ACT_HSWISH: launch_pdl(dwconv_kernel<KS, S, TW, DN_ACT_HSWISH>, blocks, 256, 0, stream, xi, w, bias, yo, B, H, W, C, Ho, Wo); break;
+        default: launch_pdl(dwconv_kernel<KS, S, TW, DN_ACT_NONE>, blocks, 256, 0, stream, xi, w, bias, yo, B, H, W, C, Ho, Wo);
     }
     DN_CHECK_LAUNCH();
     return DN_OK;
@@ -133,6 +135,8 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
                  float s1, float s2, int act) {
     __shared__ __align__(16) float sw[27 * COUT];
     __shared__ float sb[COUT];
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
     __syncthreads();
@@ -254,11 +258,11 @@ extern "C" int dn_stem_conv(const float* images, const float* w, const float* bi
     const unsigned blocks = (unsigned)((total + 127) / 128);
     cudaStream_t s = (cudaStream_t)stream_;
     if (Cout == 16)
-        stem_conv_kernel<16><<<blocks, 128, 0, s>>>(images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0], mean3_host[1],
-                                                   mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
+        launch_pdl(stem_conv_kernel<16>, blocks, 128, 0, s, images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0],
+                   mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
     else
-        stem_conv_kernel<32><<<blocks, 128, 0, s>>>(images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0], mean3_host[1],
-                                                   mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
+        launch_pdl(stem_conv_kernel<32>, blocks, 128, 0, s, images, w, bias, (uint4*)y, B, H, W, Ho, Wo, mean3_host[0],
+                   mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2], act);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

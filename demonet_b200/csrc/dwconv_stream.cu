@@ -73,7 +73,9 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();                 // the barriers are set up; nothing above touches activation memory
 
     // this CTA's channel block and its share of that block's output-row stream (B * H rows)
     const int cblk = blockIdx.x % sp.ncblk;
@@ -268,7 +270,7 @@ static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* 
     if (parts < 1) parts = 1;
     if (parts > (long long)B * H) parts = (long long)B * H;
     const long long grid = parts * sp.ncblk;
-    kern<<<(unsigned)grid, sp.threads, sp.smem, stream>>>(tm, w, bias, (uint2*)y, sp, B, H, W, C);
+    launch_pdl(kern, (unsigned)grid, sp.threads, sp.smem, stream, tm, w, bias, (uint2*)y, sp, B, H, W, C);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

@@ -58,6 +58,8 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
             : "memory");
     };
 
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bars[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bars[1])) : "memory");
@@ -251,7 +253,7 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
     if (gx > n_tiles) gx = (int)n_tiles;
     if (gx < 1) gx = 1;
     dim3 grid(gx, tl.chunks);
-    dwconv_tma_kernel<KS, S, ACT><<<grid, DW_THREADS, smem, stream>>>(tm, w, bias, (uint4*)y, tl, C, Ho, Wo, (int)n_tiles);
+    launch_pdl(dwconv_tma_kernel<KS, S, ACT>, grid, DW_THREADS, smem, stream, tm, w, bias, (uint4*)y, tl, C, Ho, Wo, (int)n_tiles);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

@@ -289,8 +289,8 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
             if (o.kind != DN_OP_PW) continue;
             int bn, nt, st, cols;
             size_t smem;
-            pwconv_tc_plan(o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
             const long long m_max = (long long)e->max_batch * o.h_in * o.w_in;
+            pwconv_tc_plan(m_max, o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
             int rc = make_tmap_bf16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128, 64);
             if (rc) return rc;
             rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn, 64);
@@ -347,8 +347,8 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 ep.out_row_stride = o.out_row_stride ? o.out_row_stride : o.c_out;
                 const int M = B * hw;
                 if (e->desc.gemm_impl == 0)
-                    rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], e->has_tmap_y[i] ? &e->tmap_y[i] : nullptr, ep, M, o.c_in,
-                                          o.c_out, s);
+                    rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], e->has_tmap_y[i] ? &e->tmap_y[i] : nullptr, ep, M,
+                                          (long long)e->max_batch * hw, o.c_in, o.c_out, s);
                 else
                     rc = pwconv_simt(buf_ptr(e, o.in_buf), W + o.w_off, ep, M, o.c_in, o.c_out, s);
                 break;

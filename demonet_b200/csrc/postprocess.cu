@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(P1_THREADS)
 softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict__ bbox,
                       const float* __restrict__ anchors, float* __restrict__ scores_t,
                       float4* __restrict__ boxes, int* __restrict__ hist, int P, int K, dn_postprocess_params prm) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_tile[];                    // [P1_ROWS][ld], ld odd -> conflict-free column reads
     __shared__ int s_hist[HIST_BINS];
     for (int i = threadIdx.x; i < HIST_BINS; i += P1_THREADS) s_hist[i] = 0;
@@ -317,6 +319,8 @@ struct RoundTargets {
 };
 __global__ void __launch_bounds__(32)
 pick_thresholds_kernel(const int* __restrict__ hist, float* __restrict__ thr, RoundTargets targets) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, lane = threadIdx.x;
     const int* gh = hist + (size_t)b * HIST_BINS;
     constexpr int PER = (HIST_BINS + 31) / 32;
@@ -369,6 +373,8 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
                   unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_counts, int P, int K, int cap,
                   float score_thresh, int topk, float min_box_size, const float* __restrict__ thr,
                   const int* __restrict__ done, int round) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_raw);              // [next_pow2(P)]
     __shared__ int s_n;
@@ -449,6 +455,8 @@ __global__ void __launch_bounds__(256)
 class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ prefix,
                       const float4* __restrict__ boxes, Entry* __restrict__ out_entries, int* __restrict__ out_counts,
                       const int* __restrict__ done, int B, int P, int K, int cap, float thr_up, int D, int round) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nc = K - 1;
@@ -531,6 +539,8 @@ __global__ void __launch_bounds__(NMS_CTA_THREADS)
 class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ prefix,
                      const float4* __restrict__ boxes, Entry* __restrict__ out_entries, int* __restrict__ out_counts,
                      const int* __restrict__ done, int P, int K, int cap, float thr_up, int D, int round) {
+    pdl_trigger();
+    pdl_wait();
     const int nc = K - 1;
     const int prob = blockIdx.x;
     const int b = prob / nc;
@@ -595,6 +605,8 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
                   const float4* __restrict__ boxes, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
                   long long* __restrict__ out_labels, int* __restrict__ out_counts, int* __restrict__ done, int P, int K,
                   int D, int round) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     if (round > 0 && done[b]) return;
     __shared__ Entry s_ent[P3_SMEM_ENTRIES];
@@ -852,26 +864,25 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
                 softmax_decode_kernel<<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors, scores_t,
                                                                           boxes, hist, P, K, *p);
                 DN_CHECK_LAUNCH();
-                pick_thresholds_kernel<<<B, 32, 0, stream>>>(hist, thr, targets);
+                launch_pdl(pick_thresholds_kernel, B, 32, 0, stream, (const int*)hist, thr, targets);
                 DN_CHECK_LAUNCH();
             }
             for (int r = 0; r < NMS_ROUNDS; ++r) {
                 if (phase == 1 || !ms3) {
                     dim3 grid(K - 1, B);
-                    class_sort_kernel<<<grid, P2_THREADS, smem_sort, stream>>>(scores_t, boxes, cand, ccount, P, K, cap,
-                                                                              p->score_thresh, p->topk_candidates,
-                                                                              p->min_box_size, thr, done, r);
+                    launch_pdl(class_sort_kernel, grid, P2_THREADS, smem_sort, stream, scores_t, boxes, cand, ccount, P, K, cap,
+                               p->score_thresh, p->topk_candidates, p->min_box_size, thr, done, r);
                     DN_CHECK_LAUNCH();
-                    class_nms_warp_kernel<<<(unsigned)ceil_div<long long>(problems, nms_warps), nms_warps * 32, smem_nms,
-                                            stream>>>(cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
+                    launch_pdl(class_nms_warp_kernel, (unsigned)ceil_div<long long>(problems, nms_warps), nms_warps * 32, smem_nms,
+                               stream, cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
                     DN_CHECK_LAUNCH();
-                    class_nms_cta_kernel<<<(unsigned)problems, NMS_CTA_THREADS, (size_t)D * 20, stream>>>(
-                        cand, ccount, boxes, entries, counts, done, P, K, cap, thr_up, D, r);
+                    launch_pdl(class_nms_cta_kernel, (unsigned)problems, NMS_CTA_THREADS, (size_t)D * 20, stream, cand, ccount,
+                               boxes, entries, counts, done, P, K, cap, thr_up, D, r);
                     DN_CHECK_LAUNCH();
                 }
                 if (phase == 2 || !ms3) {
-                    merge_topd_kernel<<<B, P3_THREADS, 0, stream>>>(entries, counts, thr, boxes, (float4*)out_boxes, out_scores,
-                                                            (long long*)out_labels, out_counts, done, P, K, D, r);
+                    launch_pdl(merge_topd_kernel, B, P3_THREADS, 0, stream, entries, counts, thr, boxes, (float4*)out_boxes,
+                               out_scores, (long long*)out_labels, out_counts, done, P, K, D, r);
                     DN_CHECK_LAUNCH();
                 }
             }
@@ -1036,17 +1047,20 @@ bnms_class_kernel(const float4* __restrict__ boxes, const long long* __restrict_
         // feed the tile's members to the consumer in groups that complete 32-wide chunks
         int fed = 0;
         while (fed < total) {
-            const int room = 32 - s_cnt;                                   // uniform (read after barrier)
+            // s_cnt is read ONCE per iteration, here, behind the barrier that closed the previous one: thread 0
+            // rewrites it below, possibly before a slower warp would get to a second read
+            const int cur = s_cnt;
+            const int room = 32 - cur;
             const int take = min(room, total - fed);
             if (mine && my_pos >= fed && my_pos < fed + take) {
-                const int slot = s_cnt + (my_pos - fed);
+                const int slot = cur + (my_pos - fed);
                 const float4 q = boxes[idx];
                 s_chunk_box[slot] = q;
                 s_chunk_area[slot] = box_area(q);
                 s_chunk_rank[slot] = r;
             }
             __syncthreads();
-            const int cnt = s_cnt + take;
+            const int cnt = cur + take;
             fed += take;
             const bool last_of_class = (seen + fed == members);
             if (cnt == 32 || last_of_class) {

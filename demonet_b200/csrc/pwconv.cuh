@@ -40,8 +40,10 @@ int pwconv_simt(const void* x, const void* w, const PwEpilogue& ep, int M, int K
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream);
 // pieces of pwconv_tc that the engine caches per layer
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols);
-void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes);
-int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, int K,
+// m_plan: the row count the tile shape is planned for (the engine passes its max-batch M so that the weight tensor
+// map built at load time and every later launch agree)
+void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes);
+int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
                      int N, cudaStream_t stream);
 
 }  // namespace dn

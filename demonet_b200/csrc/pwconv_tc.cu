@@ -207,10 +207,12 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
+    pdl_trigger();
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();                 // descriptors prefetched, barriers and TMEM set up while the previous kernel drains
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -451,13 +453,17 @@ static size_t smem_cap(int n) {
     return n == 1 ? (size_t)(227 * 1024 - TC_STATIC_SMEM - 256) : (size_t)(228 * 1024) / n - TC_STATIC_SMEM - 1024 - 256;
 }
 
-void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
+void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
     static const int bn_max = [] {                     // measurement aid: DN_PW_BN_MAX=64|128 caps the tile width
         const char* v = getenv("DN_PW_BN_MAX");
         const int x = v ? atoi(v) : 256;
         return (x == 64 || x == 128) ? x : 256;
     }();
-    const int nt = (N + bn_max - 1) / bn_max;
+    // small maps: with 256-wide tiles the grid would leave most SMs idle, so split N further (r01 A/B)
+    const long long m_tiles = (m_plan + TC_BLOCK_M - 1) / TC_BLOCK_M;
+    int cap_n = bn_max;
+    while (cap_n > 64 && m_tiles * ((N + cap_n - 1) / cap_n) < sm_count()) cap_n >>= 1;
+    const int nt = (N + cap_n - 1) / cap_n;
     int bn = (N + nt - 1) / nt;
     bn = nt > 1 ? (bn + 63) & ~63 : (bn + 15) & ~15;      // 64-column groups must not straddle two N tiles
     int cols = 32;
@@ -468,6 +474,23 @@ void pwconv_tc_plan(int K, int N, int* block_n, int* n_tiles, int* stages, int* 
     int st = kb >= 3 ? TC_MAX_STAGES : kb + 1;            // short-K layers: fewer stages -> more CTAs per SM
     auto need = [&](int stg) { return 1024 + (size_t)stg * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2) + sizeof(TcBarriers); };
     while (st > 2 && need(st) > smem_cap(1)) --st;
+    // Resident CTAs beat ring depth: these GEMMs are bound by the latency chains of the epilogue warps and of the
+    // load -> MMA -> commit loop, not by bytes in flight (same total either way), so take the largest CTA count whose
+    // TMEM columns and a 2-stage ring fit, then deepen the ring as far as that count allows (r01 A/B: never slower,
+    // up to 1.45x on the K >> N project layers).  DN_PW_OCC=0 restores the deep-ring plan (measurement aid).
+    static const int prefer_occ = [] {
+        const char* v = getenv("DN_PW_OCC");
+        return v ? atoi(v) : 1;
+    }();
+    if (prefer_occ) {
+        for (int n = 4; n >= 2; --n)
+            if (n * cols <= 512 && need(2) <= smem_cap(n)) {
+                int s2 = 2;
+                while (s2 < TC_MAX_STAGES && s2 < kb + 1 && need(s2 + 1) <= smem_cap(n)) ++s2;
+                st = s2;
+                break;
+            }
+    }
     *stages = st;
     *tmem_cols = cols;
     *smem_bytes = need(st);
@@ -483,18 +506,18 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CU
                                            (int)smem_cap(1)));
         configured = true;
     }
-    pwconv_tc_kernel<ACT, TMA_STORE><<<grid, TC_THREADS, smem_req, stream>>>(ta, tw, ty, ep, M, K, N, bn, nt, tiles, st, cols);
+    launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles, st, cols);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
 
 // ty: tensor map of the bf16 output ([rows, N], box 32 x 64) or nullptr.  The TMA-store epilogue is used when
 // ty is given and the layer has neither a residual nor fp32 / strided output.
-int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, int K,
+int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
                      int N, cudaStream_t stream) {
     int bn, nt, st, cols;
     size_t smem;
-    pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
+    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem);
     // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
     // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
     // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).
@@ -529,7 +552,7 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream) {
     int bn, nt, st, cols;
     size_t smem;
-    pwconv_tc_plan(K, N, &bn, &nt, &st, &cols, &smem);
+    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem);
     CUtensorMap ta, tw, ty;
     int rc = make_tmap_bf16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
     if (rc) return rc;
@@ -541,7 +564,7 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
         rc = make_tmap_bf16_2d(&ty, ep.y, M, N, 32, 32);
         if (rc) return rc;
     }
-    return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, K, N, stream);
+    return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, M, K, N, stream);
 }
 
 }  // namespace dn

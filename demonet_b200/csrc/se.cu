@@ -54,6 +54,8 @@ static SePlan se_plan(int B, int HW, int C) {
 __global__ void __launch_bounds__(SE_POOL_THREADS)
 se_pool_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int HW, int C, int CV, int rows, int chunk_px) {
     extern __shared__ float s_part[];           // [rows][C]
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
     const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
@@ -101,6 +103,8 @@ se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, c
               float* __restrict__ hidden_g, int B, int HW, int C, int Cs, int chunks) {
     extern __shared__ __align__(16) float s_fc[];
     float* pooled = s_fc;                       // [SE_GI][C]
+    pdl_trigger();
+    pdl_wait();
     const int rank = blockIdx.x;
     const int b0 = blockIdx.y * SE_GI;
     float* hidden = hidden_g + (long long)blockIdx.y * Cs * SE_GI;
@@ -170,6 +174,8 @@ se_fc2_kernel(const float* __restrict__ hidden_g, const float* __restrict__ w2t,
     extern __shared__ __align__(16) float s_fc[];
     float* hidden = s_fc;                       // [Cs][SE_GI]
     float* part = hidden + Cs * SE_GI;          // [SE_NC slices][SE_GI][C / SE_NC]
+    pdl_trigger();
+    pdl_wait();
     const int rank = blockIdx.x;
     const int b0 = blockIdx.y * SE_GI;
     const int tid = threadIdx.x;
@@ -224,6 +230,8 @@ se_fc2_kernel(const float* __restrict__ hidden_g, const float* __restrict__ w2t,
 // x[b][p][c] *= scale[b][c]
 __global__ void __launch_bounds__(SE_POOL_THREADS)
 se_scale_kernel(uint4* __restrict__ x, const float* __restrict__ scale, int HW, int C, int CV, int rows, int chunk_px) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
     if (r >= rows) return;
@@ -287,14 +295,16 @@ extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const fl
         DN_CHECK_CUDA(cudaFuncSetAttribute(se_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         fc_configured = 160 * 1024;
     }
-    se_pool_kernel<<<dim3(p.pool_chunks, B), SE_POOL_THREADS, pool_smem, s>>>((const uint4*)x, partial, HW, C, p.CV, p.rows,
-                                                                                p.pool_px);
+    launch_pdl(se_pool_kernel, dim3(p.pool_chunks, B), SE_POOL_THREADS, pool_smem, s, (const uint4*)x, partial, HW, C, p.CV, p.rows,
+               p.pool_px);
     DN_CHECK_LAUNCH();
-    se_fc1_kernel<<<dim3(SE_NC, groups), SE_FC_THREADS, fc1_smem, s>>>(partial, w1, b1, hidden, B, HW, C, Cs, p.pool_chunks);
+    launch_pdl(se_fc1_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc1_smem, s, (const float*)partial, w1, b1, hidden, B, HW, C, Cs,
+               p.pool_chunks);
     DN_CHECK_LAUNCH();
-    se_fc2_kernel<<<dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s>>>(hidden, w2t, b2, scale, B, C, Cs);
+    launch_pdl(se_fc2_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)hidden, w2t, b2, scale, B, C, Cs);
     DN_CHECK_LAUNCH();
-    se_scale_kernel<<<dim3(p.scale_chunks, B), SE_POOL_THREADS, 0, s>>>((uint4*)x, scale, HW, C, p.CV, p.rows, p.scale_px);
+    launch_pdl(se_scale_kernel, dim3(p.scale_chunks, B), SE_POOL_THREADS, 0, s, (uint4*)x, (const float*)scale, HW, C, p.CV, p.rows,
+               p.scale_px);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

@@ -65,6 +65,8 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __res
             "l"(&tmap_img), "r"(ba), "r"(tx * ST_TW * 2 - ST_XOFF), "r"(ty * ST_TH * 2 - 1), "r"(b * 3)
             : "memory");
     };
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_smem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -222,7 +224,7 @@ static int stem_launch_t(const CUtensorMap& tm, const float* w, const float* bia
     DN_REQUIRE(n_tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "stem problem too large");
     long long grid = (long long)ctas_per_sm * sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    stem_tma_kernel<COUT, NPX><<<(unsigned)grid, THREADS, smem, stream>>>(tm, w, bias, (uint4*)y, H, W, Ho, Wo, tiles_x, tiles_y,
+    launch_pdl(stem_tma_kernel<COUT, NPX>, (unsigned)grid, THREADS, smem, stream, tm, w, bias, (uint4*)y, H, W, Ho, Wo, tiles_x, tiles_y,
                                                                          (int)n_tiles, nm, act);
     DN_CHECK_LAUNCH();
     return DN_OK;
