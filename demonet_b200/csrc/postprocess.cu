@@ -597,8 +597,9 @@ class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int
 // otherwise done[b] stays 0 and the next round goes deeper.
 // ---------------------------------------------------------------------------------------------
 constexpr int P3_MAX_PER_LANE = 8;     // supports K-1 <= 256 classes
-constexpr int P3_THREADS = 128;
-constexpr int P3_SMEM_ENTRIES = 3840;  // 30 KiB of kept entries staged in shared memory
+constexpr int P3_THREADS = 256;
+constexpr int P3_SORT_CAP = 2048;      // kept entries per image that are staged and sorted in shared memory (rank < 4096,
+                                       // class < 256 and slot < 4096 share the low 32 key bits)
 
 __global__ void __launch_bounds__(P3_THREADS)
 merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts, const float* __restrict__ thr,
@@ -609,7 +610,7 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
     pdl_wait();
     const int b = blockIdx.x;
     if (round > 0 && done[b]) return;
-    __shared__ Entry s_ent[P3_SMEM_ENTRIES];
+    __shared__ Entry s_ent[P3_SORT_CAP];
     __shared__ int s_off[32 * P3_MAX_PER_LANE + 1];
     const int nc = K - 1;
     const int lane = threadIdx.x & 31;
@@ -630,22 +631,54 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
         if (threadIdx.x == 0) done[b] = 0;
         return;
     }
-    // stage the kept lists of the image in shared memory (class-major, each list in descending order) so
-    // that the serial merge below reads shared memory instead of chasing L2 latency
-    const bool staged = total <= P3_SMEM_ENTRIES;
-    if (staged) {
-        for (int f = threadIdx.x; f < total; f += P3_THREADS) {
-            int lo = 0, hi = nc;                  // class whose [off, off + cnt) contains f
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_off[mid] <= f) lo = mid;
-                else hi = mid;
+    // Usual case (the kept entries of the image fit in shared memory): stage them, sort 64-bit keys
+    // (score desc | class asc | rank-in-class asc | slot) with the whole CTA and emit the first D in parallel.
+    __shared__ __align__(16) unsigned long long s_key[P3_SORT_CAP];      // aliased by s_sel_prior in the serial path
+    if (total <= P3_SORT_CAP) {
+        int n_pad = 32;
+        while (n_pad < total) n_pad <<= 1;
+        for (int f = threadIdx.x; f < n_pad; f += P3_THREADS) {
+            unsigned long long key = ~0ull;
+            if (f < total) {
+                int lo = 0, hi = nc;              // class whose [off, off + cnt) contains f
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= f) lo = mid;
+                    else hi = mid;
+                }
+                const int rank = f - s_off[lo];
+                const Entry e = entries[((size_t)b * nc + lo) * D + rank];
+                s_ent[f] = e;
+                key = ((unsigned long long)(~orderable(e.score)) << 32) |
+                      ((unsigned long long)lo << 24) | ((unsigned long long)rank << 12) | (unsigned long long)f;
             }
-            s_ent[f] = entries[((size_t)b * nc + lo) * D + (f - s_off[lo])];
+            s_key[f] = key;
         }
+        __syncthreads();
+        bitonic_sort_u64(s_key, n_pad);
+        const int nsel = min(D, total);
+        for (int i = threadIdx.x; i < D; i += P3_THREADS) {
+            if (i < nsel) {
+                const unsigned long long key = s_key[i];
+                const Entry e = s_ent[(int)(key & 0xfffu)];
+                out_scores[(size_t)b * D + i] = e.score;
+                out_labels[(size_t)b * D + i] = (long long)((int)((key >> 24) & 0xffu) + 1);
+                out_boxes[(size_t)b * D + i] = boxes[(size_t)b * P + e.prior];
+            } else {
+                out_scores[(size_t)b * D + i] = 0.f;
+                out_labels[(size_t)b * D + i] = 0;
+                out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (threadIdx.x == 0) {
+            done[b] = 1;
+            out_counts[b] = nsel;
+        }
+        return;
     }
-    __syncthreads();
-    __shared__ int s_sel_prior[4096];       // detections_per_img <= 4096
+    // Rare case (deep rounds of the stress configuration): serial k-way merge by one warp straight from global memory
+    const bool staged = false;
+    int* s_sel_prior = reinterpret_cast<int*>(s_key);       // detections_per_img <= 4096 = 2 * P3_SORT_CAP ints
     __shared__ int s_nsel;
     if (threadIdx.x < 32) {
     if (lane == 0) done[b] = 1;

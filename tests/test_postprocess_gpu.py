@@ -41,7 +41,9 @@ def test_stress_golden(golden_dir):
 
 
 @pytest.mark.parametrize("B,P,K,topk,D,thr", [(3, 3234, 91, 300, 300, 0.001), (2, 3000, 21, 400, 100, 0.01),
-                                              (1, 8190, 21, 400, 200, 0.02), (5, 37, 3, 10, 7, 0.2), (2, 3234, 91, 300, 300, 0.9999)])
+                                              (1, 8190, 21, 400, 200, 0.02), (5, 37, 3, 10, 7, 0.2), (2, 3234, 91, 300, 300, 0.9999),
+                                              # > 2048 kept entries per image: the serial k-way merge instead of the sorted one
+                                              (1, 8190, 21, 1000, 3000, 0.001)])
 def test_vs_oracle(B, P, K, topk, D, thr):
     gen = torch.Generator().manual_seed(P + K)
     logits = torch.randn(B, P, K, generator=gen) * 3.0
@@ -58,6 +60,8 @@ def test_vs_oracle(B, P, K, topk, D, thr):
         if o["labels"].shape[0] == 0:
             assert dets[i]["labels"].numel() == 0
             continue
+        if D == 3000:
+            assert o["labels"].shape[0] > 2048
         _match(dets[i], o["labels"], o["scores"], o["boxes"], min_frac=0.97)
 
 
