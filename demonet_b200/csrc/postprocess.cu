@@ -372,15 +372,18 @@ __global__ void __launch_bounds__(P2_THREADS)
 class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__ boxes,
                   unsigned long long* __restrict__ cand_keys, int* __restrict__ cand_counts, int P, int K, int cap,
                   float score_thresh, int topk, float min_box_size, const float* __restrict__ thr,
-                  const int* __restrict__ done, int round) {
+                  const int* __restrict__ done, int round, int B) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_raw);              // [next_pow2(P)]
     __shared__ int s_n;
-    const int c = blockIdx.x, b = blockIdx.y;
-    if (round > 0 && done[b]) return;
+    const int c = blockIdx.x;
     const int lane = threadIdx.x & 31;
+    // round 0: gridDim.y == B, one image per CTA.  Later rounds run on a few image slots per class and skip the
+    // images that are done (usually all of them), instead of launching B x (K-1) CTAs that exit at once.
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    if (round > 0 && done[b]) continue;
     const float* sc = scores_t + ((size_t)b * (K - 1) + c) * P;
     const float4* bx = boxes + (size_t)b * P;
     const float round_thr = thr[b * NMS_ROUNDS + round];      // lazy NMS: only the top of the image this round
@@ -421,17 +424,19 @@ class_sort_kernel(const float* __restrict__ scores_t, const float4* __restrict__
     const size_t slot = (size_t)b * (K - 1) + c;
     if (n == 0) {
         if (threadIdx.x == 0) cand_counts[slot] = 0;
-        return;
+    } else {
+        int n_pad = 32;
+        while (n_pad < n) n_pad <<= 1;
+        for (int i = n + threadIdx.x; i < n_pad; i += P2_THREADS) keys[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_u64(keys, n_pad);                       // (score desc, prior asc)
+        const int m = (topk > 0 && topk < n) ? topk : n;     // top-k, generalized_ssd.py:376-378
+        unsigned long long* dst = cand_keys + slot * cap;
+        for (int i = threadIdx.x; i < m; i += P2_THREADS) dst[i] = keys[i];
+        if (threadIdx.x == 0) cand_counts[slot] = m;
     }
-    int n_pad = 32;
-    while (n_pad < n) n_pad <<= 1;
-    for (int i = n + threadIdx.x; i < n_pad; i += P2_THREADS) keys[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort_u64(keys, n_pad);                       // (score desc, prior asc)
-    const int m = (topk > 0 && topk < n) ? topk : n;     // top-k, generalized_ssd.py:376-378
-    unsigned long long* dst = cand_keys + slot * cap;
-    for (int i = threadIdx.x; i < m; i += P2_THREADS) dst[i] = keys[i];
-    if (threadIdx.x == 0) cand_counts[slot] = m;
+    __syncthreads();                                         // keys / s_n are reused by the next image of this CTA
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -454,16 +459,21 @@ constexpr int NMS_WARP_MAX = 96;       // class lists up to this length run on o
 __global__ void __launch_bounds__(256)
 class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ prefix,
                       const float4* __restrict__ boxes, Entry* __restrict__ out_entries, int* __restrict__ out_counts,
-                      const int* __restrict__ done, int B, int P, int K, int cap, float thr_up, int D, int round) {
+                      const int* __restrict__ done, int B, int P, int K, int cap, float thr_up, int D, int round,
+                      int img_slots) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nc = K - 1;
-    const long long prob = (long long)blockIdx.x * warps + warp;
-    if (prob >= (long long)B * nc) return;
-    const int b = (int)(prob / nc);
-    if (round > 0 && done[b]) return;
+    // warp = (image slot, class); round 0 has one slot per image, later rounds a few slots that walk the images
+    // and skip the ones that are done
+    const long long wg = (long long)blockIdx.x * warps + warp;
+    if (wg >= (long long)img_slots * nc) return;
+    const int cls = (int)(wg % nc);
+    for (int b = (int)(wg / nc); b < B; b += img_slots) {
+    if (round > 0 && done[b]) continue;
+    const long long prob = (long long)b * nc + cls;
     // per-warp slices: kept boxes [D], chunk boxes [32], kept areas [D], chunk areas [32]
     float4* kept_box = reinterpret_cast<float4*>(s_raw) + (size_t)warp * (D + 32);
     float4* cbox = kept_box + D;
@@ -475,7 +485,7 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
     const float4* bx = boxes + (size_t)b * P;
     Entry* dst = out_entries + (size_t)prob * D;
     const int q = prefix[prob];
-    if (q > NMS_WARP_MAX) return;                     // long lists are handled by class_nms_cta_kernel
+    if (q > NMS_WARP_MAX) continue;                   // long lists are handled by class_nms_cta_kernel
     int nk = 0;
     for (int c0 = 0; c0 < q && nk < D; c0 += 32) {
         const int cnt = min(32, q - c0);
@@ -529,12 +539,16 @@ class_nms_warp_kernel(const unsigned long long* __restrict__ cand_keys, const in
         __syncwarp();
     }
     if (lane == 0) out_counts[prob] = nk;
+    __syncwarp();
+    }
 }
 
 // Long class lists (a dominant class easily holds a few hundred candidates) would make their warp the
 // straggler of the whole launch, so they get a full CTA: every warp tests the 32-candidate chunk against a
 // slice of the kept list (nms_consume_chunk), warp 0 resolves the chunk.
 constexpr int NMS_CTA_THREADS = 256;
+constexpr int NMS_CTA_CLASS_SLOTS = 4;      // CTAs per image of class_nms_cta_kernel (classes are dealt round-robin)
+constexpr int LATE_ROUND_SLOTS = 8;         // image slots per class of the sort / warp-NMS launches of rounds >= 1
 __global__ void __launch_bounds__(NMS_CTA_THREADS)
 class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int* __restrict__ prefix,
                      const float4* __restrict__ boxes, Entry* __restrict__ out_entries, int* __restrict__ out_counts,
@@ -542,11 +556,10 @@ class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int
     pdl_trigger();
     pdl_wait();
     const int nc = K - 1;
-    const int prob = blockIdx.x;
-    const int b = prob / nc;
+    // CTA = (image, class residue): walks the classes c = blockIdx.y, blockIdx.y + gridDim.y, ... of its image and
+    // only works on the long lists -- a grid of B x (K-1) CTAs that nearly all exit at once costs more than the NMS
+    const int b = blockIdx.x;
     if (round > 0 && done[b]) return;
-    const int q = prefix[prob];
-    if (q <= NMS_WARP_MAX) return;
     extern __shared__ __align__(16) unsigned char s_raw[];
     float4* kept_box = reinterpret_cast<float4*>(s_raw);               // [D]
     float* kept_area = reinterpret_cast<float*>(kept_box + D);         // [D]
@@ -555,6 +568,12 @@ class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int
     __shared__ float4 s_chunk_box[32];
     __shared__ float s_chunk_area[32];
     __shared__ unsigned long long s_chunk_key[32];
+    const int lane = threadIdx.x & 31;
+    const float4* bx = boxes + (size_t)b * P;
+    for (int cls = blockIdx.y; cls < nc; cls += gridDim.y) {
+    const int prob = b * nc + cls;
+    const int q = prefix[prob];
+    if (q <= NMS_WARP_MAX) continue;                   // uniform
     if (threadIdx.x == 0) {
         s_nkept = 0;
         s_dead = 0u;
@@ -562,9 +581,7 @@ class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int
     __syncthreads();
     NmsState st{kept_box, kept_area, s_chunk_box, s_chunk_area, &s_dead, &s_nkept};
     const unsigned long long* keys = cand_keys + (size_t)prob * cap;
-    const float4* bx = boxes + (size_t)b * P;
     Entry* dst = out_entries + (size_t)prob * D;
-    const int lane = threadIdx.x & 31;
     for (int c0 = 0; c0 < q; c0 += 32) {
         const int cnt = min(32, q - c0);
         if (threadIdx.x < cnt) {
@@ -588,6 +605,8 @@ class_nms_cta_kernel(const unsigned long long* __restrict__ cand_keys, const int
         __syncthreads();
     }
     if (threadIdx.x == 0) out_counts[prob] = s_nkept;
+    __syncthreads();                         // the next class of this CTA resets s_nkept / the chunk buffers
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -880,7 +899,6 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
     }
     const float thr_up = threshold_up(p->nms_thresh);
     const RoundTargets targets = round_targets(D);
-    const long long problems = (long long)B * (K - 1);
     cudaEvent_t ev[2] = {nullptr, nullptr};
     if (ms3) {
         DN_CHECK_CUDA(cudaEventCreate(&ev[0]));
@@ -902,15 +920,17 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
             }
             for (int r = 0; r < NMS_ROUNDS; ++r) {
                 if (phase == 1 || !ms3) {
-                    dim3 grid(K - 1, B);
+                    const int slots = (r == 0) ? B : std::min(B, LATE_ROUND_SLOTS);
+                    dim3 grid(K - 1, slots);
                     launch_pdl(class_sort_kernel, grid, P2_THREADS, smem_sort, stream, scores_t, boxes, cand, ccount, P, K, cap,
-                               p->score_thresh, p->topk_candidates, p->min_box_size, thr, done, r);
+                               p->score_thresh, p->topk_candidates, p->min_box_size, thr, done, r, B);
                     DN_CHECK_LAUNCH();
-                    launch_pdl(class_nms_warp_kernel, (unsigned)ceil_div<long long>(problems, nms_warps), nms_warps * 32, smem_nms,
-                               stream, cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up, D, r);
+                    launch_pdl(class_nms_warp_kernel, (unsigned)ceil_div<long long>((long long)slots * (K - 1), nms_warps),
+                               nms_warps * 32, smem_nms, stream, cand, ccount, boxes, entries, counts, done, B, P, K, cap, thr_up,
+                               D, r, slots);
                     DN_CHECK_LAUNCH();
-                    launch_pdl(class_nms_cta_kernel, (unsigned)problems, NMS_CTA_THREADS, (size_t)D * 20, stream, cand, ccount,
-                               boxes, entries, counts, done, P, K, cap, thr_up, D, r);
+                    launch_pdl(class_nms_cta_kernel, dim3(B, std::min(K - 1, NMS_CTA_CLASS_SLOTS)), NMS_CTA_THREADS, (size_t)D * 20,
+                               stream, cand, ccount, boxes, entries, counts, done, P, K, cap, thr_up, D, r);
                     DN_CHECK_LAUNCH();
                 }
                 if (phase == 2 || !ms3) {
