@@ -52,13 +52,37 @@ __device__ __forceinline__ uint2 dws_lds64(uint32_t addr) {
     return v;
 }
 
+// one staged pixel of a thread: NP packed bf16 pairs (8 or 4 bytes)
+template <int NP>
+__device__ __forceinline__ void dws_lds_px(uint32_t addr, uint32_t* v) {
+    if (NP == 2) {
+        const uint2 t = dws_lds64(addr);
+        v[0] = t.x, v[NP - 1] = t.y;
+    } else {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[0]) : "r"(addr));
+    }
+}
+// one tap of a thread's channels: NP float pairs (16 or 8 bytes)
+template <int NP>
+__device__ __forceinline__ void dws_lds_tap(uint32_t addr, float2* wv) {
+    if (NP == 2) {
+        const float4 f = dws_lds128(addr);
+        wv[0] = make_float2(f.x, f.y), wv[NP - 1] = make_float2(f.z, f.w);
+    } else {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(wv[0].x), "=f"(wv[0].y) : "r"(addr));
+    }
+}
+
 constexpr int DWS_MAX_STAGES = 8;
 
-template <int KS, int TW, int ACT, int NT>
+// CH = channels per consumer thread (4 or 2).  Every tap is read from shared memory once per input row and thread and
+// feeds TW * CH / 2 packed FMAs: the 5x5 kernel runs CH = 2, TW = 4 (8-byte tap loads, 4 FFMA2 each) because with
+// CH = 4, TW = 2 (16-byte tap loads, 4 FFMA2 each) the tap traffic alone oversubscribes the shared-memory pipe 2x.
+template <int KS, int TW, int CH, int ACT, int NT>
 __global__ void __launch_bounds__(NT, NT <= 160 ? 3 : 1)
 dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w, const float* __restrict__ bias,
-                     uint2* __restrict__ y, DwStream sp, int B, int H, int W, int C) {
-    constexpr int P = KS / 2, TWIN = TW + KS - 1;
+                     uint32_t* __restrict__ y, DwStream sp, int B, int H, int W, int C) {
+    constexpr int P = KS / 2, TWIN = TW + KS - 1, NP = CH / 2;
     extern __shared__ __align__(128) unsigned char dws_smem[];
     __shared__ uint64_t full[DWS_MAX_STAGES], empty[DWS_MAX_STAGES];
     unsigned char* stages = dws_smem;
@@ -110,11 +134,11 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
 
     // ---- consumers ----
     const int ct = threadIdx.x - 32;
-    const int nqb = sp.CB >> 2;                      // channel quads per block
+    const int nqb = sp.CB / CH;                      // channel groups (CH channels) per block
     const int q = ct % nqb, cb = ct / nqb;
     const bool active = cb < sp.ncb;
     const int ow0 = cb * TW;
-    const int nq = C >> 2;
+    const int cw = C >> 1;                           // 32-bit words per pixel of the output
     const int row_bytes = sp.IW * sp.CB * 2;
     const int n_cons = n_cons_warps * 32;
 
@@ -123,49 +147,51 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     // (no per-tap address registers); lanes are k*k*16 bytes apart = 4 banks mod 32, conflict-free for LDS.128
     for (int i = ct; i < KS * KS * sp.CB; i += n_cons) {
         const int c = i % sp.CB, t = i / sp.CB;
-        wsm[((c >> 2) * (KS * KS) + t) * 4 + (c & 3)] = __ldg(w + t * C + cblk * sp.CB + c);
+        wsm[((c / CH) * (KS * KS) + t) * CH + (c % CH)] = __ldg(w + t * C + cblk * sp.CB + c);
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
-    const uint32_t wq = dws_u32(wsm + q * (KS * KS) * 4);
-    float2 b01, b23;
-    {
-        const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + cblk * sp.CB + (active ? q : 0) * 4));
-        b01 = make_float2(bs.x, bs.y), b23 = make_float2(bs.z, bs.w);
-    }
-    const uint32_t stage0 = dws_u32(stages) + (uint32_t)((ow0 * sp.CB + q * 4) * 2);
+    const uint32_t wq = dws_u32(wsm + q * (KS * KS) * CH);
+    float2 bv[NP];
+#pragma unroll
+    for (int h = 0; h < NP; ++h) bv[h] = __ldg(reinterpret_cast<const float2*>(bias + cblk * sp.CB + (active ? q : 0) * CH) + h);
+    const uint32_t stage0 = dws_u32(stages) + (uint32_t)((ow0 * sp.CB + q * CH) * 2);
     const uint32_t cstep = (uint32_t)sp.CB * 2;     // bytes between staged pixels
-    float2 acc[KS][TW][2];                          // ring of k output rows (slot = row mod k)
+    float2 acc[KS][TW][NP];                         // ring of k output rows (slot = row mod k)
 #pragma unroll
     for (int s2 = 0; s2 < KS; ++s2)
 #pragma unroll
-        for (int p = 0; p < TW; ++p) acc[s2][p][0] = b01, acc[s2][p][1] = b23;
+        for (int p = 0; p < TW; ++p)
+#pragma unroll
+            for (int h = 0; h < NP; ++h) acc[s2][p][h] = bv[h];
     uint32_t seq = 0;
     for (long long g = g_begin; g < g_end;) {
         const int b = (int)(g / H), o0 = (int)(g - (long long)b * H);
         const int o1 = (int)min((long long)H, o0 + (g_end - g));
         const int n_steps = o1 - o0 + 2 * P;
         const int groups = (n_steps + KS - 1) / KS;
-        uint2* yrow = y + ((long long)b * H * W) * nq + (cblk * nqb + q) + ((long long)o0 * W + ow0) * nq;
+        uint32_t* yrow = y + ((long long)b * H * W) * cw + (cblk * nqb + q) * NP + ((long long)o0 * W + ow0) * cw;
 
         for (int gi = 0; gi < groups; ++gi, ++seq) {
             const uint32_t slot = seq % sp.nst, round = seq / sp.nst;
             dws_wait(dws_u32(&full[slot]), round & 1u);
             if (active) {
                 const uint32_t st = stage0 + slot * (uint32_t)sp.stage_stride;
-                uint2 raw[TWIN];
+                uint32_t raw[TWIN][NP];
 #pragma unroll
-                for (int j = 0; j < TWIN; ++j) raw[j] = dws_lds64(st + j * cstep);
+                for (int j = 0; j < TWIN; ++j) dws_lds_px<NP>(st + j * cstep, raw[j]);
 #pragma unroll
                 for (int u = 0; u < KS; ++u) {
                     const int i = gi * KS + u;
                     if (i < n_steps) {
                         const int ih = o0 - P + i;
-                        float2 in[TWIN][2];
+                        float2 in[TWIN][NP];
 #pragma unroll
-                        for (int j = 0; j < TWIN; ++j) in[j][0] = bf16x2_to_float2(raw[j].x), in[j][1] = bf16x2_to_float2(raw[j].y);
+                        for (int j = 0; j < TWIN; ++j)
+#pragma unroll
+                            for (int h = 0; h < NP; ++h) in[j][h] = bf16x2_to_float2(raw[j][h]);
                         if (u + 1 < KS) {                              // next staged row, in flight during this row's math
 #pragma unroll
-                            for (int j = 0; j < TWIN; ++j) raw[j] = dws_lds64(st + (u + 1) * (uint32_t)row_bytes + j * cstep);
+                            for (int j = 0; j < TWIN; ++j) dws_lds_px<NP>(st + (u + 1) * (uint32_t)row_bytes + j * cstep, raw[j]);
                         }
                         constexpr int NEWEST = KS - 1;                 // output row that receives its first contribution
                         if ((unsigned)ih < (unsigned)H) {
@@ -175,32 +201,37 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                                 const int sl = (u + 1 + m) % KS;
 #pragma unroll
                                 for (int kw = 0; kw < KS; ++kw) {
-                                    const float4 f = dws_lds128(wq + (kh * KS + kw) * 16);
-                                    const float2 w0 = make_float2(f.x, f.y), w1 = make_float2(f.z, f.w);
+                                    float2 wv[NP];
+                                    dws_lds_tap<NP>(wq + (kh * KS + kw) * (CH * 4), wv);
 #pragma unroll
                                     for (int p = 0; p < TW; ++p) {
                                         const bool first = (m == NEWEST) && (kw == 0);      // starts from the bias
-                                        acc[sl][p][0] = __ffma2_rn(in[p + kw][0], w0, first ? b01 : acc[sl][p][0]);
-                                        acc[sl][p][1] = __ffma2_rn(in[p + kw][1], w1, first ? b23 : acc[sl][p][1]);
+#pragma unroll
+                                        for (int h = 0; h < NP; ++h)
+                                            acc[sl][p][h] = __ffma2_rn(in[p + kw][h], wv[h], first ? bv[h] : acc[sl][p][h]);
                                     }
                                 }
                             }
                         } else {                                       // a row above / below the image contributes nothing
 #pragma unroll
-                            for (int p = 0; p < TW; ++p) acc[(u + 1 + NEWEST) % KS][p][0] = b01, acc[(u + 1 + NEWEST) % KS][p][1] = b23;
+                            for (int p = 0; p < TW; ++p)
+#pragma unroll
+                                for (int h = 0; h < NP; ++h) acc[(u + 1 + NEWEST) % KS][p][h] = bv[h];
                         }
                         if (i >= 2 * P) {                              // output row o0 + i - 2P is complete
                             const int sl = (u + 1) % KS;
 #pragma unroll
                             for (int p = 0; p < TW; ++p) {
                                 if (ow0 + p < W) {
-                                    uint2 v;
-                                    v.x = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][0].x), dws_act<ACT>(acc[sl][p][0].y));
-                                    v.y = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][1].x), dws_act<ACT>(acc[sl][p][1].y));
-                                    yrow[(long long)p * nq] = v;
+                                    uint32_t v[NP];
+#pragma unroll
+                                    for (int h = 0; h < NP; ++h)
+                                        v[h] = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][h].x), dws_act<ACT>(acc[sl][p][h].y));
+                                    if (NP == 2) *reinterpret_cast<uint2*>(yrow + (long long)p * cw) = make_uint2(v[0], v[NP - 1]);
+                                    else yrow[(long long)p * cw] = v[0];
                                 }
                             }
-                            yrow += (long long)W * nq;
+                            yrow += (long long)W * cw;
                         }
                     }
                 }
@@ -214,11 +245,14 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
 
 // ---- host side -----------------------------------------------------------------------------------------------
 template <int KS>
-static constexpr int dws_tw() { return KS == 3 ? 4 : 2; }
+static constexpr int dws_tw() { return 4; }
+template <int KS>
+static constexpr int dws_ch() { return KS == 3 ? 4 : 2; }      // channels per consumer thread
 
 bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     if (stride != 1 || (k != 3 && k != 5) || C % 8 != 0 || H < 4) return false;
     const int TW = (k == 3) ? dws_tw<3>() : dws_tw<5>();
+    const int CH = (k == 3) ? dws_ch<3>() : dws_ch<5>();
     const int P = k / 2;
     const int ncb = (W + TW - 1) / TW;
     const int IW = ncb * TW + 2 * P;
@@ -227,7 +261,7 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     int best = 0, best_thr = 0;
     for (int cb = 8; cb <= C; cb += 8) {
         if (C % cb) continue;
-        const int thr = (cb / 4) * ncb;
+        const int thr = (cb / CH) * ncb;
         if (thr > DWS_MAX_THREADS - 32) break;
         const bool good = thr >= 96 && thr <= 128, best_good = best_thr >= 96 && best_thr <= 128;
         if (!best || (good && !best_good) || (good == best_good)) best = cb, best_thr = thr;     // later (larger) wins ties
@@ -242,7 +276,7 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     int nst = (60 * 1024) / sp->stage_stride;             // ~60 KB of ring per CTA, three CTAs per SM
     nst = nst < 3 ? 3 : (nst > DWS_MAX_STAGES ? DWS_MAX_STAGES : nst);
     sp->nst = nst;
-    sp->threads = 32 + (((best / 4) * ncb + 31) / 32) * 32;
+    sp->threads = 32 + (((best / CH) * ncb + 31) / 32) * 32;
     sp->smem = (size_t)nst * sp->stage_stride + (size_t)k * k * best * 4;
     return sp->smem <= 200 * 1024;
 }
@@ -256,7 +290,7 @@ int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, in
 template <int KS, int ACT, int NT>
 static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
                         int C, cudaStream_t stream) {
-    auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), ACT, NT>;
+    auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), dws_ch<KS>(), ACT, NT>;
     static size_t configured = 0;
     if (sp.smem > configured) {
         DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -270,7 +304,7 @@ static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* 
     if (parts < 1) parts = 1;
     if (parts > (long long)B * H) parts = (long long)B * H;
     const long long grid = parts * sp.ncblk;
-    launch_pdl(kern, (unsigned)grid, sp.threads, sp.smem, stream, tm, w, bias, (uint2*)y, sp, B, H, W, C);
+    launch_pdl(kern, (unsigned)grid, sp.threads, sp.smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
