@@ -186,21 +186,30 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 }
 
 // Kernel per layer shape (measured on B200, profiles/r01_dw_*.txt): stride-1 layers with at least 8 rows run on the
-// TMA-fed row stream (dwconv_stream.cu, 3.0-4.0 TB/s); of the rest, the TMA-fed shared-memory tiles win on the
-// large maps (>= 40x40 outputs) and the register-tiled direct kernel on the small ones.
+// TMA-fed row stream (dwconv_stream.cu, 3.0-4.0 TB/s), stride-2 layers with wide enough channel blocks on its
+// stride-2 sibling (dwconv_stream2.cu); of the rest, the TMA-fed shared-memory tiles win on the large maps
+// (>= 40x40 outputs) and the register-tiled direct kernel on the small ones.
 DwImpl dw_choose(int H, int W, int C, int k, int stride) {
-    static const int forced = [] {                  // measurement aid: DN_DW_IMPL=1|2|4 forces one kernel where it applies
+    static const int forced = [] {                  // measurement aid: DN_DW_IMPL=1|2|4|8 forces one kernel where it applies
         const char* e = getenv("DN_DW_IMPL");
         return e ? atoi(e) : 0;
     }();
     const int pad = (k - 1) / 2;
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     DwStream sp;
+    int tw2 = 0;
     const bool stream_ok = H >= 8 && dw_stream_plan(H, W, C, k, stride, &sp);
+    const bool stream2_ok = stride == 2 && dw_stream2_plan(H, W, C, k, &sp, &tw2);
     const DwImpl tiled = (long long)Ho * Wo >= 1600 ? DW_TMA : DW_DIRECT;      // 40x40 outputs and up (r01 A/B table)
     if (forced == DW_DIRECT) return DW_DIRECT;
     if (forced == DW_TMA) return DW_TMA;
     if (forced == DW_STREAM) return stream_ok ? DW_STREAM : tiled;
+    if (forced == DW_STREAM2) return stream2_ok ? DW_STREAM2 : (stream_ok ? DW_STREAM : tiled);
+    if (forced == 16) return stream_ok ? DW_STREAM : tiled;          // the plan before the stride-2 stream existed
+    // stride 2: the row stream wins when a channel block is at least 24 channels wide (48-byte TMA rows) and the map has
+    // at least 8 output rows (r01 A/B: 80x80x72 k5 0.162 -> 0.079 ms, 20x20x672 k5 0.084 -> 0.067, 40x40x240 k3
+    // 0.062 -> 0.048; 160x160x64, where the block is 8 channels, stays on the tiles: 0.179 vs 0.334)
+    if (stream2_ok && sp.CB >= 24 && Ho >= 8) return DW_STREAM2;
     return stream_ok ? DW_STREAM : tiled;
 }
 
@@ -226,6 +235,15 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
         int rc = dw_stream_make_tmap(&tm, x, B, H, W, C, k, sp);
         if (rc) return rc;
         return dwconv_stream_launch(tm, sp, w, bias, y, B, H, W, C, k, act, s);
+    }
+    if (impl == DW_STREAM2) {
+        DwStream sp;
+        int tw = 0;
+        DN_REQUIRE(dw_stream2_plan(H, W, C, k, &sp, &tw), DN_ERR_UNSUPPORTED, "no stride-2 stream plan");
+        CUtensorMap tm;
+        int rc = dw_stream2_make_tmap(&tm, x, B, H, W, C, k, sp);
+        if (rc) return rc;
+        return dwconv_stream2_launch(tm, sp, tw, w, bias, y, B, H, W, C, k, act, s);
     }
     if (impl == DW_TMA) {
         DwTiling tl;

@@ -37,8 +37,14 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp);
 int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
 int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
                          int W, int C, int k, int act, cudaStream_t stream);
+// TMA-fed row stream, stride 2 (dwconv_stream2.cu): same DwStream plan record (stage = 2 * ((k + 1) / 2) input rows),
+// tw = output columns per consumer thread (4 or 2)
+bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out);
+int dw_stream2_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
+int dwconv_stream2_launch(const CUtensorMap& tm, const DwStream& sp, int tw, const float* w, const float* bias, void* y, int B,
+                          int H, int W, int C, int k, int act, cudaStream_t stream);
 // which depthwise kernel a layer shape runs on
-enum DwImpl { DW_DIRECT = 1, DW_TMA = 2, DW_STREAM = 4 };
+enum DwImpl { DW_DIRECT = 1, DW_TMA = 2, DW_STREAM = 4, DW_STREAM2 = 8 };
 DwImpl dw_choose(int H, int W, int C, int k, int stride);
 
 // TMA-tiled stem (stem_tma.cu)

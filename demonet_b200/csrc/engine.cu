@@ -51,7 +51,8 @@ struct dn_engine {
     std::vector<CUtensorMap> tmap_dw;               // per op (DW only)
     std::vector<DwTiling> dw_tiling;
     std::vector<DwStream> dw_stream;
-    std::vector<char> dw_tma;                       // per op: TMA-tiled kernel selected
+    std::vector<char> dw_tma;                       // per op: 0 direct, 1 TMA tiles, 2 row stream, 3 stride-2 row stream
+    std::vector<int> dw_tw;                         // per op: output columns per thread of the stride-2 stream
     bool dw_ready = false;
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
@@ -258,6 +259,7 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
         e->dw_tiling.resize(e->ops.size());
         e->dw_stream.resize(e->ops.size());
         e->dw_tma.assign(e->ops.size(), 0);
+        e->dw_tw.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
             if (o.kind != DN_OP_DW) continue;
@@ -267,6 +269,14 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
                 if (!dw_stream_plan(o.h_in, o.w_in, o.c_in, o.ksize, o.stride, &e->dw_stream[i])) return DN_ERR_UNSUPPORTED;
                 int rc = dw_stream_make_tmap(&e->tmap_dw[i], buf_ptr(e, o.in_buf), e->max_batch, o.h_in, o.w_in, o.c_in, o.ksize,
                                              e->dw_stream[i]);
+                if (rc) return rc;
+                continue;
+            }
+            if (impl == DW_STREAM2) {
+                e->dw_tma[i] = 3;
+                if (!dw_stream2_plan(o.h_in, o.w_in, o.c_in, o.ksize, &e->dw_stream[i], &e->dw_tw[i])) return DN_ERR_UNSUPPORTED;
+                int rc = dw_stream2_make_tmap(&e->tmap_dw[i], buf_ptr(e, o.in_buf), e->max_batch, o.h_in, o.w_in, o.c_in, o.ksize,
+                                              e->dw_stream[i]);
                 if (rc) return rc;
                 continue;
             }
@@ -323,6 +333,12 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                     rc = dwconv_stream_launch(e->tmap_dw[i], e->dw_stream[i], (const float*)(W + o.w_off),
                                               (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
                                               o.act, s);
+                    break;
+                }
+                if (e->dw_ready && e->dw_tma[i] == 3) {
+                    rc = dwconv_stream2_launch(e->tmap_dw[i], e->dw_stream[i], e->dw_tw[i], (const float*)(W + o.w_off),
+                                               (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
+                                               o.act, s);
                     break;
                 }
                 if (e->dw_ready && e->dw_tma[i] == 1) {

@@ -40,17 +40,21 @@ def test_dwconv(C, k, s, H, act):
     _close_bf16(y, ref)
 
 
-@pytest.mark.parametrize("B,H,W,C,k", [(37, 12, 27, 40, 3), (37, 12, 27, 40, 5), (300, 8, 8, 64, 3), (5, 64, 9, 16, 5)])
-def test_dwconv_rect_many_images(B, H, W, C, k):
-    """Non-square maps and enough images that a CTA's share of the row stream (dwconv_stream.cu) starts and ends
-    in the middle of images and spans several of them."""
-    g = torch.Generator().manual_seed(B + H * 3 + W * 5 + C * 7 + k)
+@pytest.mark.parametrize("B,H,W,C,k,s", [(37, 12, 27, 40, 3, 1), (37, 12, 27, 40, 5, 1), (300, 8, 8, 64, 3, 1), (5, 64, 9, 16, 5, 1),
+                                         (37, 12, 27, 40, 3, 2), (37, 13, 27, 40, 5, 2), (300, 8, 8, 64, 3, 2), (5, 64, 9, 16, 5, 2),
+                                         (64, 80, 80, 72, 5, 2), (9, 33, 47, 24, 3, 2)])
+def test_dwconv_rect_many_images(B, H, W, C, k, s):
+    """Non-square maps and enough images that a CTA's share of the row stream (dwconv_stream.cu, dwconv_stream2.cu)
+    starts and ends in the middle of images and spans several of them."""
+    g = torch.Generator().manual_seed(B + H * 3 + W * 5 + C * 7 + k + s)
     x = (torch.randn(B, H, W, C, generator=g) * 2).bfloat16().cuda()
     w = (torch.randn(k * k, C, generator=g) / k).cuda()
     b = torch.randn(C, generator=g).cuda()
-    y = ops.dwconv(x, w, b, k, 1, "hardswish")
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, k, k), b, 1, (k - 1) // 2, 1, C)
-    _close_bf16(y, ACTS["hardswish"](ref).permute(0, 2, 3, 1))
+    y = ops.dwconv(x, w, b, k, s, "hardswish")
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, k, k), b, s, (k - 1) // 2, 1, C)
+    ref = ACTS["hardswish"](ref).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    _close_bf16(y, ref)
 
 
 # (M, K, N): Appendix C GEMM shapes (per-image M times a small batch), incl. N not multiple of 16 / > 256
