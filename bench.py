@@ -339,10 +339,15 @@ def main():
         cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")))
         if cands and B == 256:
             nl = json.load(open(cands[-1]))["kernels"]
-            fam = {"dwconv_kernel": ["dn::dwconv_kernel", "dn::dwconv_tma_kernel"], "pwconv_tc_kernel": ["dn::pwconv_tc_kernel"]}
-            names = fam.get(dominant, ["dn::" + dominant])
+            fam = {"dwconv_kernel": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
+                   "pwconv_tc_kernel": ["pwconv_tc_kernel"], "stem_conv_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
+                   "se_pool+fc1+fc2+scale kernels": ["se_pool_kernel", "se_fc1_kernel", "se_fc2_kernel", "se_scale_kernel"]}
+            names = fam.get(dominant, [dominant])
+            names = names + ["dn::" + n for n in names]              # ncu reports the name with or without the namespace
             tb = sum(nl[n]["dram_bytes"] for n in names if n in nl)
             tl = sum(nl[n]["launches"] for n in names if n in nl)
+            if dominant.startswith("se_pool"):
+                tl //= 4                                             # four launches per squeeze-excitation layer
             if tl:
                 traffic, traffic_src = tb / tl, os.path.basename(cands[-1])
     except Exception:
