@@ -88,7 +88,7 @@ def run_reference(args):
                        "batch_per_step": args.cpu_sample, "weights": "seeded re-init 1234", "images": "torch.rand seed 1"},
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_claim_stdout(), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,8 +215,23 @@ def plan_D(plan):
     return 300
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever
+    a library prints (NCCL's version banner under NCCL_DEBUG, warnings of C++ runtimes) cannot get in front of it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -397,7 +412,7 @@ def main():
                                 "sample": "%d images x 3 steps, fp32, oracle torch port of SSD.forward (%.0f ms/step)"
                                           % (args.cpu_sample, cpu_ms)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
