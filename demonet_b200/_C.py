@@ -78,6 +78,8 @@ _SIGNATURES = {
     "dn_resize_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dn_u8_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "dn_rescale_boxes": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dn_detections_to_coco": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "dn_engine_buffer": (c_int, [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
     "dn_engine_copy_buffer": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "dn_engine_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),

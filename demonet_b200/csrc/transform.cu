@@ -6,6 +6,7 @@
 //   * dn_u8_to_f32       : uint8 -> fp32 / 255, the ToTensor conversion, for the uint8 ingest of the engine
 //   * dn_rescale_boxes   : boxes *= (orig / resized) per image = resize_boxes (transform.py:278-292) as applied by
 //                          GeneralizedRCNNTransform.postprocess (transform.py:228-247)
+//   * dn_detections_to_coco : padded detections -> compact COCO result rows (coco_eval.py:76-98,162-164)
 // All three are HBM-bound elementwise kernels: 16-byte accesses where the layout allows, one pass over the data.
 #include <algorithm>
 
@@ -77,6 +78,43 @@ rescale_boxes_kernel(float4* __restrict__ boxes, const float2* __restrict__ rati
     boxes[i] = b;
 }
 
+// Detection sink: padded per-image detections -> compact COCO result rows in image order, the
+// device-side form of CocoEvaluator.prepare_for_coco_detection (demonet/data/coco_eval.py:76-98) with
+// convert_to_xywh (coco_eval.py:162-164).  CTA b sums counts[0..b) itself (B is a few thousand at most), so one
+// launch does scan + compaction deterministically and without atomics.
+__global__ void __launch_bounds__(256)
+coco_rows_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, const long long* __restrict__ labels,
+                 const int* __restrict__ counts, const long long* __restrict__ image_ids, int B, int D,
+                 long long* __restrict__ out_image_id, long long* __restrict__ out_category, float4* __restrict__ out_bbox,
+                 float* __restrict__ out_score, long long* __restrict__ out_total) {
+    __shared__ long long s_warp[8];
+    __shared__ long long s_off;
+    const int b = blockIdx.x;
+    long long part = 0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) part += min(max(counts[i], 0), D);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s_warp[w];
+        s_off = t;
+    }
+    __syncthreads();
+    const long long off = s_off;
+    const int n = min(max(counts[b], 0), D);
+    const long long id = image_ids[b];
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+        const float4 q = boxes[(long long)b * D + d];
+        out_image_id[off + d] = id;
+        out_category[off + d] = labels[(long long)b * D + d];
+        out_bbox[off + d] = make_float4(q.x, q.y, __fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));      // xywh
+        out_score[off + d] = scores[(long long)b * D + d];
+    }
+    if (b == B - 1 && threadIdx.x == 0) *out_total = off + n;
+}
+
 int u8_to_f32_launch(const unsigned char* src, float* dst, size_t n, cudaStream_t s) {
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
     const long long n16 = aligned ? (long long)(n / 16) : 0;
@@ -128,6 +166,23 @@ extern "C" int dn_rescale_boxes(float* boxes, const float* ratio_hw, int B, int 
     const long long n = (long long)B * D;
     rescale_boxes_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, (cudaStream_t)stream_>>>((float4*)boxes,
                                                                                                  (const float2*)ratio_hw, D, n);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+extern "C" int dn_detections_to_coco(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
+                                     const int64_t* image_ids, int B, int D, int64_t* out_image_id, int64_t* out_category_id,
+                                     float* out_bbox_xywh, float* out_score, int64_t* out_total, void* stream_) {
+    DN_REQUIRE(boxes && scores && labels && counts && image_ids && out_image_id && out_category_id && out_bbox_xywh &&
+                   out_score && out_total,
+               DN_ERR_INVALID, "NULL tensor pointer");
+    DN_REQUIRE(B > 0 && D > 0, DN_ERR_INVALID, "bad shape");
+    DN_REQUIRE(((reinterpret_cast<uintptr_t>(boxes) | reinterpret_cast<uintptr_t>(out_bbox_xywh)) & 15) == 0, DN_ERR_INVALID,
+               "box arrays must be 16-byte aligned");
+    coco_rows_kernel<<<B, 256, 0, (cudaStream_t)stream_>>>((const float4*)boxes, scores, (const long long*)labels, counts,
+                                                            (const long long*)image_ids, B, D, (long long*)out_image_id,
+                                                            (long long*)out_category_id, (float4*)out_bbox_xywh, out_score,
+                                                            (long long*)out_total);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

@@ -66,3 +66,25 @@ def unpack_gathered(packed: PackedDetections, gathered: torch.Tensor) -> List[Di
         for i, n in enumerate(counts.tolist()):
             dets.append({"boxes": boxes[i, :n], "scores": scores[i, :n], "labels": labels[i, :n]})
     return dets
+
+
+def gather_image_ids(image_ids: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather the per-rank image ids (int64 [B], equal B per rank) -> [world * B] in rank-major order, the order of
+    `unpack_gathered`.  The reference pickles python lists through all_gather (coco_eval.py:167-186, misc.py:75-115)."""
+    world = dist.get_world_size(group)
+    ids = image_ids.to(torch.int64).contiguous()
+    out = torch.empty(world * ids.numel(), dtype=torch.int64, device=ids.device)
+    dist.all_gather_into_tensor(out, ids, group=group)
+    return out
+
+
+def first_occurrence_sorted(image_ids: torch.Tensor) -> torch.Tensor:
+    """Indices that keep every image once, in ascending id order, choosing the first occurrence -- np.unique(ids,
+    return_index=True) as used by coco_eval.merge (coco_eval.py:181-183) to drop the images a DistributedSampler
+    repeats to pad the last batch."""
+    ids = image_ids.detach().cpu()
+    order = torch.argsort(ids, stable=True)
+    sorted_ids = ids[order]
+    keep = torch.ones_like(sorted_ids, dtype=torch.bool)
+    keep[1:] = sorted_ids[1:] != sorted_ids[:-1]
+    return order[keep]

@@ -8,6 +8,7 @@ They keep the reference's names / argument meaning where the reference has a cou
   PostProcess(...)                                   box_head.PostProcess (legacy V2 flavour)
   DefaultBoxGenerator                                anchor_utils.DefaultBoxGenerator (table)
   resize_bilinear / u8_to_f32 / rescale_boxes_       GeneralizedRCNNTransform resize, ToTensor, resize_boxes (transform.py)
+  detections_to_coco / coco_results                  CocoEvaluator.prepare_for_coco_detection (data/coco_eval.py:76-98)
 Everything raises if the CUDA library is missing or the tensors are not on a CUDA device.
 """
 import ctypes
@@ -227,3 +228,37 @@ def se_inplace(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor) -> Te
                                         w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(), B, HW, C, w1.shape[0],
                                         ws.data_ptr(), ws_bytes, _stream(x)))
     return x
+
+
+# ---- detection sink ---------------------------------------------------------------
+def detections_to_coco(boxes: Tensor, scores: Tensor, labels: Tensor, counts: Tensor, image_ids) -> Dict[str, Tensor]:
+    """Padded detections (boxes [B,D,4] xyxy, scores [B,D], labels [B,D], counts [B], as written by the engine) ->
+    compact COCO rows in image order: {"image_id" i64[n], "category_id" i64[n], "bbox" f32[n,4] xywh, "score" f32[n]}.
+    The device-side CocoEvaluator.prepare_for_coco_detection (demonet/data/coco_eval.py:76-98)."""
+    _require_cuda(boxes, scores, labels, counts)
+    B, D = boxes.shape[0], boxes.shape[1]
+    dev = boxes.device
+    ids = torch.as_tensor(image_ids, dtype=torch.int64).to(dev).contiguous()
+    if ids.shape != (B,):
+        raise ValueError("image_ids must have one id per image")
+    out = {"image_id": torch.empty(B * D, dtype=torch.int64, device=dev),
+           "category_id": torch.empty(B * D, dtype=torch.int64, device=dev),
+           "bbox": torch.empty(B * D, 4, dtype=torch.float32, device=dev),
+           "score": torch.empty(B * D, dtype=torch.float32, device=dev)}
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    if B == 0:
+        return {k: v[:0] for k, v in out.items()}
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().dn_detections_to_coco(
+            boxes.contiguous().data_ptr(), scores.contiguous().data_ptr(), labels.to(torch.int64).contiguous().data_ptr(),
+            counts.to(torch.int32).contiguous().data_ptr(), ids.data_ptr(), B, D, out["image_id"].data_ptr(),
+            out["category_id"].data_ptr(), out["bbox"].data_ptr(), out["score"].data_ptr(), total.data_ptr(), _stream(boxes)))
+    n = int(total.item())
+    return {k: v[:n] for k, v in out.items()}
+
+
+def coco_results(rows: Dict[str, Tensor]) -> List[dict]:
+    """The list of dicts pycocotools' loadRes takes, from the rows of detections_to_coco (one D2H copy per column)."""
+    ids, cats = rows["image_id"].tolist(), rows["category_id"].tolist()
+    boxes, scores = rows["bbox"].tolist(), rows["score"].tolist()
+    return [{"image_id": ids[k], "category_id": cats[k], "bbox": boxes[k], "score": scores[k]} for k in range(len(ids))]

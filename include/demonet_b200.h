@@ -99,6 +99,16 @@ int dn_u8_to_f32(const uint8_t* src, float* dst, size_t n, void* stream);
  * boxes: fp32 [B,D,4] in place; ratio_hw: fp32 [B,2] device. */
 int dn_rescale_boxes(float* boxes, const float* ratio_hw, int B, int D, void* stream);
 
+/* Detection sink: padded per-image detections (the outputs of dn_postprocess / dn_engine_forward) -> compact COCO
+ * result rows in image order, i.e. CocoEvaluator.prepare_for_coco_detection (demonet/data/coco_eval.py:76-98) with
+ * convert_to_xywh (coco_eval.py:162-164: w = xmax - xmin, h = ymax - ymin in fp32) on the device.
+ * boxes fp32 [B,D,4] xyxy, scores fp32 [B,D], labels int64 [B,D], counts int32 [B], image_ids int64 [B].
+ * Outputs (capacity B*D rows): out_image_id int64, out_category_id int64, out_bbox_xywh fp32 [.,4], out_score fp32,
+ * out_total int64 [1] = number of rows written (sum of counts). */
+int dn_detections_to_coco(const float* boxes, const float* scores, const int64_t* labels, const int32_t* counts,
+                          const int64_t* image_ids, int B, int D, int64_t* out_image_id, int64_t* out_category_id,
+                          float* out_bbox_xywh, float* out_score, int64_t* out_total, void* stream);
+
 typedef struct {
     int32_t num_priors;          /* P                                                          */
     int32_t num_classes;         /* K, including background column 0                           */

@@ -46,6 +46,14 @@ def _worker(rank, world, port, B, D, q):
                 n = int(ec[i])
                 ok &= d["boxes"].shape == (n, 4) and torch.equal(d["boxes"], eb[i, :n])
                 ok &= torch.equal(d["scores"], es[i, :n]) and torch.equal(d["labels"], el[i, :n])
+        # image ids travel the same way; the sampler's padding duplicates are dropped like coco_eval.merge does
+        ids = torch.tensor([rank * 3 + i for i in range(B)], dtype=torch.int64)       # ranks overlap on purpose
+        all_ids = ddist.gather_image_ids(ids)
+        ok &= all_ids.tolist() == [r * 3 + i for r in range(world) for i in range(B)]
+        keep = ddist.first_occurrence_sorted(all_ids)
+        import numpy as np
+        want_ids, want_idx = np.unique(all_ids.numpy(), return_index=True)
+        ok &= keep.tolist() == want_idx.tolist() and all_ids[keep].tolist() == want_ids.tolist()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -65,3 +73,13 @@ def test_gather_detections_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_first_occurrence_sorted_matches_numpy_unique():
+    import numpy as np
+    g = torch.Generator().manual_seed(3)
+    for n in (0, 1, 17, 1000):
+        ids = torch.randint(0, max(1, n // 2), (n,), generator=g, dtype=torch.int64)
+        keep = ddist.first_occurrence_sorted(ids)
+        want_ids, want_idx = np.unique(ids.numpy(), return_index=True)
+        assert keep.tolist() == want_idx.tolist() and ids[keep].tolist() == want_ids.tolist()

@@ -97,3 +97,46 @@ def test_forward_uint8_equals_float_forward():
         model.forward_uint8(torch.zeros(2, 3, 300, 320, dtype=torch.uint8))
     with pytest.raises(TypeError):
         model([torch.zeros(3, 320, 320, dtype=torch.uint8).cuda()])          # the float contract of forward() is unchanged
+
+
+def _reference_coco(predictions):
+    """CocoEvaluator.prepare_for_coco_detection + convert_to_xywh, demonet/data/coco_eval.py:76-98,162-164 (restated:
+    the module itself needs pycocotools to import)."""
+    out = []
+    for original_id, p in predictions.items():
+        if len(p) == 0:
+            continue
+        xmin, ymin, xmax, ymax = p["boxes"].unbind(1)
+        boxes = torch.stack((xmin, ymin, xmax - xmin, ymax - ymin), dim=1).tolist()
+        scores, labels = p["scores"].tolist(), p["labels"].tolist()
+        out.extend([{"image_id": original_id, "category_id": labels[k], "bbox": box, "score": scores[k]}
+                    for k, box in enumerate(boxes)])
+    return out
+
+
+@pytest.mark.parametrize("B,D", [(1, 1), (7, 300), (300, 100), (1500, 5)])
+def test_detections_to_coco_matches_reference(B, D):
+    g = torch.Generator().manual_seed(B * 1000 + D)
+    xy = torch.rand(B, D, 2, generator=g) * 300
+    boxes = torch.cat([xy, xy + torch.rand(B, D, 2, generator=g) * 80], -1)
+    scores = torch.rand(B, D, generator=g)
+    labels = torch.randint(1, 91, (B, D), generator=g)
+    counts = torch.randint(0, D + 1, (B,), generator=g, dtype=torch.int32)
+    counts[0] = 0 if B > 1 else counts[0]
+    ids = torch.randperm(100000, generator=g)[:B]
+    rows = ops.detections_to_coco(boxes.cuda(), scores.cuda(), labels.cuda(), counts.cuda(), ids)
+    got = ops.coco_results(rows)
+    want = _reference_coco({int(ids[b]): {"boxes": boxes[b, :counts[b]], "scores": scores[b, :counts[b]],
+                                         "labels": labels[b, :counts[b]]} for b in range(B)})
+    assert got == want                        # bit-exact: same fp32 subtraction, same order
+
+
+def test_model_detections_to_coco_rows():
+    model = _model()
+    x = weights.synthetic_images(3, 320).cuda()
+    dets = model(list(x))
+    eng = model._engine_for(x.device, 3)
+    io = model._io_buffers(x.device, 3, False)
+    rows = ops.detections_to_coco(io["boxes"], io["scores"], io["labels"], io["counts"], [11, 5, 7])
+    want = _reference_coco({i: {k: v.cpu() for k, v in d.items()} for i, d in zip([11, 5, 7], dets)})
+    assert ops.coco_results(rows) == want and eng is not None
