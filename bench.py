@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer time table to stderr")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="batches in flight per GPU (2 = the engine's pipeline mode, 1 = one forward at a time)")
     return ap.parse_args()
 
 
@@ -255,43 +257,71 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, D = args.batch, 300
 
-    model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=NUM_CLASSES)
+    # --pipeline 2 (default): two batches in flight on two engine instances (dn_model_desc.pipeline_slots): the
+    # latency-bound tail of batch i (small layers, NMS rounds) overlaps the bandwidth-bound head of batch i+1
+    model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=NUM_CLASSES, pipeline_slots=args.pipeline)
     model.load_state_dict(weights.seeded_state_dict(model.state_dict()))
     model = model.to(dev)
     eng = model.reserve(B, dev)
     lib = _C.lib()
     stream = torch.cuda.current_stream(dev)
+    nslot = 2 if args.pipeline == 2 else 1
 
     # inputs resident in HBM (value) and in pinned host memory (e2e); different images per rank
     imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
     imgs = imgs_host.to(dev)
-    # one packed output buffer per rank so that the final gather is ONE collective
+    # one packed output buffer per rank and slot so that the gather of a batch is ONE collective
     from demonet_b200 import dist as ddist
-    packed_det = ddist.PackedDetections(B, D, dev)
-    packed = packed_det.buffer
-    io = packed_det.as_io()
-    gathered = torch.empty(world * packed.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
-    host_out = {"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
-                "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
-                "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
-                "counts": torch.empty(B, dtype=torch.int32).pin_memory()}
+    packed_det = [ddist.PackedDetections(B, D, dev) for _ in range(nslot)]
+    io = [p.as_io() for p in packed_det]
+    gathered = torch.empty(world * packed_det[0].buffer.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    host_outs = [{"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
+                  "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
+                  "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
+                  "counts": torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(nslot)]
+    host_out = host_outs[0]
+    tick = {"dev": 0, "host": 0, "u8": 0, "gather_owed": False}
 
     def step_device():
-        eng.forward(imgs, io)
+        # forward of batch i on slot i % nslot; with N > 1 every step closes with ONE all-gather of detections: those
+        # of this batch, or in pipeline mode those of the previous batch (its forward is joined, this one keeps running)
+        k = tick["dev"] % nslot
+        tick["dev"] += 1
+        eng.forward(imgs, io[k])
         if world > 1:
-            ddist.gather_detections(packed_det, gathered)
+            if nslot == 1:
+                ddist.gather_detections(packed_det[0], gathered)
+            else:
+                if tick["gather_owed"]:
+                    eng.join_previous()
+                    ddist.gather_detections(packed_det[k ^ 1], gathered)
+                tick["gather_owed"] = True
+
+    def finish_device():
+        # drain the pipeline inside the timed region: join the last forward(s) and gather the batch still owed
+        if nslot == 2:
+            eng.join()
+            if world > 1 and tick["gather_owed"]:
+                ddist.gather_detections(packed_det[(tick["dev"] - 1) % nslot], gathered)
+                tick["gather_owed"] = False
 
     def step_host():
-        eng.forward_host(imgs_host, host_out)       # results land in each rank's own host memory: no gather
+        k = tick["host"] % nslot
+        tick["host"] += 1
+        eng.forward_host(imgs_host, host_outs[k])   # results land in each rank's own host memory: no gather
 
     imgs_u8_host = (imgs_host * 255).round().to(torch.uint8).pin_memory()      # what an image decoder hands over
 
     def step_host_u8():
-        eng.forward_host_u8(imgs_u8_host, host_out)
+        k = tick["u8"] % nslot
+        tick["u8"] += 1
+        eng.forward_host_u8(imgs_u8_host, host_outs[k])
 
-    def timed(fn, steps, warmup, sampler=None):
+    def timed(fn, steps, warmup, sampler=None, finish=None):
         for _ in range(warmup):
             fn()
+        if finish:
+            finish()
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
@@ -302,6 +332,8 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             fn()
+        if finish:
+            finish()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -315,13 +347,13 @@ def main():
 
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    total_ms, clocks = timed(step_device, args.steps, warm, sampler)
+    total_ms, clocks = timed(step_device, args.steps, warm, sampler, finish_device)
     ms_per_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms * 1e-3)
 
     e2e_ms, _ = timed(step_host, args.steps, warm)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    counts_ok = int(host_out["counts"].min()) >= 0
+    counts_ok = all(int(h["counts"].min()) >= 0 for h in host_outs)
     u8_ms, _ = timed(step_host_u8, args.steps, warm)
     u8_value = world * B * args.steps / (u8_ms * 1e-3)
 
@@ -393,7 +425,8 @@ def main():
                        "all-gather of detections)" % world, "weights": "seeded re-init 1234 (demonet_b200/seeded.py)",
                        "images": "torch.rand seed 1+rank", "l2": "inputs larger than L2 (%.0f MB fp32 images per step; "
                        "activation arena %.1f GB)" % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
-                       "cuda_graph": True},
+                       "cuda_graph": True,
+                       "batches_in_flight": nslot},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,

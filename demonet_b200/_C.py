@@ -46,7 +46,7 @@ class ModelDesc(ctypes.Structure):
                 ("n_ops", c_int32), ("n_bufs", c_int32), ("ops_host", ctypes.POINTER(Op)),
                 ("bufs_host", ctypes.POINTER(Buf)), ("logits_buf", c_int32), ("bbox_buf", c_int32),
                 ("anchors_host", ctypes.POINTER(c_float)), ("post", PostprocessParams), ("gemm_impl", c_int32),
-                ("use_cuda_graph", c_int32)]
+                ("use_cuda_graph", c_int32), ("pipeline_slots", c_int32), ("reserved", c_int32)]
 
 
 _SIGNATURES = {
@@ -73,6 +73,8 @@ _SIGNATURES = {
     "dn_engine_destroy": (c_int, [c_void_p]),
     "dn_engine_load_weights": (c_int, [c_void_p, c_void_p, c_size_t]),
     "dn_engine_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dn_engine_join": (c_int, [c_void_p, c_void_p]),
+    "dn_engine_join_previous": (c_int, [c_void_p, c_void_p]),
     "dn_engine_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dn_engine_forward_host_u8": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dn_resize_bilinear": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),

@@ -65,6 +65,14 @@ struct dn_engine {
     std::vector<cudaEvent_t> op_done;               // per op, nullptr when nobody waits for it
     std::vector<std::vector<int>> deps;             // per op: producers on other lanes
     cudaEvent_t fork_ev = nullptr;
+    // pipeline mode (dn_model_desc.pipeline_slots == 2): `twin` is a second complete engine (own arena, tensor maps,
+    // graphs); consecutive forwards alternate between the two on engine-owned streams, so the latency-bound tail of
+    // forward i (tiny layers, NMS rounds) overlaps the bandwidth-bound head of forward i+1
+    dn_engine* twin = nullptr;
+    int next_slot = 0;
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    cudaEvent_t slot_in[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+    bool slot_pending[2] = {false, false};
     // staging for dn_engine_forward_host: two input buffers so that the H2D copy of call i+1 (on copy_stream)
     // overlaps the forward of call i (on the caller's stream)
     float* stage_images = nullptr;              // [2][max_batch,3,H,W]
@@ -202,6 +210,22 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
     }
     TRY(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
 #undef TRY
+#define TRY_AFTER(x)                                                            \
+    if ((x) != cudaSuccess) {                                                   \
+        set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); \
+        return fail(DN_ERR_CUDA);                                               \
+    }
+    if (d->pipeline_slots == 2) {
+        dn_model_desc d1 = *d;
+        d1.pipeline_slots = 0;
+        int rc = dn_engine_create(&e->twin, &d1, max_batch);
+        if (rc) return fail(rc);
+        for (int i = 0; i < 2; ++i) {
+            TRY_AFTER(cudaStreamCreateWithFlags(&e->slot_stream[i], cudaStreamNonBlocking));
+            TRY_AFTER(cudaEventCreateWithFlags(&e->slot_in[i], cudaEventDisableTiming));
+            TRY_AFTER(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
+        }
+    }
     e->device_bytes = e->arena_bytes + e->post_ws_bytes + e->se_ws_bytes + 2 * e->stage_image_bytes + e->so_total + e->anchors_host.size() * 4;
     *out = e;
     return DN_OK;
@@ -209,6 +233,15 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
 
 extern "C" int dn_engine_destroy(dn_engine* e) {
     if (!e) return DN_OK;
+    if (e->twin) {
+        cudaDeviceSynchronize();
+        dn_engine_destroy(e->twin);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (e->slot_stream[i]) cudaStreamDestroy(e->slot_stream[i]);
+        if (e->slot_in[i]) cudaEventDestroy(e->slot_in[i]);
+        if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
+    }
     drop_graphs(e);
     if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -237,6 +270,10 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
 
 extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes) {
     DN_REQUIRE(e && blob_host && bytes > 0, DN_ERR_INVALID, "NULL argument");
+    if (e->twin) {
+        int rc = dn_engine_load_weights(e->twin, blob_host, bytes);
+        if (rc) return rc;
+    }
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const dn_op& o = e->ops[i];
         DN_REQUIRE(o.w_off >= 0 && (size_t)o.w_off < bytes && o.b_off >= 0 && (size_t)o.b_off < bytes, DN_ERR_INVALID,
@@ -411,8 +448,51 @@ static int enqueue_forward(dn_engine* e, const float* images, int B, float* out_
                           out_counts, s);
 }
 
+static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
+                       int64_t* out_labels, int32_t* out_counts, void* stream_);
+
 extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
                                  int64_t* out_labels, int32_t* out_counts, void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    if (!e->twin) return forward_one(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, stream_);
+    // pipeline mode: the forward runs on the slot's own stream behind everything already enqueued on the caller's
+    // stream; the caller's stream is NOT made to wait for it here (that would serialise the next call behind this
+    // one) -- dn_engine_join / dn_engine_join_previous order the results on a stream
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int k = e->next_slot;
+    e->next_slot ^= 1;
+    DN_CHECK_CUDA(cudaEventRecord(e->slot_in[k], s));
+    DN_CHECK_CUDA(cudaStreamWaitEvent(e->slot_stream[k], e->slot_in[k], 0));
+    int rc = forward_one(k ? e->twin : e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, e->slot_stream[k]);
+    if (rc) return rc;
+    DN_CHECK_CUDA(cudaEventRecord(e->slot_done[k], e->slot_stream[k]));
+    e->slot_pending[k] = true;
+    return DN_OK;
+}
+
+extern "C" int dn_engine_join(dn_engine* e, void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    for (int k = 0; k < 2; ++k)
+        if (e->twin && e->slot_pending[k]) {
+            DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
+            e->slot_pending[k] = false;
+        }
+    return DN_OK;
+}
+
+extern "C" int dn_engine_join_previous(dn_engine* e, void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    if (!e->twin) return DN_OK;
+    const int k = e->next_slot;          // the slot the NEXT call will use = the one used by the call before the last
+    if (e->slot_pending[k]) {
+        DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
+        e->slot_pending[k] = false;
+    }
+    return DN_OK;
+}
+
+static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
+                       int64_t* out_labels, int32_t* out_counts, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
     DN_REQUIRE(e->weights != nullptr, DN_ERR_INVALID, "weights have not been loaded");
     DN_REQUIRE(B > 0 && B <= e->max_batch, DN_ERR_INVALID, "batch %d outside [1, %d]", B, e->max_batch);
@@ -478,8 +558,8 @@ static int forward_host_impl(dn_engine* e, const void* images_host, bool u8, int
         DN_CHECK_CUDA(cudaStreamWaitEvent(s, e->h2d_done[par], 0));
     }
     unsigned char* so = e->stage_out;
-    int rc = dn_engine_forward(e, stage, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
-                               (int64_t*)(so + e->so_labels), (int32_t*)(so + e->so_counts), s);
+    int rc = forward_one(e, stage, B, (float*)(so + e->so_boxes), (float*)(so + e->so_scores),
+                         (int64_t*)(so + e->so_labels), (int32_t*)(so + e->so_counts), s);
     if (rc) return rc;
     DN_CHECK_CUDA(cudaEventRecord(e->fwd_done[par], s));
     e->fwd_recorded[par] = true;
@@ -490,16 +570,32 @@ static int forward_host_impl(dn_engine* e, const void* images_host, bool u8, int
     return DN_OK;
 }
 
+// Pipeline mode keeps the plain contract of the host entry points (results valid once `stream` is synchronised): the
+// upload, forward and download of a call run on the slot's streams, which do not depend on the caller's stream, and
+// the caller's stream only collects one wait per call.
+static int forward_host_slots(dn_engine* e, const void* images_host, bool u8, int B, float* ob, float* os, int64_t* ol,
+                              int32_t* oc, void* stream_) {
+    DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
+    if (!e->twin) return forward_host_impl(e, images_host, u8, B, ob, os, ol, oc, stream_);
+    const int k = e->next_slot;
+    e->next_slot ^= 1;
+    int rc = forward_host_impl(k ? e->twin : e, images_host, u8, B, ob, os, ol, oc, e->slot_stream[k]);
+    if (rc) return rc;
+    DN_CHECK_CUDA(cudaEventRecord(e->slot_done[k], e->slot_stream[k]));
+    DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
+    return DN_OK;
+}
+
 extern "C" int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float* out_boxes_host,
                                       float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
                                       void* stream_) {
-    return forward_host_impl(e, images_host, false, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
+    return forward_host_slots(e, images_host, false, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
 }
 
 extern "C" int dn_engine_forward_host_u8(dn_engine* e, const uint8_t* images_host, int B, float* out_boxes_host,
                                          float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
                                          void* stream_) {
-    return forward_host_impl(e, images_host, true, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
+    return forward_host_slots(e, images_host, true, B, out_boxes_host, out_scores_host, out_labels_host, out_counts_host, stream_);
 }
 
 extern "C" int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out) {
@@ -563,4 +659,6 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
 // layers (a squeeze-excitation is 4 launches) + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS,
 // CTA NMS, merge)
 extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 3 * e->n_se + 14 : 0; }
-extern "C" size_t dn_engine_device_bytes(dn_engine* e) { return e ? e->device_bytes : 0; }
+extern "C" size_t dn_engine_device_bytes(dn_engine* e) {
+    return e ? e->device_bytes + (e->twin ? e->twin->device_bytes : 0) : 0;
+}

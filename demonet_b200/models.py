@@ -26,7 +26,7 @@ model_urls = {
 # are accepted and ignored because this build is inference only
 _SSD_KWARGS = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std"}
 _SSD_TRAIN_KWARGS = {"iou_thresh", "positive_fraction"}
-_ENGINE_KWARGS = {"gemm_impl", "use_cuda_graph", "keep_activations"}
+_ENGINE_KWARGS = {"gemm_impl", "use_cuda_graph", "keep_activations", "pipeline_slots"}
 
 
 def ssdlite320_mobilenet_v3_large(pretrained: bool = False, progress: bool = True, num_classes: int = 91,

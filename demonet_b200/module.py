@@ -54,6 +54,7 @@ class _Engine:
                                   kw.get("min_box_size", -1.0))
         d.gemm_impl = int(kw.get("gemm_impl", 0))
         d.use_cuda_graph = int(kw.get("use_cuda_graph", 1))
+        d.pipeline_slots = int(kw.get("pipeline_slots", 0))
         with torch.cuda.device(self.device):
             _C.check(lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
         self._created = True
@@ -74,6 +75,20 @@ class _Engine:
             _C.check(_C.lib().dn_engine_forward(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
                                                out["scores"].data_ptr(), out["labels"].data_ptr(),
                                                out["counts"].data_ptr(), stream))
+
+    @property
+    def pipelined(self) -> bool:
+        return int(self._desc_kwargs.get("pipeline_slots", 0)) == 2
+
+    def join(self):
+        """Pipeline mode: order every forward issued so far before later work on the current stream."""
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_join(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def join_previous(self):
+        """Pipeline mode: order the forward issued BEFORE the most recent one before later work on the current stream."""
+        with torch.cuda.device(self.device):
+            _C.check(_C.lib().dn_engine_join_previous(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
 
     def forward_host(self, images: Tensor, out):
         B = images.shape[0]
@@ -102,6 +117,8 @@ class _Engine:
                 self._read(self.bbox_buf, batch, (P, 4), torch.float32))
 
     def _read(self, buf_id, batch, shape, dtype):
+        if self.pipelined:
+            raise RuntimeError("intermediate buffers are not addressable in pipeline mode (two arenas alternate)")
         n = batch * int(np.prod(shape))
         out = torch.empty(n, dtype=dtype, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -204,7 +221,7 @@ class SSDLiteB200(nn.Module):
 
     def __init__(self, plan: _plan.Plan, score_thresh=0.01, nms_thresh=0.45, detections_per_img=200,
                  topk_candidates=400, image_mean=None, image_std=None, postprocess="ssd", init="normal",
-                 gemm_impl=0, use_cuda_graph=True, keep_activations=False):
+                 gemm_impl=0, use_cuda_graph=True, keep_activations=False, pipeline_slots=0):
         super().__init__()
         if postprocess not in ("ssd", "legacy"):
             raise ValueError("postprocess must be 'ssd' or 'legacy'")
@@ -219,6 +236,7 @@ class SSDLiteB200(nn.Module):
         self.image_std = list(image_std) if image_std is not None else [0.229, 0.224, 0.225]
         self._gemm_impl = gemm_impl
         self._use_cuda_graph = use_cuda_graph
+        self._pipeline_slots = int(pipeline_slots)      # 2: consecutive batches overlap on two engine instances
         self._keep_activations = keep_activations      # debug: one arena buffer per tensor
         self._engines: Dict[Tuple[str, int], _Engine] = {}
         self._io: Dict[Tuple[str, int], dict] = {}
@@ -274,6 +292,7 @@ class SSDLiteB200(nn.Module):
                       nms_thresh=self.nms_thresh, topk_candidates=self.topk_candidates,
                       detections_per_img=self.detections_per_img, gemm_impl=self._gemm_impl,
                       use_cuda_graph=int(self._use_cuda_graph), keep_activations=self._keep_activations,
+                      pipeline_slots=self._pipeline_slots,
                       min_box_size=1e-2 if self.postprocess_flavour == "legacy" else -1.0)
             eng = _Engine(self.plan, kw, max(batch, 1), device)
             self._engines[key] = eng
@@ -343,6 +362,8 @@ class SSDLiteB200(nn.Module):
             torch.cuda.current_stream(device).synchronize()
         else:
             eng.forward(batch, io)
+            if eng.pipelined:
+                eng.join()                        # a single call has nothing to overlap with: plain stream semantics
             if resized:                           # transform.postprocess / resize_boxes, transform.py:228-292
                 rescale_boxes_(io["boxes"], original_sizes, (S, S))
         return self._detections(io, B, in_dev if host else None)
@@ -386,7 +407,39 @@ class SSDLiteB200(nn.Module):
         else:
             u8_to_f32(images, out=io["images"])
             eng.forward(io["images"], io)
+            if eng.pipelined:
+                eng.join()
         return self._detections(io, B, images.device if host else None)
+
+    def forward_batches(self, batches):
+        """Throughput path: iterate over [B,3,S,S] fp32 CUDA batches and yield their detections, keeping two batches in
+        flight when the model was built with pipeline_slots=2 (the post-processing tail of batch i overlaps the backbone
+        of batch i+1).  Every batch must stay alive and unchanged until its detections have been yielded."""
+        pending = None
+        slot = 0
+        for images in batches:
+            if images.dim() != 4 or tuple(images.shape[1:]) != (3, self.plan.size, self.plan.size) or not images.is_cuda:
+                raise ValueError("forward_batches expects fp32 CUDA batches of shape [B,3,%d,%d]" % (self.plan.size, self.plan.size))
+            B = images.shape[0]
+            eng = self._engine_for(images.device, B)
+            key = (str(images.device) + "/slot%d" % slot, B)
+            io = self._io.get(key)
+            if io is None:
+                io = self._io[key] = {k: v for k, v in self._io_buffers(images.device, B, False).items() if k == "images"}
+                D = self.detections_per_img
+                io.update(boxes=torch.empty(B, D, 4, device=images.device), scores=torch.empty(B, D, device=images.device),
+                          labels=torch.empty(B, D, dtype=torch.int64, device=images.device),
+                          counts=torch.empty(B, dtype=torch.int32, device=images.device))
+            eng.forward(images.contiguous(), io)
+            if pending is not None:
+                if eng.pipelined:
+                    eng.join_previous()
+                yield self._detections(pending[0], pending[1])
+            pending = (io, B, eng)
+            slot ^= 1
+        if pending is not None:
+            pending[2].join()
+            yield self._detections(pending[0], pending[1])
 
     def head_outputs(self, images: Tensor):
         """(cls_logits [B,P,K], bbox_regression [B,P,4]) of a [B,3,S,S] CUDA batch -- parity hook."""

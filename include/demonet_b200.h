@@ -195,6 +195,10 @@ typedef struct {
     dn_postprocess_params post;
     int32_t gemm_impl;                     /* 0 = tcgen05 (product), 1 = SIMT self-check      */
     int32_t use_cuda_graph;
+    int32_t pipeline_slots;                /* 0 / 1: one forward at a time (strict stream semantics).  2: consecutive
+                                              dn_engine_forward calls alternate between two complete engine instances on
+                                              engine-owned streams and overlap; see dn_engine_join                     */
+    int32_t reserved;
 } dn_model_desc;
 
 typedef struct dn_engine dn_engine;
@@ -206,6 +210,13 @@ int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes);
 /* images_dev: fp32 [B,3,H,W]; outputs as in dn_postprocess */
 int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
                       int64_t* out_labels, int32_t* out_counts, void* stream);
+/* Pipeline mode only (pipeline_slots == 2): dn_engine_forward returns with the forward enqueued on an engine-owned
+ * stream (ordered behind the work already on `stream`), NOT yet ordered before later work on `stream`.
+ * dn_engine_join makes `stream` wait for every forward issued so far; dn_engine_join_previous only for the forward
+ * issued before the most recent one (so that a consumer of batch i-1 runs while batch i computes).
+ * Both are no-ops without pipeline mode.  The host entry points keep their plain contract in either mode. */
+int dn_engine_join(dn_engine* e, void* stream);
+int dn_engine_join_previous(dn_engine* e, void* stream);
 /* same, taking PINNED HOST buffers: H2D copy, forward, D2H copy.  The forward and the D2H copies are
  * enqueued on `stream`; the H2D copy runs on an engine-owned stream that `stream` waits for, into one of two
  * staging buffers, so back-to-back calls overlap the upload of call i+1 with the forward of call i.

@@ -234,3 +234,25 @@ def test_default_box_generator_op():
     want = boxes_np.default_boxes([(s, s) for s in (20, 10, 5, 3, 2, 1)], (320, 320))
     assert len(out) == 2 and np.array_equal(out[0].cpu().numpy(), want)
     assert gen.num_anchors_per_location() == [6] * 6
+
+
+def test_pipeline_mode_matches_plain_engine():
+    """pipeline_slots=2: consecutive batches alternate between two engine instances on engine-owned streams.  The
+    detections must equal the plain engine's, batch by batch, for the streaming API, single calls and host inputs."""
+    plain, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large)
+    piped, _ = _model(demonet_b200.ssdlite320_mobilenet_v3_large, pipeline_slots=2)
+    batches = [weights.synthetic_images(4, 320, seed=10 + i).cuda() for i in range(5)]
+    want = [plain(list(b)) for b in batches]
+    got = list(piped.forward_batches(batches))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["labels"], b["labels"])
+    for _ in range(3):                                   # single calls join at once; slots keep alternating underneath
+        one = piped(list(batches[2]))
+        assert all(torch.equal(a["scores"], b["scores"]) for a, b in zip(one, want[2]))
+    host = [piped(list(b.cpu())) for b in batches[:3]]    # pinned host path, also alternating slots
+    for g, w in zip(host, want[:3]):
+        assert all(torch.equal(a["boxes"], b["boxes"].cpu()) for a, b in zip(g, w))
+    with pytest.raises(RuntimeError):
+        piped._engine_for(batches[0].device, 4).head_outputs(4)
