@@ -5,7 +5,8 @@ Drop-in builders (`ssdlite320_mobilenet_v3_large`, `ssd_lite_mobilenet_v2`) retu
 hand-written CUDA behind the C ABI of include/demonet_b200.h.
 """
 from . import ops  # noqa: F401
+from . import custom_ops  # noqa: F401  (registers torch.ops.demonet_b200.*)
 from .models import ssd_lite_mobilenet_v2, ssdlite320_mobilenet_v3_large  # noqa: F401
 from .module import SSDLiteB200  # noqa: F401
 
-__all__ = ["ssdlite320_mobilenet_v3_large", "ssd_lite_mobilenet_v2", "SSDLiteB200", "ops"]
+__all__ = ["ssdlite320_mobilenet_v3_large", "ssd_lite_mobilenet_v2", "SSDLiteB200", "ops", "custom_ops"]

@@ -411,6 +411,21 @@ class SSDLiteB200(nn.Module):
                 eng.join()
         return self._detections(io, B, images.device if host else None)
 
+    def forward_padded(self, images: Tensor):
+        """[B,3,S,S] fp32 CUDA batch -> fresh padded (boxes [B,D,4], scores [B,D], labels [B,D], counts [B]) with no host
+        synchronisation and no data-dependent shape: the contract of torch.ops.demonet_b200.ssdlite_forward."""
+        S = self.plan.size
+        if images.dim() != 4 or tuple(images.shape[1:]) != (3, S, S) or not images.is_cuda:
+            raise ValueError("forward_padded expects a CUDA batch of shape [B,3,%d,%d]" % (S, S))
+        B = images.shape[0]
+        eng = self._engine_for(images.device, B)
+        io = self._io_buffers(images.device, B, False)
+        io["images"].copy_(images)
+        eng.forward(io["images"], io)
+        if eng.pipelined:
+            eng.join()
+        return io["boxes"].clone(), io["scores"].clone(), io["labels"].clone(), io["counts"].clone()
+
     def forward_batches(self, batches):
         """Throughput path: iterate over [B,3,S,S] fp32 CUDA batches and yield their detections, keeping two batches in
         flight when the model was built with pipeline_slots=2 (the post-processing tail of batch i overlaps the backbone

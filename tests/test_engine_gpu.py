@@ -256,3 +256,32 @@ def test_pipeline_mode_matches_plain_engine():
         assert all(torch.equal(a["boxes"], b["boxes"].cpu()) for a, b in zip(g, w))
     with pytest.raises(RuntimeError):
         piped._engine_for(batches[0].device, 4).head_outputs(4)
+
+
+def test_exported_program_runs_the_engine():
+    """torch.export captures the detector through torch.ops.demonet_b200.ssdlite_forward (static, padded
+    output shapes) and the exported program reproduces the module's detections; the post-processing op exports too."""
+    from demonet_b200 import custom_ops, ops
+    model, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large)
+    x = weights.synthetic_images(3, 320).cuda()
+    want = model(list(x))
+    wrapper = custom_ops.ExportableSSDLite(model)
+    ep = torch.export.export(wrapper, (x,))
+    assert "demonet_b200.ssdlite_forward" in ep.graph_module.code
+    boxes, scores, labels, counts = ep.module()(x)
+    for i, w in enumerate(want):
+        n = int(counts[i])
+        assert n == w["scores"].numel() and torch.equal(scores[i, :n], w["scores"]) and torch.equal(boxes[i, :n], w["boxes"])
+        assert torch.equal(labels[i, :n], w["labels"])
+
+    class Post(torch.nn.Module):
+        def forward(self, lg, bb, an):
+            return torch.ops.demonet_b200.postprocess(lg, bb, an, 320, 320, 0.001, 0.55, 300, 300, -1.0)
+
+    cls, reg = model.head_outputs(x)
+    anchors = torch.from_numpy(dplan.default_boxes(model.plan)).cuda()
+    ep2 = torch.export.export(Post(), (cls, reg, anchors))
+    b2, s2, l2, c2 = ep2.module()(cls, reg, anchors)
+    assert torch.equal(c2, counts) and torch.equal(s2, scores) and torch.equal(b2, boxes)
+    keep = torch.ops.demonet_b200.nms(boxes[0, :int(counts[0])], scores[0, :int(counts[0])], 0.5)
+    assert torch.equal(keep, ops.nms(boxes[0, :int(counts[0])], scores[0, :int(counts[0])], 0.5))

@@ -188,3 +188,21 @@ def test_side_lanes_never_share_buffers(make):
     for t in touched:
         assert owners[t2b[t]] == [t], "buffer of %s is shared: %s" % (t, owners[t2b[t]])
     assert set(p.feature_names) <= touched
+
+
+def test_custom_ops_are_registered_with_fake_kernels():
+    """the hot-path operators are torch.library ops; shape propagation needs no GPU, and there is no
+    CPU kernel to fall back to."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from torch.fx.experimental.symbolic_shapes import ShapeEnv
+    assert "Tensor cls_logits" in str(torch.ops.demonet_b200.postprocess.default._schema)
+    with pytest.raises(NotImplementedError):
+        torch.ops.demonet_b200.nms(torch.zeros(4, 4), torch.zeros(4), 0.5)
+    with FakeTensorMode(shape_env=ShapeEnv()):
+        lg, bb, an = torch.empty(2, 3234, 91, device="cuda"), torch.empty(2, 3234, 4, device="cuda"), torch.empty(3234, 4, device="cuda")
+        boxes, scores, labels, counts = torch.ops.demonet_b200.postprocess(lg, bb, an, 320, 320, 0.001, 0.55, 300, 300, -1.0)
+        assert tuple(boxes.shape) == (2, 300, 4) and tuple(scores.shape) == (2, 300) and labels.dtype == torch.int64
+        assert tuple(counts.shape) == (2,) and counts.dtype == torch.int32
+        keep = torch.ops.demonet_b200.batched_nms(torch.empty(10, 4, device="cuda"), torch.empty(10, device="cuda"),
+                                                  torch.empty(10, dtype=torch.int64, device="cuda"), 0.5)
+        assert keep.dtype == torch.int64 and keep.dim() == 1          # data-dependent length
