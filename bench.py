@@ -383,7 +383,12 @@ def main():
     traffic, traffic_src = None, None
     try:
         import glob
-        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")))
+        import re
+
+        def _ver(path):                         # r01_ncu_launches_v14.json -> (1, 14): newest round / version last
+            m = re.search(r"r(\d+)_ncu_launches_v(\d+)", os.path.basename(path))
+            return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")), key=_ver)
         if cands and B == 256:
             nl = json.load(open(cands[-1]))["kernels"]
             fam = {"dwconv_kernel": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
