@@ -176,6 +176,7 @@ __device__ unsigned int nms_consume_chunk(NmsState& st, int cand_cnt, float thr_
             st.kept_area[nk + rank] = ma;
         }
         unsigned int taken = __ballot_sync(0xffffffffu, mine);
+        __syncwarp();                                    // every lane has read *st.dead before lane 0 clears it
         if (lane == 0) {
             *st.n_kept = nk + __popc(taken);
             *st.dead = 0u;

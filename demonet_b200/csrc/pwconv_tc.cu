@@ -294,10 +294,29 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float f[8];
+                        uint4 o;
+                        if constexpr (ACT == DN_ACT_HSWISH) {
+                            float f[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = act_fn<ACT>(__uint_as_float(v[q * 8 + i]) + sbw[q * 8 + i]);
-                        *reinterpret_cast<uint4*>(obuf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pack8(f);
+                            for (int i = 0; i < 8; ++i) f[i] = act_fn<ACT>(__uint_as_float(v[q * 8 + i]) + sbw[q * 8 + i]);
+                            o = pack8(f);
+                        } else {
+                            // bias add as packed FFMA2 (x * 1 + b: one rounding, = the fp32 add), ReLU / ReLU6 on the packed
+                            // bf16 pair AFTER the rounding (rounding is monotone and keeps 0 and 6: same values)
+                            uint32_t w[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 bb = *reinterpret_cast<const float2*>(sbw + q * 8 + 2 * i);
+                                const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 2 * i]), __uint_as_float(v[q * 8 + 2 * i + 1])),
+                                                            make_float2(1.f, 1.f), bb);
+                                __nv_bfloat162 h = __floats2bfloat162_rn(t.x, t.y);
+                                if constexpr (ACT == DN_ACT_RELU || ACT == DN_ACT_RELU6) h = __hmax2(h, __float2bfloat162_rn(0.f));
+                                if constexpr (ACT == DN_ACT_RELU6) h = __hmin2(h, __float2bfloat162_rn(6.f));
+                                w[i] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            o = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        *reinterpret_cast<uint4*>(obuf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();

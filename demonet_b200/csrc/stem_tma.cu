@@ -39,11 +39,19 @@ struct StemNorm {
     float mean[3], std[3], rinv[3];
 };
 
-template <int COUT, int NPX>
+template <int ACT>
+__device__ __forceinline__ float st_act(float v) {
+    if (ACT == DN_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == DN_ACT_RELU6) return fminf(fmaxf(v, 0.f), 6.f);
+    if (ACT == DN_ACT_HSWISH) return v * __saturatef(fmaf(v, 1.f / 6.f, 0.5f));      // x * relu6(x + 3) / 6
+    return v;
+}
+
+template <int COUT, int NPX, int ACT>
 __global__ void __launch_bounds__(ST_TH * (ST_TW / NPX))
 stem_tma_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __restrict__ w, const float* __restrict__ bias,
                 uint4* __restrict__ y, int H, int W, int Ho, int Wo, int tiles_x, int tiles_y, int n_tiles,
-                const __grid_constant__ StemNorm nm, int act) {
+                const __grid_constant__ StemNorm nm) {
     constexpr int QW = ST_TW / NPX;                  // threads across a tile row
     constexpr int THREADS = ST_TH * QW;
     constexpr int NV = 2 * NPX + 1;                  // input columns one thread touches per (ci, kh)
@@ -161,10 +169,10 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __res
 #pragma unroll
                     for (int v8 = 0; v8 < COUT / 8; ++v8) {
                         uint4 o;
-                        o.x = float2_to_bf16x2(apply_act(acc[p][v8 * 4 + 0].x, act), apply_act(acc[p][v8 * 4 + 0].y, act));
-                        o.y = float2_to_bf16x2(apply_act(acc[p][v8 * 4 + 1].x, act), apply_act(acc[p][v8 * 4 + 1].y, act));
-                        o.z = float2_to_bf16x2(apply_act(acc[p][v8 * 4 + 2].x, act), apply_act(acc[p][v8 * 4 + 2].y, act));
-                        o.w = float2_to_bf16x2(apply_act(acc[p][v8 * 4 + 3].x, act), apply_act(acc[p][v8 * 4 + 3].y, act));
+                        o.x = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 0].x), st_act<ACT>(acc[p][v8 * 4 + 0].y));
+                        o.y = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 1].x), st_act<ACT>(acc[p][v8 * 4 + 1].y));
+                        o.z = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 2].x), st_act<ACT>(acc[p][v8 * 4 + 2].y));
+                        o.w = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 3].x), st_act<ACT>(acc[p][v8 * 4 + 3].y));
                         yo[p * (COUT / 8) + v8] = o;
                     }
                 }
@@ -206,16 +214,16 @@ int stem_make_tmap(CUtensorMap* map, const float* images, int B, int H, int W) {
     return DN_OK;
 }
 
-template <int COUT, int NPX>
+template <int COUT, int NPX, int ACT>
 static int stem_launch_t(const CUtensorMap& tm, const float* w, const float* bias, const StemNorm& nm, void* y, int B, int H,
-                         int W, int act, cudaStream_t stream) {
+                         int W, cudaStream_t stream) {
     constexpr int THREADS = ST_TH * (ST_TW / NPX);
     const size_t smem = (size_t)(ST_RAW_FLOATS + ST_NRM_FLOATS + 28 * COUT) * 4;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(stem_tma_kernel<COUT, NPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DN_CHECK_CUDA(cudaFuncSetAttribute(stem_tma_kernel<COUT, NPX, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int n = 0;
-        DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_tma_kernel<COUT, NPX>, THREADS, smem));
+        DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_tma_kernel<COUT, NPX, ACT>, THREADS, smem));
         ctas_per_sm = n > 0 ? n : 1;
     }
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
@@ -224,10 +232,21 @@ static int stem_launch_t(const CUtensorMap& tm, const float* w, const float* bia
     DN_REQUIRE(n_tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "stem problem too large");
     long long grid = (long long)ctas_per_sm * sm_count();
     if (grid > n_tiles) grid = n_tiles;
-    launch_pdl(stem_tma_kernel<COUT, NPX>, (unsigned)grid, THREADS, smem, stream, tm, w, bias, (uint4*)y, H, W, Ho, Wo, tiles_x, tiles_y,
-                                                                         (int)n_tiles, nm, act);
+    launch_pdl(stem_tma_kernel<COUT, NPX, ACT>, (unsigned)grid, THREADS, smem, stream, tm, w, bias, (uint4*)y, H, W, Ho, Wo, tiles_x,
+               tiles_y, (int)n_tiles, nm);
     DN_CHECK_LAUNCH();
     return DN_OK;
+}
+
+template <int COUT, int NPX>
+static int stem_launch_a(const CUtensorMap& tm, const float* w, const float* bias, const StemNorm& nm, void* y, int B, int H,
+                         int W, int act, cudaStream_t stream) {
+    switch (act) {
+        case DN_ACT_RELU: return stem_launch_t<COUT, NPX, DN_ACT_RELU>(tm, w, bias, nm, y, B, H, W, stream);
+        case DN_ACT_RELU6: return stem_launch_t<COUT, NPX, DN_ACT_RELU6>(tm, w, bias, nm, y, B, H, W, stream);
+        case DN_ACT_HSWISH: return stem_launch_t<COUT, NPX, DN_ACT_HSWISH>(tm, w, bias, nm, y, B, H, W, stream);
+        default: return stem_launch_t<COUT, NPX, DN_ACT_NONE>(tm, w, bias, nm, y, B, H, W, stream);
+    }
 }
 
 // r = RN(1/s); false when the shortcut division is not provably exact for this divisor
@@ -253,8 +272,8 @@ int stem_tma_launch(const CUtensorMap& tm, const float* w, const float* bias, co
         DN_REQUIRE(stem_recip(std3[i], &nm.rinv[i]), DN_ERR_INVALID, "image_std[%d] = %g is not usable by the tiled stem", i,
                    (double)std3[i]);
     }
-    if (Cout == 16) return stem_launch_t<16, 4>(tm, w, bias, nm, y, B, H, W, act, stream);
-    return stem_launch_t<32, 2>(tm, w, bias, nm, y, B, H, W, act, stream);
+    if (Cout == 16) return stem_launch_a<16, 4>(tm, w, bias, nm, y, B, H, W, act, stream);
+    return stem_launch_a<32, 2>(tm, w, bias, nm, y, B, H, W, act, stream);
 }
 
 }  // namespace dn
