@@ -192,8 +192,18 @@ def layer_costs(plan, B):
     Algorithmic bytes = input + output activations at their stored width + weights."""
     out = []
     P, K = plan.num_priors, plan.num_classes
-    for L in plan.layers:
+    from demonet_b200 import plan as dplan
+    fused = set(dplan.fused_pairs(plan)) if int(os.environ.get("DN_FUSE", "1")) else set()
+    for i, L in enumerate(plan.layers):
         hi, wi, ho, wo = L.h_in, L.w_in, L.h_out, L.w_out
+        if i in fused:            # expand + depthwise in one launch: the expanded tensor is not algorithmic traffic any more
+            D = plan.layers[i + 1]
+            out.append(("pwdw_fused_kernel", B * (hi * wi * L.cin + D.h_out * D.w_out * D.cout) * 2 + L.cin * L.cout * 2 + D.k * D.k * D.cout * 4,
+                        2 * B * (hi * wi * L.cin * L.cout + D.h_out * D.w_out * D.cout * D.k * D.k)))
+            continue
+        if i - 1 in fused:
+            out.append(("(fused into the previous launch)", 0, 0))
+            continue
         if L.kind == "stem":
             out.append(("stem_conv_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
         elif L.kind == "dw":
@@ -365,6 +375,8 @@ def main():
     costs = layer_costs(model.plan, B)
     per_kernel = {}
     for (name, nbytes, flops), t in zip(costs, list(ms)):
+        if nbytes == 0 and flops == 0 and name.startswith("(fused"):
+            continue
         k = per_kernel.setdefault(name, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
         k["ms"] += t; k["bytes"] += nbytes; k["flops"] += flops; k["launches"] += 1
     sum_ms = sum(k["ms"] for k in per_kernel.values())
@@ -418,8 +430,11 @@ def main():
         for i, ((name, nbytes, flops), t) in enumerate(zip(costs, list(ms))):
             L = model.plan.layers[i] if i < len(model.plan.layers) else None
             desc = "%s %dx%d c%d->%d k%d s%d" % (L.kind, L.h_in, L.w_in, L.cin, L.cout, L.k, L.stride) if L else name
-            print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (t * 1e-3) / 1e9,
-                                                             flops / (t * 1e-3) / 1e12), file=sys.stderr)
+            tt = max(t, 1e-9)
+            if name == "pwdw_fused_kernel":
+                desc = "pw+dw fused " + desc[3:]
+            print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (tt * 1e-3) / 1e9,
+                                                             flops / (tt * 1e-3) / 1e12), file=sys.stderr)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -15,7 +15,7 @@ DN_ERR_UNSUPPORTED = -3
 DN_ERR_WORKSPACE = -4
 
 ACT = {"none": 0, "relu": 1, "relu6": 2, "hardswish": 3}
-OP_STEM, OP_DW, OP_PW, OP_SE = 0, 1, 2, 3
+OP_STEM, OP_DW, OP_PW, OP_SE, OP_PWDW, OP_NOP = 0, 1, 2, 3, 4, 5
 BUF_NONE, BUF_IMAGES = -1, -2
 
 c_void_p, c_int, c_int32, c_int64, c_float, c_double, c_size_t = (
@@ -33,7 +33,7 @@ class Op(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("act", c_int32), ("in_buf", c_int32), ("out_buf", c_int32), ("res_buf", c_int32),
                 ("h_in", c_int32), ("w_in", c_int32), ("c_in", c_int32), ("h_out", c_int32), ("w_out", c_int32),
                 ("c_out", c_int32), ("ksize", c_int32), ("stride", c_int32), ("c_mid", c_int32), ("out_fp32", c_int32),
-                ("lane", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
+                ("lane", c_int32), ("act2", c_int32), ("reserved", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
                 ("out_batch_stride", c_int64), ("out_row_stride", c_int64), ("out_offset", c_int64)]
 
 
@@ -55,6 +55,8 @@ _SIGNATURES = {
     "dn_dwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dn_pwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int64, c_int64, c_int, c_void_p]),
+    "dn_pwdw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_int, c_int, c_void_p]),
     "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dn_se_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

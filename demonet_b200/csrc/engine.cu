@@ -48,7 +48,7 @@ struct dn_engine {
     int n_se = 0;
     std::vector<CUtensorMap> tmap_a, tmap_w, tmap_y;       // per op (PW only)
     std::vector<char> has_tmap_y;
-    std::vector<CUtensorMap> tmap_dw;               // per op (DW only)
+    std::vector<CUtensorMap> tmap_dw;               // per op (DW only; PWDW: the input window map)
     std::vector<DwTiling> dw_tiling;
     std::vector<DwStream> dw_stream;
     std::vector<char> dw_tma;                       // per op: 0 direct, 1 TMA tiles, 2 row stream, 3 stride-2 row stream
@@ -105,7 +105,10 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
                DN_ERR_INVALID, "bad head buffer ids");
     for (int i = 0; i < d->n_ops; ++i) {
         const dn_op& o = d->ops_host[i];
-        DN_REQUIRE(o.kind >= DN_OP_STEM && o.kind <= DN_OP_SE, DN_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        DN_REQUIRE(o.kind >= DN_OP_STEM && o.kind <= DN_OP_NOP, DN_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        if (o.kind == DN_OP_NOP) continue;
+        DN_REQUIRE(o.kind != DN_OP_PWDW || pwdw_fused_supported(o.h_in, o.w_in, o.c_in, o.c_out, o.ksize, o.stride),
+                   DN_ERR_UNSUPPORTED, "op %d: shape not supported by the fused expand + depthwise kernel", i);
         DN_REQUIRE(o.in_buf == DN_BUF_IMAGES || (o.in_buf >= 0 && o.in_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad in_buf", i);
         DN_REQUIRE(o.kind == DN_OP_SE || (o.out_buf >= 0 && o.out_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad out_buf", i);
         DN_REQUIRE(o.res_buf == DN_BUF_NONE || (o.res_buf >= 0 && o.res_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad res_buf", i);
@@ -333,6 +336,12 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
         e->has_tmap_y.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
+            if (o.kind == DN_OP_PWDW) {
+                int rc = pwdw_fused_make_tmaps(&e->tmap_a[i], &e->tmap_w[i], buf_ptr(e, o.in_buf), e->weights + o.w_off,
+                                               e->max_batch, o.h_in, o.w_in);
+                if (rc) return rc;
+                continue;
+            }
             if (o.kind != DN_OP_PW) continue;
             int bn, nt, st, cols;
             size_t smem;
@@ -406,6 +415,12 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                     rc = pwconv_simt(buf_ptr(e, o.in_buf), W + o.w_off, ep, M, o.c_in, o.c_out, s);
                 break;
             }
+            case DN_OP_PWDW:
+                rc = pwdw_fused_launch(e->tmap_a[i], e->tmap_w[i], (const float*)(W + o.b_off), (const float*)(W + o.w2_off),
+                                       (const float*)(W + o.b2_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.act, o.act2, s);
+                break;
+            case DN_OP_NOP:
+                break;
             case DN_OP_SE:
                 rc = dn_se_inplace(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
                                    (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
@@ -658,7 +673,12 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
 
 // layers (a squeeze-excitation is 4 launches) + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS,
 // CTA NMS, merge)
-extern "C" int dn_engine_launches_per_forward(dn_engine* e) { return e ? (int)e->ops.size() + 3 * e->n_se + 14 : 0; }
+extern "C" int dn_engine_launches_per_forward(dn_engine* e) {
+    if (!e) return 0;
+    int nop = 0;
+    for (const auto& o : e->ops) nop += (o.kind == DN_OP_NOP);
+    return (int)e->ops.size() - nop + 3 * e->n_se + 14;
+}
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) {
     return e ? e->device_bytes + (e->twin ? e->twin->device_bytes : 0) : 0;
 }

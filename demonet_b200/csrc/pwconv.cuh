@@ -46,4 +46,10 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
                      int N, cudaStream_t stream);
 
+// fused pointwise-expand -> depthwise (pwdw_fused.cu)
+bool pwdw_fused_supported(int H, int W, int K, int N, int ksize, int stride);
+int pwdw_fused_make_tmaps(CUtensorMap* tx, CUtensorMap* tw, const void* x, const void* w_pw, int B, int H, int W);
+int pwdw_fused_launch(const CUtensorMap& tx, const CUtensorMap& tw, const float* b_pw, const float* w_dw, const float* b_dw, void* y,
+                      int B, int H, int W, int act_pw, int act_dw, cudaStream_t stream);
+
 }  // namespace dn

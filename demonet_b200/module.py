@@ -7,6 +7,7 @@ libdemonet_b200.so through ctypes; PyTorch only owns parameters, device memory a
 """
 import ctypes
 import math
+import os
 import warnings
 from typing import Dict, List, Optional, Tuple
 
@@ -36,7 +37,8 @@ class _Engine:
     def _create(self, offsets):
         lib = _C.lib()
         plan, kw = self.plan, self._desc_kwargs
-        self._ops = _plan.build_ops(plan, offsets, self.t2b, self.logits_buf, self.bbox_buf)
+        fuse = not kw.get("keep_activations", False) and int(os.environ.get("DN_FUSE", "1")) != 0 and int(kw.get("gemm_impl", 0)) == 0
+        self._ops = _plan.build_ops(plan, offsets, self.t2b, self.logits_buf, self.bbox_buf, fuse=fuse)
         bufs = (_C.Buf * len(self.bufs))()
         for i, (elems, nbytes) in enumerate(self.bufs):
             bufs[i].elems_per_image, bufs[i].elem_bytes = elems, nbytes

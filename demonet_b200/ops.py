@@ -201,6 +201,22 @@ def pwconv(x: Tensor, w: Tensor, bias: Tensor, act: str = "none", residual: Tens
     return y
 
 
+def pwdw_fused(x: Tensor, w_pw: Tensor, b_pw: Tensor, w_dw: Tensor, b_dw: Tensor, k: int, stride: int, act_pw: str,
+               act_dw: str) -> Tensor:
+    """x bf16 [B,H,W,K] -> act_dw(dw(act_pw(x . w_pw^T + b_pw))) bf16 [B,Ho,Wo,N] with the expanded tensor kept on chip.
+    w_pw bf16 [N,K]; w_dw fp32 [k*k,N]."""
+    _require_cuda(x, w_pw, b_pw, w_dw, b_dw)
+    B, H, W, K = x.shape
+    N = w_pw.shape[0]
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    y = torch.empty(B, Ho, Wo, N, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().dn_pwdw_fused(x.contiguous().data_ptr(), w_pw.contiguous().data_ptr(), b_pw.contiguous().data_ptr(),
+                                        w_dw.contiguous().data_ptr(), b_dw.contiguous().data_ptr(), y.data_ptr(), B, H, W, K, N,
+                                        k, stride, _C.ACT[act_pw], _C.ACT[act_dw], _stream(x)))
+    return y
+
+
 def stem_conv(images: Tensor, w: Tensor, bias: Tensor, mean, std, act: str) -> Tensor:
     """images fp32 [B,3,H,W]; w fp32 [27,Cout]; -> bf16 [B,Ho,Wo,Cout] (normalise + 3x3 s2 + act)."""
     _require_cuda(images, w, bias)

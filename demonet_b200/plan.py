@@ -320,10 +320,16 @@ def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
         else:                     # pw: [N,K,1,1] -> [N][K] bf16 (block-diagonal when pixels are packed)
             w2 = wf.float().reshape(L.cout, L.cin).to(torch.bfloat16)
             pf = pw_pack_factor(L)
+            raw_w, raw_b = w2.contiguous().view(torch.int16).numpy(), bias
             if pf > 1:
                 w2 = torch.block_diag(*([w2.float()] * pf)).to(torch.bfloat16)
                 bias = np.tile(bias, pf)
             w = w2.contiguous().view(torch.int16).numpy()
+            entry = {"w": put(w), "b": put(bias)}
+            # the fused expand + depthwise kernel takes the plain [N, K] weights (no pixel packing)
+            entry["w_raw"], entry["b_raw"] = (put(raw_w), put(raw_b)) if pf > 1 else (entry["w"], entry["b"])
+            offs.append(entry)
+            continue
         offs.append({"w": put(w), "b": put(bias)})
     return b"".join(chunks), offs
 
@@ -396,8 +402,30 @@ def assign_buffers(plan: Plan, reuse: bool = True):
     return t2b, [tuple(b) for b in bufs], logits_buf, bbox_buf
 
 
-def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf):
-    """ctypes dn_op array for the engine."""
+def fused_pairs(plan: Plan) -> List[int]:
+    """Indices i such that layers[i] (pointwise expand) and layers[i+1] (depthwise) run as ONE kernel with the expanded
+    tensor kept on chip (csrc/pwdw_fused.cu).  Conditions: the expand output feeds only that depthwise layer, no
+    residual / head, and the shape is one the kernel is built for (16 -> 64 channels, 3x3 stride 2: MobileNetV3
+    block 2, the largest expanded tensor of the network)."""
+    uses: Dict[str, int] = {}
+    for L in plan.layers:
+        for t in (L.src, L.res):
+            if t:
+                uses[t] = uses.get(t, 0) + 1
+    out = []
+    for i in range(len(plan.layers) - 1):
+        a, b = plan.layers[i], plan.layers[i + 1]
+        if a.kind != "pw" or b.kind != "dw" or a.head or a.res or b.src != a.dst or uses.get(a.dst, 0) != 1:
+            continue
+        if a.dst in plan.feature_names or a.conv_bias or b.conv_bias:
+            continue
+        if (a.cin, a.cout, b.k, b.stride) == (16, 64, 3, 2) and a.h_in >= 8 and a.w_in >= 8 and a.act == b.act and a.act != "none":
+            out.append(i)
+    return out
+
+
+def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True):
+    """ctypes dn_op array for the engine (fuse=False keeps every layer a launch of its own)."""
     level_off, o = [], 0
     for h, w in plan.grid_sizes:
         level_off.append(o)
@@ -406,9 +434,26 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf):
     ops = (_C.Op * len(plan.layers))()
     lanes = layer_lanes(plan)
     kinds = {"stem": _C.OP_STEM, "dw": _C.OP_DW, "pw": _C.OP_PW, "se": _C.OP_SE}
+    fused = set(fused_pairs(plan)) if fuse else set()
     for i, (L, off) in enumerate(zip(plan.layers, offsets)):
         op = ops[i]
         op.kind, op.act = kinds[L.kind], _C.ACT[L.act]
+        if i in fused:                  # expand + depthwise in one launch; the depthwise slot becomes a no-op
+            D = plan.layers[i + 1]
+            op.kind, op.act2 = _C.OP_PWDW, _C.ACT[D.act]
+            op.in_buf, op.out_buf, op.res_buf = t2b[L.src], t2b[D.dst], _C.BUF_NONE
+            op.h_in, op.w_in, op.c_in = L.h_in, L.w_in, L.cin
+            op.h_out, op.w_out, op.c_out = D.h_out, D.w_out, D.cout
+            op.ksize, op.stride, op.lane = D.k, D.stride, lanes[i]
+            op.w_off, op.b_off = off["w_raw"], off["b_raw"]
+            op.w2_off, op.b2_off = offsets[i + 1]["w"], offsets[i + 1]["b"]
+            continue
+        if i - 1 in fused:
+            op.kind = _C.OP_NOP
+            op.in_buf = op.out_buf = t2b[L.dst]
+            op.res_buf = _C.BUF_NONE
+            op.lane = lanes[i]
+            continue
         op.in_buf = _C.BUF_IMAGES if L.src == "images" else t2b[L.src]
         op.res_buf = t2b[L.res] if L.res else _C.BUF_NONE
         op.h_in, op.w_in, op.c_in = L.h_in, L.w_in, L.cin

@@ -65,6 +65,14 @@ int dn_pwconv(const void* x, const void* w, const float* bias, const void* resid
               int N, int act, int out_fp32, int hw, int64_t out_batch_stride, int64_t out_row_stride,
               int impl, void* stream);
 
+/* Fused pointwise expand (1x1 conv + folded BN + act) -> depthwise k x k (+ folded BN + act): the expanded tensor stays
+ * in shared memory.  Replaces InvertedResidual.block[0:2] (mobilenetv3.py:75-83, mobilenetv2.py:84-87) where the shape
+ * is supported -- this build: K = 16 input channels, N = 64 expanded channels, 3x3 stride 2 (MobileNetV3 block 2);
+ * DN_ERR_UNSUPPORTED otherwise.  x: bf16 [B,H,W,K]; w_pw: bf16 [N,K]; b_pw: fp32 [N]; w_dw: fp32 [k*k,N]; b_dw: fp32 [N];
+ * y: bf16 [B,Ho,Wo,N].  Results equal dn_pwconv followed by dn_dwconv up to the fp32 summation order of the stencil. */
+int dn_pwdw_fused(const void* x, const void* w_pw, const float* b_pw, const float* w_dw, const float* b_dw, void* y,
+                  int B, int H, int W, int K, int N, int ksize, int stride, int act_pw, int act_dw, void* stream);
+
 /* Stem: input normalisation + dense 3x3 stride-2 convolution + folded BN + activation.
  * Replaces GeneralizedRCNNTransform.normalize (transform.py:129-138) followed by the first
  * ConvBNActivation (mobilenetv3.py:141-142, mobilenetv2.py:157).
@@ -158,7 +166,11 @@ typedef enum {
     DN_OP_STEM = 0,      /* normalise + dense 3x3 s2 conv                      */
     DN_OP_DW = 1,        /* depthwise conv                                      */
     DN_OP_PW = 2,        /* pointwise GEMM                                      */
-    DN_OP_SE = 3         /* squeeze-excitation, in place on in_buf              */
+    DN_OP_SE = 3,        /* squeeze-excitation, in place on in_buf              */
+    DN_OP_PWDW = 4,      /* fused pointwise expand + depthwise (dn_pwdw_fused): in_buf [H,W,c_in] -> out_buf
+                            [h_out,w_out,c_out]; w_off/b_off = expand weights / bias, w2_off/b2_off = depthwise
+                            weights / bias, act = expand activation, act2 = depthwise activation             */
+    DN_OP_NOP = 5        /* placeholder of a layer that was fused into its predecessor                       */
 } dn_op_kind;
 
 #define DN_BUF_NONE (-1)
@@ -174,6 +186,8 @@ typedef struct {
     int32_t out_fp32;
     int32_t lane;                          /* launch lane: 0 = main chain, > 0 = a side branch (head) that may run
                                               concurrently; its tensors never share arena buffers with other lanes */
+    int32_t act2;                          /* second activation of a fused op               */
+    int32_t reserved;
     int64_t w_off, b_off, w2_off, b2_off;  /* byte offsets into the weight blob             */
     int64_t out_batch_stride, out_row_stride, out_offset;   /* PW output addressing (elements) */
 } dn_op;

@@ -46,6 +46,17 @@ def run_plan(plan, blob, ops, bufs, logits_buf, bbox_buf, images, mean, std, rou
             y = _act(F.conv2d(x, w, f32(op.b_off, ci), op.stride, (k - 1) // 2, 1, ci), op.act)
             assert y.shape[-2:] == (ho, wo)
             arena[op.out_buf][:B * ho * wo * co] = _bf16(y).permute(0, 2, 3, 1).reshape(-1)
+        elif op.kind == _C.OP_NOP:
+            continue
+        elif op.kind == _C.OP_PWDW:
+            hw = hi * wi
+            x = arena[op.in_buf][:B * hw * ci].view(B * hw, ci)
+            mid = _bf16(_act(x @ bf16w(op.w_off, co * ci).view(co, ci).t() + f32(op.b_off, co), op.act))
+            k = op.ksize
+            w = f32(op.w2_off, k * k * co).view(k, k, co).permute(2, 0, 1)[:, None]
+            y = _act(F.conv2d(mid.view(B, hi, wi, co).permute(0, 3, 1, 2), w, f32(op.b2_off, co), op.stride, (k - 1) // 2, 1, co), op.act2)
+            assert y.shape[-2:] == (ho, wo)
+            arena[op.out_buf][:B * ho * wo * co] = _bf16(y).permute(0, 2, 3, 1).reshape(-1)
         elif op.kind == _C.OP_SE:
             x = arena[op.in_buf][:B * hi * wi * ci].view(B, hi * wi, ci)
             cs = op.c_mid

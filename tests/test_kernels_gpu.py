@@ -155,3 +155,26 @@ def test_se(C, Cs, HW):
     ref = xf * scale[:, None, :]
     y = ops.se_inplace(x.clone(), w1, b1, w2.t().contiguous(), b2)
     _close_bf16(y, ref, extra_abs=2e-3)
+
+
+@pytest.mark.parametrize("B,H,W,act", [(3, 160, 160, "relu"), (2, 40, 40, "relu6"), (5, 50, 38, "hardswish"), (1, 17, 9, "relu"),
+                                       (40, 32, 32, "relu")])
+def test_pwdw_fused_matches_two_kernels(B, H, W, act):
+    """Fused expand (16 -> 64) + depthwise 3x3 s2 against the unfused pair: the expand GEMM is the same tensor-core
+    product with the same single rounding, so only the fp32 summation order of the stencil may differ (<= 1 bf16 ulp);
+    and against a plain fp32 PyTorch evaluation of the two convolutions."""
+    g = torch.Generator().manual_seed(B * 7 + H + W)
+    K, N = 16, 64
+    x = (torch.randn(B, H, W, K, generator=g)).bfloat16().cuda()
+    w_pw = (torch.randn(N, K, generator=g) / 4).bfloat16().cuda()
+    b_pw = torch.randn(N, generator=g).cuda()
+    w_dw = (torch.randn(9, N, generator=g) / 3).cuda()
+    b_dw = torch.randn(N, generator=g).cuda()
+    y = ops.pwdw_fused(x, w_pw, b_pw, w_dw, b_dw, 3, 2, act, act)
+    mid = ops.pwconv(x.reshape(-1, K), w_pw, b_pw, act).reshape(B, H, W, N)
+    two = ops.dwconv(mid, w_dw, b_dw, 3, 2, act)
+    assert y.shape == two.shape
+    _close_bf16(y, two.float())
+    mid_ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), w_pw.float().reshape(N, K, 1, 1), b_pw)).bfloat16().float()
+    ref = ACTS[act](F.conv2d(mid_ref, w_dw.t().reshape(N, 1, 3, 3), b_dw, 2, 1, 1, N)).permute(0, 2, 3, 1)
+    _close_bf16(y, ref, extra_abs=2e-2)
