@@ -194,6 +194,7 @@ def layer_costs(plan, B):
     P, K = plan.num_priors, plan.num_classes
     from demonet_b200 import plan as dplan
     fused = set(dplan.fused_pairs(plan)) if int(os.environ.get("DN_FUSE", "1")) else set()
+    fused_dp = set(dplan.fused_dwpw_pairs(plan)) if int(os.environ.get("DN_FUSE", "1")) and dplan.dwpw_fusion_enabled() else set()
     for i, L in enumerate(plan.layers):
         hi, wi, ho, wo = L.h_in, L.w_in, L.h_out, L.w_out
         if i in fused:            # expand + depthwise in one launch: the expanded tensor is not algorithmic traffic any more
@@ -201,8 +202,13 @@ def layer_costs(plan, B):
             out.append(("pwdw_fused_kernel", B * (hi * wi * L.cin + D.h_out * D.w_out * D.cout) * 2 + L.cin * L.cout * 2 + D.k * D.k * D.cout * 4,
                         2 * B * (hi * wi * L.cin * L.cout + D.h_out * D.w_out * D.cout * D.k * D.k)))
             continue
-        if i - 1 in fused:
+        if i - 1 in fused or i - 1 in fused_dp:
             out.append(("(fused into the previous launch)", 0, 0))
+            continue
+        if i in fused_dp:         # depthwise + project (+ residual): input read once, output written once
+            Pj = plan.layers[i + 1]
+            out.append(("dwpw_fused_kernel", B * hi * wi * (L.cin + Pj.cout) * 2 + L.k * L.k * L.cin * 4 + L.cin * Pj.cout * 2,
+                        2 * B * hi * wi * (L.cin * L.k * L.k + L.cin * Pj.cout)))
             continue
         if L.kind == "stem":
             out.append(("stem_conv_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
@@ -404,7 +410,8 @@ def main():
         if cands and B == 256:
             nl = json.load(open(cands[-1]))["kernels"]
             fam = {"dwconv_kernel": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
-                   "pwconv_tc_kernel": ["pwconv_tc_kernel"], "stem_conv_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
+                   "pwconv_tc_kernel": ["pwconv_tc_kernel"], "pwdw_fused_kernel": ["pwdw_fused_kernel"],
+                   "dwpw_fused_kernel": ["dwpw_fused_kernel"], "stem_conv_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
                    "se_pool+fc1+fc2+scale kernels": ["se_pool_kernel", "se_fc1_kernel", "se_fc2_kernel", "se_scale_kernel"]}
             names = fam.get(dominant, [dominant])
             names = names + ["dn::" + n for n in names]              # ncu reports the name with or without the namespace
@@ -433,6 +440,8 @@ def main():
             tt = max(t, 1e-9)
             if name == "pwdw_fused_kernel":
                 desc = "pw+dw fused " + desc[3:]
+            if name == "dwpw_fused_kernel":
+                desc = "dw+pw fused " + desc[3:]
             print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (tt * 1e-3) / 1e9,
                                                              flops / (tt * 1e-3) / 1e12), file=sys.stderr)
 

@@ -15,7 +15,7 @@ DN_ERR_UNSUPPORTED = -3
 DN_ERR_WORKSPACE = -4
 
 ACT = {"none": 0, "relu": 1, "relu6": 2, "hardswish": 3}
-OP_STEM, OP_DW, OP_PW, OP_SE, OP_PWDW, OP_NOP = 0, 1, 2, 3, 4, 5
+OP_STEM, OP_DW, OP_PW, OP_SE, OP_PWDW, OP_NOP, OP_DWPW = 0, 1, 2, 3, 4, 5, 6
 BUF_NONE, BUF_IMAGES = -1, -2
 
 c_void_p, c_int, c_int32, c_int64, c_float, c_double, c_size_t = (
@@ -56,6 +56,8 @@ _SIGNATURES = {
     "dn_pwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int64, c_int64, c_int, c_void_p]),
     "dn_pwdw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_dwpw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_void_p]),
     "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_void_p]),

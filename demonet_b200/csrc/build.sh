@@ -6,7 +6,7 @@ OUT="$HERE/../lib"
 mkdir -p "$OUT"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-SRCS="error.cu postprocess.cu dwconv.cu dwconv_tma.cu dwconv_stream.cu dwconv_stream2.cu se.cu transform.cu stem_tma.cu pwconv_simt.cu pwconv_tc.cu pwdw_fused.cu engine.cu"
+SRCS="error.cu postprocess.cu dwconv.cu dwconv_tma.cu dwconv_stream.cu dwconv_stream2.cu se.cu transform.cu stem_tma.cu pwconv_simt.cu pwconv_tc.cu pwdw_fused.cu dwpw_fused.cu engine.cu"
 OBJS=""
 for s in $SRCS; do
   o="$OUT/${s%.cu}.o"

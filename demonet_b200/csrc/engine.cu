@@ -105,7 +105,10 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
                DN_ERR_INVALID, "bad head buffer ids");
     for (int i = 0; i < d->n_ops; ++i) {
         const dn_op& o = d->ops_host[i];
-        DN_REQUIRE(o.kind >= DN_OP_STEM && o.kind <= DN_OP_NOP, DN_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        DN_REQUIRE(o.kind >= DN_OP_STEM && o.kind <= DN_OP_DWPW, DN_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        DN_REQUIRE(o.kind != DN_OP_DWPW || (dwpw_fused_supported(o.h_in, o.w_in, o.c_in, o.c_out, o.ksize, o.stride) &&
+                                            (o.res_buf == DN_BUF_NONE || o.res_buf == o.in_buf) && o.in_buf != o.out_buf),
+                   DN_ERR_UNSUPPORTED, "op %d: shape not supported by the fused depthwise + project kernel", i);
         if (o.kind == DN_OP_NOP) continue;
         DN_REQUIRE(o.kind != DN_OP_PWDW || pwdw_fused_supported(o.h_in, o.w_in, o.c_in, o.c_out, o.ksize, o.stride),
                    DN_ERR_UNSUPPORTED, "op %d: shape not supported by the fused expand + depthwise kernel", i);
@@ -336,6 +339,12 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
         e->has_tmap_y.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
+            if (o.kind == DN_OP_DWPW) {
+                int rc = dwpw_fused_make_tmaps(&e->tmap_a[i], &e->tmap_w[i], buf_ptr(e, o.in_buf), e->weights + o.w2_off,
+                                               e->max_batch, o.h_in, o.w_in);
+                if (rc) return rc;
+                continue;
+            }
             if (o.kind == DN_OP_PWDW) {
                 int rc = pwdw_fused_make_tmaps(&e->tmap_a[i], &e->tmap_w[i], buf_ptr(e, o.in_buf), e->weights + o.w_off,
                                                e->max_batch, o.h_in, o.w_in);
@@ -418,6 +427,11 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
             case DN_OP_PWDW:
                 rc = pwdw_fused_launch(e->tmap_a[i], e->tmap_w[i], (const float*)(W + o.b_off), (const float*)(W + o.w2_off),
                                        (const float*)(W + o.b2_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.act, o.act2, s);
+                break;
+            case DN_OP_DWPW:
+                rc = dwpw_fused_launch(e->tmap_a[i], e->tmap_w[i], (const float*)(W + o.w_off), (const float*)(W + o.b_off),
+                                       (const float*)(W + o.b2_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.act,
+                                       o.res_buf != DN_BUF_NONE, s);
                 break;
             case DN_OP_NOP:
                 break;

@@ -52,4 +52,10 @@ int pwdw_fused_make_tmaps(CUtensorMap* tx, CUtensorMap* tw, const void* x, const
 int pwdw_fused_launch(const CUtensorMap& tx, const CUtensorMap& tw, const float* b_pw, const float* w_dw, const float* b_dw, void* y,
                       int B, int H, int W, int act_pw, int act_dw, cudaStream_t stream);
 
+// fused depthwise -> pointwise project (+ residual) (dwpw_fused.cu)
+bool dwpw_fused_supported(int H, int W, int C, int N, int ksize, int stride);
+int dwpw_fused_make_tmaps(CUtensorMap* tx, CUtensorMap* tw, const void* x, const void* w_pw, int B, int H, int W);
+int dwpw_fused_launch(const CUtensorMap& tx, const CUtensorMap& tw, const float* w_dw, const float* b_dw, const float* b_pw, void* y,
+                      int B, int H, int W, int act_dw, int residual, cudaStream_t stream);
+
 }  // namespace dn

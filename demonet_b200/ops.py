@@ -217,6 +217,20 @@ def pwdw_fused(x: Tensor, w_pw: Tensor, b_pw: Tensor, w_dw: Tensor, b_dw: Tensor
     return y
 
 
+def dwpw_fused(x: Tensor, w_dw: Tensor, b_dw: Tensor, w_pw: Tensor, b_pw: Tensor, k: int, stride: int, act_dw: str,
+               residual: bool) -> Tensor:
+    """x bf16 [B,H,W,C] -> (act_dw(dw(x)) . w_pw^T + b_pw) (+ x) bf16 [B,H,W,N] with the depthwise output kept on chip."""
+    _require_cuda(x, w_dw, b_dw, w_pw, b_pw)
+    B, H, W, C = x.shape
+    N = w_pw.shape[0]
+    y = torch.empty(B, H, W, N, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().dn_dwpw_fused(x.contiguous().data_ptr(), w_dw.contiguous().data_ptr(), b_dw.contiguous().data_ptr(),
+                                        w_pw.contiguous().data_ptr(), b_pw.contiguous().data_ptr(), y.data_ptr(), B, H, W, C, N,
+                                        k, stride, _C.ACT[act_dw], int(residual), _stream(x)))
+    return y
+
+
 def stem_conv(images: Tensor, w: Tensor, bias: Tensor, mean, std, act: str) -> Tensor:
     """images fp32 [B,3,H,W]; w fp32 [27,Cout]; -> bf16 [B,Ho,Wo,Cout] (normalise + 3x3 s2 + act)."""
     _require_cuda(images, w, bias)

@@ -424,6 +424,37 @@ def fused_pairs(plan: Plan) -> List[int]:
     return out
 
 
+def dwpw_fusion_enabled() -> bool:
+    """DN_FUSE_DWPW=0 keeps the depthwise + project pair of block 1 as two launches (measurement aid; r01: fused 0.199 ms,
+    unfused 0.104 + 0.137 ms)."""
+    import os
+    return os.environ.get("DN_FUSE_DWPW", "1") != "0"
+
+
+def fused_dwpw_pairs(plan: Plan) -> List[int]:
+    """Indices i such that layers[i] (depthwise) and layers[i+1] (pointwise project, optionally `+= block input`) run as
+    ONE kernel with the depthwise output kept on chip (csrc/dwpw_fused.cu): 16 channels, 3x3 stride 1, project 16 -> 16 --
+    MobileNetV3 block 1.  The residual, if any, must be the depthwise layer's own input."""
+    uses: Dict[str, int] = {}
+    for L in plan.layers:
+        for t in (L.src, L.res):
+            if t:
+                uses[t] = uses.get(t, 0) + 1
+    taken = set(fused_pairs(plan))
+    out = []
+    for i in range(len(plan.layers) - 1):
+        a, b = plan.layers[i], plan.layers[i + 1]
+        if a.kind != "dw" or b.kind != "pw" or b.head or b.src != a.dst or uses.get(a.dst, 0) != 1 or a.conv_bias or b.conv_bias:
+            continue
+        if i in taken or i - 1 in taken or a.dst in plan.feature_names:
+            continue
+        if b.res is not None and b.res != a.src:
+            continue
+        if (a.cin, b.cout, a.k, a.stride) == (16, 16, 3, 1) and a.h_in >= 8 and a.w_in >= 16 and a.act != "none" and b.act == "none":
+            out.append(i)
+    return out
+
+
 def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True):
     """ctypes dn_op array for the engine (fuse=False keeps every layer a launch of its own)."""
     level_off, o = [], 0
@@ -435,9 +466,27 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True)
     lanes = layer_lanes(plan)
     kinds = {"stem": _C.OP_STEM, "dw": _C.OP_DW, "pw": _C.OP_PW, "se": _C.OP_SE}
     fused = set(fused_pairs(plan)) if fuse else set()
+    fused_dp = set(fused_dwpw_pairs(plan)) if fuse and dwpw_fusion_enabled() else set()
     for i, (L, off) in enumerate(zip(plan.layers, offsets)):
         op = ops[i]
         op.kind, op.act = kinds[L.kind], _C.ACT[L.act]
+        if i in fused_dp:               # depthwise + project (+ residual) in one launch
+            Pj = plan.layers[i + 1]
+            op.kind = _C.OP_DWPW
+            op.in_buf, op.out_buf = t2b[L.src], t2b[Pj.dst]
+            op.res_buf = t2b[Pj.res] if Pj.res else _C.BUF_NONE
+            op.h_in, op.w_in, op.c_in = L.h_in, L.w_in, L.cin
+            op.h_out, op.w_out, op.c_out = Pj.h_out, Pj.w_out, Pj.cout
+            op.ksize, op.stride, op.lane = L.k, L.stride, lanes[i]
+            op.w_off, op.b_off = off["w"], off["b"]
+            op.w2_off, op.b2_off = offsets[i + 1]["w_raw"], offsets[i + 1]["b_raw"]
+            continue
+        if i - 1 in fused_dp:
+            op.kind = _C.OP_NOP
+            op.in_buf = op.out_buf = t2b[L.dst]
+            op.res_buf = _C.BUF_NONE
+            op.lane = lanes[i]
+            continue
         if i in fused:                  # expand + depthwise in one launch; the depthwise slot becomes a no-op
             D = plan.layers[i + 1]
             op.kind, op.act2 = _C.OP_PWDW, _C.ACT[D.act]

@@ -73,6 +73,14 @@ int dn_pwconv(const void* x, const void* w, const float* bias, const void* resid
 int dn_pwdw_fused(const void* x, const void* w_pw, const float* b_pw, const float* w_dw, const float* b_dw, void* y,
                   int B, int H, int W, int K, int N, int ksize, int stride, int act_pw, int act_dw, void* stream);
 
+/* Fused depthwise k x k (+ folded BN + act) -> pointwise project (1x1 conv + folded BN, no activation) (+ residual = the
+ * block input): the depthwise output stays in shared memory.  Replaces InvertedResidual.block[1:] and `result += input`
+ * (mobilenetv3.py:80-99, mobilenetv2.py:87-100) where the shape is supported -- this build: C = N = 16 channels, 3x3
+ * stride 1 (MobileNetV3 block 1); DN_ERR_UNSUPPORTED otherwise.  x: bf16 [B,H,W,C]; w_dw: fp32 [k*k,C]; b_dw: fp32 [C];
+ * w_pw: bf16 [N,C]; b_pw: fp32 [N]; y: bf16 [B,H,W,N], y != x; residual != 0 adds x. */
+int dn_dwpw_fused(const void* x, const float* w_dw, const float* b_dw, const void* w_pw, const float* b_pw, void* y,
+                  int B, int H, int W, int C, int N, int ksize, int stride, int act_dw, int residual, void* stream);
+
 /* Stem: input normalisation + dense 3x3 stride-2 convolution + folded BN + activation.
  * Replaces GeneralizedRCNNTransform.normalize (transform.py:129-138) followed by the first
  * ConvBNActivation (mobilenetv3.py:141-142, mobilenetv2.py:157).
@@ -170,7 +178,10 @@ typedef enum {
     DN_OP_PWDW = 4,      /* fused pointwise expand + depthwise (dn_pwdw_fused): in_buf [H,W,c_in] -> out_buf
                             [h_out,w_out,c_out]; w_off/b_off = expand weights / bias, w2_off/b2_off = depthwise
                             weights / bias, act = expand activation, act2 = depthwise activation             */
-    DN_OP_NOP = 5        /* placeholder of a layer that was fused into its predecessor                       */
+    DN_OP_NOP = 5,       /* placeholder of a layer that was fused into its predecessor                       */
+    DN_OP_DWPW = 6       /* fused depthwise + pointwise project (dn_dwpw_fused): w_off/b_off = depthwise weights /
+                            bias, w2_off/b2_off = project weights / bias, act = depthwise activation, res_buf = in_buf
+                            for `result += input` or DN_BUF_NONE                                              */
 } dn_op_kind;
 
 #define DN_BUF_NONE (-1)

@@ -48,6 +48,15 @@ def run_plan(plan, blob, ops, bufs, logits_buf, bbox_buf, images, mean, std, rou
             arena[op.out_buf][:B * ho * wo * co] = _bf16(y).permute(0, 2, 3, 1).reshape(-1)
         elif op.kind == _C.OP_NOP:
             continue
+        elif op.kind == _C.OP_DWPW:
+            x = arena[op.in_buf][:B * hi * wi * ci].view(B, hi, wi, ci)
+            k = op.ksize
+            w = f32(op.w_off, k * k * ci).view(k, k, ci).permute(2, 0, 1)[:, None]
+            mid = _bf16(_act(F.conv2d(x.permute(0, 3, 1, 2), w, f32(op.b_off, ci), op.stride, (k - 1) // 2, 1, ci), op.act))
+            y = mid.permute(0, 2, 3, 1).reshape(-1, ci) @ bf16w(op.w2_off, co * ci).view(co, ci).t() + f32(op.b2_off, co)
+            if op.res_buf >= 0:
+                y = y + arena[op.res_buf][:B * hi * wi * co].view(-1, co)
+            arena[op.out_buf][:B * ho * wo * co] = _bf16(y).reshape(-1)
         elif op.kind == _C.OP_PWDW:
             hw = hi * wi
             x = arena[op.in_buf][:B * hw * ci].view(B * hw, ci)

@@ -178,3 +178,25 @@ def test_pwdw_fused_matches_two_kernels(B, H, W, act):
     mid_ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), w_pw.float().reshape(N, K, 1, 1), b_pw)).bfloat16().float()
     ref = ACTS[act](F.conv2d(mid_ref, w_dw.t().reshape(N, 1, 3, 3), b_dw, 2, 1, 1, N)).permute(0, 2, 3, 1)
     _close_bf16(y, ref, extra_abs=2e-2)
+
+
+@pytest.mark.parametrize("B,H,W,act,res", [(3, 160, 160, "relu", True), (2, 40, 48, "relu6", False), (5, 50, 38, "hardswish", True),
+                                           (1, 9, 17, "relu", True), (70, 16, 16, "relu", True)])
+def test_dwpw_fused_matches_two_kernels(B, H, W, act, res):
+    """Fused depthwise 3x3 s1 (16 ch) + project 16 -> 16 (+ residual) against the unfused pair and against fp32 PyTorch."""
+    g = torch.Generator().manual_seed(B * 11 + H + W)
+    C = 16
+    x = (torch.randn(B, H, W, C, generator=g)).bfloat16().cuda()
+    w_dw = (torch.randn(9, C, generator=g) / 3).cuda()
+    b_dw = torch.randn(C, generator=g).cuda()
+    w_pw = (torch.randn(C, C, generator=g) / 4).bfloat16().cuda()
+    b_pw = torch.randn(C, generator=g).cuda()
+    y = ops.dwpw_fused(x, w_dw, b_dw, w_pw, b_pw, 3, 1, act, res)
+    mid = ops.dwconv(x, w_dw, b_dw, 3, 1, act)
+    two = ops.pwconv(mid.reshape(-1, C), w_pw, b_pw, "none", residual=x.reshape(-1, C) if res else None).reshape(B, H, W, C)
+    _close_bf16(y, two.float(), extra_abs=2e-2)
+    mid_ref = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), w_dw.t().reshape(C, 1, 3, 3), b_dw, 1, 1, 1, C)).bfloat16().float()
+    ref = F.conv2d(mid_ref, w_pw.float().reshape(C, C, 1, 1), b_pw)
+    if res:
+        ref = ref + x.float().permute(0, 3, 1, 2)
+    _close_bf16(y, ref.permute(0, 2, 3, 1), extra_abs=2e-2)
