@@ -8,6 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdemonet_b200.so")
 
+ABI_VERSION = 2          # include/demonet_b200.h DN_ABI_VERSION
 DN_OK = 0
 DN_ERR_INVALID = -1
 DN_ERR_CUDA = -2
@@ -110,8 +111,8 @@ def lib():
             fn = getattr(handle, name)          # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
-        if handle.dn_abi_version() != 1:
-            raise RuntimeError("demonet_b200: ABI version mismatch")
+        if handle.dn_abi_version() != ABI_VERSION:
+            raise RuntimeError("demonet_b200: ABI version mismatch (library %d, binding %d); rebuild with `python -c 'import __graft_entry__ as g; g.build()'`" % (handle.dn_abi_version(), ABI_VERSION))
         _lib = handle
     return _lib
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 1
+#define DN_ABI_VERSION 2          /* 2: dn_op.lane / act2, dn_model_desc.pipeline_slots, fused ops, SE workspace */
 
 typedef enum {
     DN_OK = 0,

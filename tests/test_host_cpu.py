@@ -113,7 +113,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), "missing export: " + name
     assert declared == set(_C.EXPORTED_SYMBOLS)
-    assert _C.lib().dn_abi_version() == 1
+    assert _C.lib().dn_abi_version() == _C.ABI_VERSION == 2
 
 
 def test_c_abi_argument_validation_without_gpu():
