@@ -71,7 +71,9 @@ dwpw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                   const float* __restrict__ w_dw, const float* __restrict__ b_dw, const float* __restrict__ b_pw,
                   uint4* __restrict__ y, int H, int W, int tiles_x, int tiles_y, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char fd_smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fd_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic on the __shared__ array (not through an integer cast) so that the compiler keeps the
+    // shared address space and emits LDS / STS instead of generic loads and stores
+    unsigned char* base = fd_smem_raw + ((1024u - (fd_u32(fd_smem_raw) & 1023u)) & 1023u);
     unsigned char* a_t = base;                                       // [FD_SUB][128 x 16] bf16, SWIZZLE_32B (MMA A operands)
     unsigned char* w_s = a_t + FD_A_BYTES;                           // [16 x 16] bf16, SWIZZLE_32B (MMA B operand)
     unsigned char* in_t = w_s + 1024;                                // [2][10 x 18 x 16] bf16 input windows

@@ -73,7 +73,9 @@ pwdw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                   const float* __restrict__ b_pw, const float* __restrict__ w_dw, const float* __restrict__ b_dw,
                   uint4* __restrict__ y, int H, int W, int Ho, int Wo, int tiles_x, int tiles_y, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char fu_smem_raw[];
-    unsigned char* fu_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fu_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer arithmetic on the __shared__ array (not through an integer cast) so that the compiler keeps the
+    // shared address space and emits LDS / STS instead of generic loads and stores
+    unsigned char* fu_smem = fu_smem_raw + ((1024u - (fu_u32(fu_smem_raw) & 1023u)) & 1023u);
     unsigned char* a_in = fu_smem;                                  // [2][FU_A_BYTES]
     unsigned char* w_s = a_in + 2 * FU_A_BYTES;                     // [64 x 16] bf16, SWIZZLE_32B
     unsigned char* exp_t = w_s + 2048;                              // [289][64] bf16, chunk-swizzled
