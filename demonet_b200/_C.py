@@ -65,6 +65,8 @@ _SIGNATURES = {
     "dn_se_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dn_se_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                               c_size_t, c_void_p]),
+    "dn_dwconv_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, ctypes.POINTER(c_int), c_void_p]),
     "dn_postprocess_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(PostprocessParams)]),
     "dn_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p, c_size_t,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

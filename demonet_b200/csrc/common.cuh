@@ -21,6 +21,10 @@ namespace dn {
 void set_error(const char* fmt, ...);
 // uint8 -> fp32 / 255 (transform.cu), used by the engine's uint8 ingest
 int u8_to_f32_launch(const unsigned char* src, float* dst, size_t n, cudaStream_t s);
+// squeeze-excitation whose pooling was done by the producing depthwise launch (se.cu)
+int se_max_pool_slots();
+int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW, int C, int Cs,
+                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s);
 
 #define DN_CHECK_CUDA(expr)                                                                      \
     do {                                                                                         \

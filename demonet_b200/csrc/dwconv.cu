@@ -260,6 +260,41 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
     return launch_dw<5, 2, 2>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
 }
 
+// Depthwise conv followed by squeeze-excitation of its output (InvertedResidual with use_se, mobilenetv3.py:43-96):
+// when the layer runs on the stride-1 row stream and the batch is large enough, the stream leaves the SE channel sums
+// in the workspace and the SE pooling pass is skipped (*pooled_out = 1); otherwise dn_dwconv + dn_se_inplace.
+extern "C" int dn_dwconv_se(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
+                            int stride, int act, const float* se_w1, const float* se_b1, const float* se_w2t,
+                            const float* se_b2, int Cs, void* workspace, size_t workspace_bytes, int* pooled_out,
+                            void* stream_) {
+    DN_REQUIRE(x && w && bias && y && se_w1 && se_b1 && se_w2t && se_b2, DN_ERR_INVALID, "NULL tensor pointer");
+    DN_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && Cs > 0, DN_ERR_INVALID, "bad shape");
+    DN_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), DN_ERR_UNSUPPORTED,
+               "depthwise supports k in {3,5}, stride in {1,2} (got k=%d stride=%d)", k, stride);
+    const int pad = (k - 1) / 2;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    DN_REQUIRE(workspace != nullptr && workspace_bytes >= dn_se_workspace_bytes(B, Ho * Wo, C), DN_ERR_WORKSPACE,
+               "SE workspace too small (%zu < %zu bytes)", workspace_bytes, dn_se_workspace_bytes(B, Ho * Wo, C));
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (pooled_out) *pooled_out = 0;
+    if (C % 8 == 0 && dw_choose(H, W, C, k, stride) == DW_STREAM) {
+        DwStream sp;
+        DN_REQUIRE(dw_stream_plan(H, W, C, k, stride, &sp), DN_ERR_UNSUPPORTED, "no stream plan");
+        CUtensorMap tm;
+        int rc = dw_stream_make_tmap(&tm, x, B, H, W, C, k, sp);
+        if (rc) return rc;
+        DwPool pool{(float*)workspace, se_max_pool_slots(), 0, 0};
+        rc = dwconv_stream_launch(tm, sp, w, bias, y, B, H, W, C, k, act, s, &pool);
+        if (rc) return rc;
+        if (pooled_out) *pooled_out = pool.parts > 0;
+        return se_inplace_pooled(y, se_w1, se_b1, se_w2t, se_b2, B, Ho * Wo, C, Cs, workspace, workspace_bytes, pool.parts,
+                                 pool.slots, H, s);
+    }
+    int rc = dn_dwconv(x, w, bias, y, B, H, W, C, k, stride, act, stream_);
+    if (rc) return rc;
+    return dn_se_inplace(y, se_w1, se_b1, se_w2t, se_b2, B, Ho * Wo, C, Cs, workspace, workspace_bytes, stream_);
+}
+
 extern "C" int dn_stem_conv(const float* images, const float* w, const float* bias, const float* mean3_host,
                             const float* std3_host, void* y, int B, int H, int W, int Cout, int act, void* stream_) {
     DN_REQUIRE(images && w && bias && y && mean3_host && std3_host, DN_ERR_INVALID, "NULL pointer");

@@ -35,8 +35,16 @@ struct DwStream {
 };
 bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp);
 int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
+// Pooling side output of a row-stream launch for the squeeze-excitation that follows (dwconv_stream.cu, se.cu).
+// In: partial (fp32 [B][max_slots][C] workspace, NULL = no pooling), max_slots.  Out: parts = CTA shares per channel
+// block of the launch (0 = the launch did not pool: too many shares per image), slots = slot stride of `partial`.
+struct DwPool {
+    float* partial;
+    int max_slots;
+    int parts, slots;
+};
 int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
-                         int W, int C, int k, int act, cudaStream_t stream);
+                         int W, int C, int k, int act, cudaStream_t stream, DwPool* pool = nullptr);
 // TMA-fed row stream, stride 2 (dwconv_stream2.cu): same DwStream plan record (stage = 2 * ((k + 1) / 2) input rows),
 // tw = output columns per consumer thread (4 or 2)
 bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out);

@@ -78,15 +78,21 @@ constexpr int DWS_MAX_STAGES = 8;
 // CH = channels per consumer thread (4 or 2).  Every tap is read from shared memory once per input row and thread and
 // feeds TW * CH / 2 packed FMAs: the 5x5 kernel runs CH = 2, TW = 4 (8-byte tap loads, 4 FFMA2 each) because with
 // CH = 4, TW = 2 (16-byte tap loads, 4 FFMA2 each) the tap traffic alone oversubscribes the shared-memory pipe 2x.
-template <int KS, int TW, int CH, int ACT, int NT>
+//
+// POOL: the kernel also leaves the per-channel sums of its outputs for the squeeze-excitation that follows (SE pools the
+// depthwise output, mobilenetv3.py:22-40), saving that layer's read of the tensor.  Every CTA share of an image's rows
+// writes one slot pool[b][slot][c], slot = this CTA's index among the CTAs that touch image b (se_fc1_kernel derives
+// the slot count of an image from the same split), summed in a fixed order: deterministic, no atomics.
+template <int KS, int TW, int CH, int ACT, int NT, bool POOL>
 __global__ void __launch_bounds__(NT, NT <= 160 ? 3 : 1)
 dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w, const float* __restrict__ bias,
-                     uint32_t* __restrict__ y, DwStream sp, int B, int H, int W, int C) {
+                     uint32_t* __restrict__ y, DwStream sp, int B, int H, int W, int C, float* __restrict__ pool, int pool_stride) {
     constexpr int P = KS / 2, TWIN = TW + KS - 1, NP = CH / 2;
     extern __shared__ __align__(128) unsigned char dws_smem[];
     __shared__ uint64_t full[DWS_MAX_STAGES], empty[DWS_MAX_STAGES];
     unsigned char* stages = dws_smem;
     float* wsm = reinterpret_cast<float*>(dws_smem + (size_t)sp.nst * sp.stage_stride);     // [KS*KS][CB]
+    float* psm = wsm + KS * KS * sp.CB;                                                      // POOL: [ncb][CB]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_cons_warps = (blockDim.x >> 5) - 1;
@@ -149,6 +155,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
         const int c = i % sp.CB, t = i / sp.CB;
         wsm[((c / CH) * (KS * KS) + t) * CH + (c % CH)] = __ldg(w + t * C + cblk * sp.CB + c);
     }
+    __syncwarp();
     asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
     const uint32_t wq = dws_u32(wsm + q * (KS * KS) * CH);
     float2 bv[NP];
@@ -163,6 +170,9 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
         for (int p = 0; p < TW; ++p)
 #pragma unroll
             for (int h = 0; h < NP; ++h) acc[s2][p][h] = bv[h];
+    float2 ps[NP];                                  // POOL: this thread's output sums over the current image share
+#pragma unroll
+    for (int h = 0; h < NP; ++h) ps[h] = make_float2(0.f, 0.f);
     uint32_t seq = 0;
     for (long long g = g_begin; g < g_end;) {
         const int b = (int)(g / H), o0 = (int)(g - (long long)b * H);
@@ -225,8 +235,12 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                                 if (ow0 + p < W) {
                                     uint32_t v[NP];
 #pragma unroll
-                                    for (int h = 0; h < NP; ++h)
+                                    for (int h = 0; h < NP; ++h) {
                                         v[h] = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][h].x), dws_act<ACT>(acc[sl][p][h].y));
+                                        // the STORED (bf16) values are pooled, as a separate pass over y would: their fp32
+                                        // sums are (all but) exact, so the result does not depend on how the rows are shared
+                                        if (POOL) ps[h] = __fadd2_rn(ps[h], bf16x2_to_float2(v[h]));
+                                    }
                                     if (NP == 2) *reinterpret_cast<uint2*>(yrow + (long long)p * cw) = make_uint2(v[0], v[NP - 1]);
                                     else yrow[(long long)p * cw] = v[0];
                                 }
@@ -238,6 +252,28 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dws_u32(&empty[slot])) : "memory");
+        }
+        if (POOL) {
+            // column blocks -> channel sums of this share, in a fixed order
+            if (active) {
+#pragma unroll
+                for (int h = 0; h < NP; ++h) {
+                    *reinterpret_cast<float2*>(psm + cb * sp.CB + q * CH + 2 * h) = ps[h];
+                    ps[h] = make_float2(0.f, 0.f);
+                }
+            }
+            __syncwarp();                           // bar.sync is warp-aligned: rejoin the idle lanes first
+            asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
+            // first CTA share that holds a row of image b: smallest part whose end lies beyond row b * H
+            const long long first = (((long long)b * H + 1) * parts + T - 1) / T - 1;
+            float* dst = pool + ((long long)b * pool_stride + (part - first)) * C + cblk * sp.CB;
+            for (int c = ct; c < sp.CB; c += n_cons) {
+                float s = 0.f;
+                for (int j = 0; j < sp.ncb; ++j) s += psm[j * sp.CB + c];
+                dst[c] = s;
+            }
+            __syncwarp();
+            asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
         }
         g += o1 - o0;
     }
@@ -287,53 +323,76 @@ int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, in
     return dw_make_tmap(map, x, B, H, W, C, tl);
 }
 
-template <int KS, int ACT, int NT>
-static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
-                        int C, cudaStream_t stream) {
-    auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), dws_ch<KS>(), ACT, NT>;
+template <int KS, int ACT, int NT, bool POOL>
+static int dws_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, DwPool* pool, bool probe, cudaStream_t stream) {
+    auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), dws_ch<KS>(), ACT, NT, POOL>;
+    const size_t smem = sp.smem + (POOL ? (size_t)sp.ncb * sp.CB * sizeof(float) : 0);
     static size_t configured = 0;
-    if (sp.smem > configured) {
+    if (smem > configured) {
         DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
     int per_sm = 0;
-    DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, sp.smem));
+    DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;
     // a multiple of the channel-block count, at most one CTA per output row of a block
     long long parts = (long long)per_sm * sm_count() / sp.ncblk;
     if (parts < 1) parts = 1;
     if (parts > (long long)B * H) parts = (long long)B * H;
+    if (POOL) {
+        // CTA shares that can touch one image: every share holds at least floor(B * H / parts) rows
+        const long long rmin = (long long)B * H / parts;
+        const long long slots = (H + rmin - 1) / rmin + 1;
+        pool->parts = slots <= pool->max_slots ? (int)parts : 0;
+        pool->slots = (int)slots;
+        if (probe) return DN_OK;
+    }
     const long long grid = parts * sp.ncblk;
-    launch_pdl(kern, (unsigned)grid, sp.threads, sp.smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C);
+    launch_pdl(kern, (unsigned)grid, sp.threads, smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C,
+               POOL ? pool->partial : (float*)nullptr, POOL ? pool->slots : 0);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
 
+template <int KS, int ACT, int NT>
+static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, DwPool* pool, cudaStream_t stream) {
+    if (pool && pool->partial) {
+        // the pooled variant has its own occupancy: see whether its split keeps the slots of an image within bounds
+        int rc = dws_launch_p<KS, ACT, NT, true>(tm, sp, w, bias, y, B, H, W, C, pool, true, stream);
+        if (rc) return rc;
+        if (pool->parts > 0) return dws_launch_p<KS, ACT, NT, true>(tm, sp, w, bias, y, B, H, W, C, pool, false, stream);
+    }
+    if (pool) pool->parts = 0;
+    return dws_launch_p<KS, ACT, NT, false>(tm, sp, w, bias, y, B, H, W, C, nullptr, false, stream);
+}
+
 template <int KS, int ACT>
 static int dws_launch_a(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
-                        int C, cudaStream_t stream) {
+                        int C, DwPool* pool, cudaStream_t stream) {
     // small CTAs (<= 4 consumer warps) are compiled for three per SM; wide rows with few channels need up to 8
-    if (sp.threads <= 160) return dws_launch_n<KS, ACT, 160>(tm, sp, w, bias, y, B, H, W, C, stream);
-    return dws_launch_n<KS, ACT, DWS_MAX_THREADS>(tm, sp, w, bias, y, B, H, W, C, stream);
+    if (sp.threads <= 160) return dws_launch_n<KS, ACT, 160>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
+    return dws_launch_n<KS, ACT, DWS_MAX_THREADS>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
 }
 
 template <int KS>
 static int dws_launch_k(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
-                        int C, int act, cudaStream_t stream) {
+                        int C, int act, DwPool* pool, cudaStream_t stream) {
     switch (act) {
-        case DN_ACT_NONE: return dws_launch_a<KS, DN_ACT_NONE>(tm, sp, w, bias, y, B, H, W, C, stream);
-        case DN_ACT_RELU: return dws_launch_a<KS, DN_ACT_RELU>(tm, sp, w, bias, y, B, H, W, C, stream);
-        case DN_ACT_RELU6: return dws_launch_a<KS, DN_ACT_RELU6>(tm, sp, w, bias, y, B, H, W, C, stream);
-        case DN_ACT_HSWISH: return dws_launch_a<KS, DN_ACT_HSWISH>(tm, sp, w, bias, y, B, H, W, C, stream);
+        case DN_ACT_NONE: return dws_launch_a<KS, DN_ACT_NONE>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
+        case DN_ACT_RELU: return dws_launch_a<KS, DN_ACT_RELU>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
+        case DN_ACT_RELU6: return dws_launch_a<KS, DN_ACT_RELU6>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
+        case DN_ACT_HSWISH: return dws_launch_a<KS, DN_ACT_HSWISH>(tm, sp, w, bias, y, B, H, W, C, pool, stream);
     }
     DN_REQUIRE(false, DN_ERR_INVALID, "bad activation %d", act);
 }
 
 int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
-                         int W, int C, int k, int act, cudaStream_t stream) {
+                         int W, int C, int k, int act, cudaStream_t stream, DwPool* pool) {
     DN_REQUIRE((long long)sp.ncblk * B * H < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
-    if (k == 3) return dws_launch_k<3>(tm, sp, w, bias, y, B, H, W, C, act, stream);
-    return dws_launch_k<5>(tm, sp, w, bias, y, B, H, W, C, act, stream);
+    if (k == 3) return dws_launch_k<3>(tm, sp, w, bias, y, B, H, W, C, act, pool, stream);
+    return dws_launch_k<5>(tm, sp, w, bias, y, B, H, W, C, act, pool, stream);
 }
 
 }  // namespace dn

@@ -51,6 +51,8 @@ struct dn_engine {
     std::vector<CUtensorMap> tmap_dw;               // per op (DW only; PWDW: the input window map)
     std::vector<DwTiling> dw_tiling;
     std::vector<DwStream> dw_stream;
+    std::vector<DwPool> dw_pool;                    // per SE op: pooling done by the depthwise launch before it (parts > 0)
+    int n_se_pooled = 0;                            // ... how many of them in the forward enqueued last
     std::vector<char> dw_tma;                       // per op: 0 direct, 1 TMA tiles, 2 row stream, 3 stride-2 row stream
     std::vector<int> dw_tw;                         // per op: output columns per thread of the stride-2 stream
     bool dw_ready = false;
@@ -373,6 +375,16 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
     return DN_OK;
 }
 
+// DN_SE_POOL=0: squeeze-excitation layers pool with their own pass instead of taking the sums from the depthwise
+// row stream in front of them (measurement aid)
+static bool se_pool_fusion() {
+    static const bool on = [] {
+        const char* v = getenv("DN_SE_POOL");
+        return !(v && atoi(v) == 0);
+    }();
+    return on;
+}
+
 static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaStream_t s) {
     {
         const dn_op& o = e->ops[i];
@@ -385,9 +397,15 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 break;
             case DN_OP_DW:
                 if (e->dw_ready && e->dw_tma[i] == 2) {
+                    // a squeeze-excitation right behind: let the row stream leave its channel sums in the SE workspace
+                    DwPool pool{nullptr, se_max_pool_slots(), 0, 0};
+                    const bool se_next = i + 1 < e->ops.size() && e->ops[i + 1].kind == DN_OP_SE &&
+                                         e->ops[i + 1].in_buf == o.out_buf && e->ops[i + 1].lane == o.lane && se_pool_fusion();
+                    if (se_next) pool.partial = (float*)e->se_ws;
                     rc = dwconv_stream_launch(e->tmap_dw[i], e->dw_stream[i], (const float*)(W + o.w_off),
                                               (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
-                                              o.act, s);
+                                              o.act, s, se_next ? &pool : nullptr);
+                    if (se_next) e->dw_pool[i + 1] = pool;
                     break;
                 }
                 if (e->dw_ready && e->dw_tma[i] == 3) {
@@ -435,11 +453,14 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 break;
             case DN_OP_NOP:
                 break;
-            case DN_OP_SE:
-                rc = dn_se_inplace(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
-                                   (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
-                                   o.c_mid, e->se_ws, e->se_ws_bytes, s);
+            case DN_OP_SE: {
+                const DwPool& pool = e->dw_pool[i];      // parts > 0: the depthwise launch just before pooled for us
+                rc = se_inplace_pooled(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
+                                       (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
+                                       o.c_mid, e->se_ws, e->se_ws_bytes, pool.parts, pool.slots, o.h_in, s);
+                e->n_se_pooled += pool.parts > 0;
                 break;
+            }
         }
         return rc;
     }
@@ -451,6 +472,8 @@ static int enqueue_forward(dn_engine* e, const float* images, int B, float* out_
     // waits for the producers it reads from (op_done) and is joined again before the post-processing.  Under
     // stream capture the same event calls turn into parallel branches of the graph.
     std::vector<char> lane_used(e->n_lanes, 0);
+    e->n_se_pooled = 0;
+    e->dw_pool.assign(e->ops.size(), DwPool{nullptr, 0, 0, 0});
     if (e->n_lanes > 0) DN_CHECK_CUDA(cudaEventRecord(e->fork_ev, s));
     for (size_t i = 0; i < e->ops.size(); ++i) {
         const int lane = e->ops[i].lane;
@@ -685,13 +708,13 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
     return rc;
 }
 
-// layers (a squeeze-excitation is 4 launches) + softmax/decode + round thresholds + 3 rounds x (class sort, warp NMS,
-// CTA NMS, merge)
+// layers (a squeeze-excitation is 4 launches, 3 when the depthwise launch before it pooled) + softmax/decode + round
+// thresholds + 3 rounds x (class sort, warp NMS, CTA NMS, merge)
 extern "C" int dn_engine_launches_per_forward(dn_engine* e) {
     if (!e) return 0;
     int nop = 0;
     for (const auto& o : e->ops) nop += (o.kind == DN_OP_NOP);
-    return (int)e->ops.size() - nop + 3 * e->n_se + 14;
+    return (int)e->ops.size() - nop + 3 * e->n_se - e->n_se_pooled + 14;
 }
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) {
     return e ? e->device_bytes + (e->twin ? e->twin->device_bytes : 0) : 0;

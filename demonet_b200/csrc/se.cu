@@ -100,7 +100,7 @@ se_pool_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int HW,
 // independent weight loads to issue.  hidden: fp32 [groups][Cs][SE_GI].
 __global__ void __launch_bounds__(SE_FC_THREADS)
 se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, const float* __restrict__ b1,
-              float* __restrict__ hidden_g, int B, int HW, int C, int Cs, int chunks) {
+              float* __restrict__ hidden_g, int B, int HW, int C, int Cs, int chunks, int dw_parts, int dw_rows) {
     extern __shared__ __align__(16) float s_fc[];
     float* pooled = s_fc;                       // [SE_GI][C]
     pdl_trigger();
@@ -114,14 +114,24 @@ se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, c
     const int C4 = C >> 2;
     for (int i = tid; i < SE_GI * C4; i += SE_FC_THREADS) {
         const int g = i / C4, c4 = i - g * C4;
-        const float4* src = reinterpret_cast<const float4*>(partial + (long long)min(b0 + g, B - 1) * chunks * C) + c4;
+        const int b = min(b0 + g, B - 1);
+        const float4* src = reinterpret_cast<const float4*>(partial + (long long)b * chunks * C) + c4;
+        // sums left by the depthwise row stream (dw_parts > 0): `chunks` is the slot stride, the image holds one slot per
+        // CTA share that touched its rows [b * dw_rows, (b + 1) * dw_rows) of the B * dw_rows row stream
+        int nch = chunks;
+        if (dw_parts > 0) {
+            const long long T = (long long)B * dw_rows;
+            const long long first = (((long long)b * dw_rows + 1) * dw_parts + T - 1) / T - 1;
+            const long long last = (((long long)(b + 1) * dw_rows) * dw_parts + T - 1) / T - 1;
+            nch = (int)(last - first + 1);
+        }
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k0 = 0; k0 < SE_MAX_CHUNKS; k0 += 8) {
             float4 v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                v[k] = (k0 + k < chunks) ? __ldg(src + (long long)(k0 + k) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[k] = (k0 + k < nch) ? __ldg(src + (long long)(k0 + k) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) a.x += v[k].x, a.y += v[k].y, a.z += v[k].z, a.w += v[k].w;
         }
@@ -272,6 +282,18 @@ extern "C" size_t dn_se_workspace_bytes(int B, int HW, int C) {
 
 extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
                              int C, int Cs, void* workspace, size_t workspace_bytes, void* stream_) {
+    return dn::se_inplace_pooled(x, w1, b1, w2t, b2, B, HW, C, Cs, workspace, workspace_bytes, 0, 0, 0, (cudaStream_t)stream_);
+}
+
+namespace dn {
+
+int se_max_pool_slots() { return SE_MAX_CHUNKS; }
+
+// dw_parts > 0: the channel sums are already in the workspace, written by the depthwise row stream that produced x
+// (dwconv_stream.cu, POOL) as [B][dw_slots][C] over dw_parts CTA shares of a B * dw_rows row stream; the pooling pass is
+// skipped.
+int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW, int C, int Cs,
+                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s) {
     DN_REQUIRE(x && w1 && b1 && w2t && b2, DN_ERR_INVALID, "NULL tensor pointer");
     DN_REQUIRE(B > 0 && HW > 0 && C > 0 && Cs > 0, DN_ERR_INVALID, "bad shape");
     DN_REQUIRE(C % 8 == 0 && C / 8 <= SE_POOL_THREADS && C <= 2048, DN_ERR_UNSUPPORTED,
@@ -279,7 +301,7 @@ extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const fl
     DN_REQUIRE(workspace != nullptr && workspace_bytes >= dn_se_workspace_bytes(B, HW, C), DN_ERR_WORKSPACE,
                "SE workspace too small (%zu < %zu bytes)", workspace_bytes, dn_se_workspace_bytes(B, HW, C));
     DN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, DN_ERR_INVALID, "SE workspace must be 16-byte aligned");
-    cudaStream_t s = (cudaStream_t)stream_;
+    DN_REQUIRE(dw_parts == 0 || (dw_slots >= 1 && dw_slots <= SE_MAX_CHUNKS && dw_rows > 0), DN_ERR_INVALID, "bad pooled layout");
     const SePlan p = se_plan(B, HW, C);
     float* partial = (float*)workspace;
     float* scale = partial + (size_t)B * SE_MAX_CHUNKS * C;
@@ -295,11 +317,13 @@ extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const fl
         DN_CHECK_CUDA(cudaFuncSetAttribute(se_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         fc_configured = 160 * 1024;
     }
-    launch_pdl(se_pool_kernel, dim3(p.pool_chunks, B), SE_POOL_THREADS, pool_smem, s, (const uint4*)x, partial, HW, C, p.CV, p.rows,
-               p.pool_px);
-    DN_CHECK_LAUNCH();
+    if (dw_parts == 0) {
+        launch_pdl(se_pool_kernel, dim3(p.pool_chunks, B), SE_POOL_THREADS, pool_smem, s, (const uint4*)x, partial, HW, C, p.CV,
+                   p.rows, p.pool_px);
+        DN_CHECK_LAUNCH();
+    }
     launch_pdl(se_fc1_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc1_smem, s, (const float*)partial, w1, b1, hidden, B, HW, C, Cs,
-               p.pool_chunks);
+               dw_parts ? dw_slots : p.pool_chunks, dw_parts, dw_rows);
     DN_CHECK_LAUNCH();
     launch_pdl(se_fc2_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)hidden, w2t, b2, scale, B, C, Cs);
     DN_CHECK_LAUNCH();
@@ -308,3 +332,5 @@ extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const fl
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
+
+}  // namespace dn

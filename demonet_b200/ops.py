@@ -260,6 +260,27 @@ def se_inplace(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor) -> Te
     return x
 
 
+def dwconv_se(x: Tensor, w: Tensor, bias: Tensor, k: int, stride: int, act: str, w1: Tensor, b1: Tensor, w2t: Tensor,
+              b2: Tensor):
+    """Depthwise conv + squeeze-excitation of its output (the middle of an InvertedResidual with use_se,
+    mobilenetv3.py:43-96).  Returns (y bf16 [B,Ho,Wo,C], pooled): pooled tells whether the depthwise launch produced the
+    SE channel sums itself (stride-1 row stream, large batch) or the SE ran its own pooling pass."""
+    _require_cuda(x, w, bias, w1, b1, w2t, b2)
+    B, H, W, C = x.shape
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
+    ws_bytes = _C.lib().dn_se_workspace_bytes(B, Ho * Wo, C)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    pooled = ctypes.c_int(0)
+    with torch.cuda.device(x.device):
+        _C.check(_C.lib().dn_dwconv_se(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(),
+                                       y.data_ptr(), B, H, W, C, k, stride, _C.ACT[act], w1.contiguous().data_ptr(),
+                                       b1.contiguous().data_ptr(), w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(),
+                                       w1.shape[0], ws.data_ptr(), ws_bytes, ctypes.byref(pooled), _stream(x)))
+    return y, bool(pooled.value)
+
+
 # ---- detection sink (SURVEY 8(f2)) ---------------------------------------------------------------
 def detections_to_coco(boxes: Tensor, scores: Tensor, labels: Tensor, counts: Tensor, image_ids) -> Dict[str, Tensor]:
     """Padded detections (boxes [B,D,4] xyxy, scores [B,D], labels [B,D], counts [B], as written by the engine) ->

@@ -97,6 +97,16 @@ size_t dn_se_workspace_bytes(int B, int HW, int C);
 int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
                   int C, int Cs, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Depthwise convolution (dn_dwconv) followed by the squeeze-excitation of its output (dn_se_inplace), the pair an
+ * InvertedResidual with use_se runs between its expand and project convolutions (mobilenetv3.py:43-96).  When the
+ * layer runs on the stride-1 row-stream kernel and the batch is large enough for every image to be covered by at most
+ * 16 CTA shares, the depthwise launch leaves the SE channel sums in the workspace and the SE pooling pass over y is
+ * skipped (*pooled_out = 1, may be NULL); otherwise the two calls above run back to back.  Arguments as for
+ * dn_dwconv and dn_se_inplace; workspace of dn_se_workspace_bytes(B, Ho * Wo, C) bytes. */
+int dn_dwconv_se(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
+                 int stride, int act, const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2,
+                 int Cs, void* workspace, size_t workspace_bytes, int* pooled_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Transforms either side of the path (GeneralizedRCNNTransform, demonet/models/transform.py)
  * ---------------------------------------------------------------------------------------- */

@@ -157,6 +157,48 @@ def test_se(C, Cs, HW):
     _close_bf16(y, ref, extra_abs=2e-3)
 
 
+@pytest.mark.parametrize("B,H,W,C,Cs,k,act,want_pooled", [
+    (64, 40, 40, 120, 32, 5, "relu", True),            # V3 blocks 4-5 at batch size
+    (48, 20, 20, 480, 120, 3, "hardswish", True),      # block 10
+    (37, 20, 20, 672, 168, 3, "hardswish", True),      # block 11; CTA shares cut the images at irregular rows
+    (96, 24, 22, 40, 16, 3, "relu", True),             # width not a multiple of the 4-column thread tile
+    (3, 40, 40, 120, 32, 5, "relu", False),            # small batch: > 16 shares per image, SE pools by itself
+    (16, 10, 10, 480, 120, 5, "hardswish", True),      # blocks 13-14
+    (16, 6, 6, 480, 120, 5, "hardswish", False),       # maps under 8 rows run on the direct kernel
+    (8, 40, 40, 240, 64, 3, "hardswish", False),       # stride 2 (below): no pooled variant
+])
+def test_dwconv_se_pooled_by_the_row_stream(B, H, W, C, Cs, k, act, want_pooled):
+    """dn_dwconv_se (depthwise + SE; the row stream leaves the SE channel sums) against the two separate calls and
+    against fp32 PyTorch.  The sums are taken before the bf16 rounding of the outputs and in another order, so the
+    scales agree to fp32 round-off, the scaled tensor to one bf16 ulp."""
+    stride = 2 if (C == 240) else 1
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16().cuda()
+    w = (torch.randn(C, k, k, generator=g) * 0.3).cuda()
+    b = torch.randn(C, generator=g).cuda() * 0.5
+    w1 = (torch.randn(Cs, C, generator=g) / C ** 0.5).cuda()
+    b1 = torch.randn(Cs, generator=g).cuda() * 0.5
+    w2 = (torch.randn(C, Cs, generator=g) / Cs ** 0.5).cuda()
+    b2 = torch.randn(C, generator=g).cuda() * 0.5
+    wk = w.permute(1, 2, 0).reshape(k * k, C).contiguous()
+    w2t = w2.t().contiguous()
+    y, pooled = ops.dwconv_se(x, wk, b, k, stride, act, w1, b1, w2t, b2)
+    assert pooled == want_pooled
+    mid = ops.dwconv(x, wk, b, k, stride, act)
+    two = ops.se_inplace(mid.clone().view(B, -1, C), w1, b1, w2t, b2).view_as(mid)
+    assert y.shape == two.shape
+    d = (y.float() - two.float()).abs()
+    assert float((d / two.float().abs().clamp_min(1e-2)).max()) <= 2.0 ** -7, "more than one bf16 ulp from the unfused pair"
+    assert float((d > 0).float().mean()) < 0.02                      # and nearly all elements identical
+    conv = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), w[:, None], b, stride, (k - 1) // 2, 1, C))
+    scale = F.hardsigmoid(F.relu(conv.mean((2, 3)) @ w1.t() + b1) @ w2.t() + b2)
+    ref = (conv * scale[:, :, None, None]).permute(0, 2, 3, 1)
+    _close_bf16(y, ref, extra_abs=4e-3)
+    # deterministic: fixed summation order, no atomics
+    y2, _ = ops.dwconv_se(x, wk, b, k, stride, act, w1, b1, w2t, b2)
+    assert torch.equal(y, y2)
+
+
 @pytest.mark.parametrize("B,H,W,act", [(3, 160, 160, "relu"), (2, 40, 40, "relu6"), (5, 50, 38, "hardswish"), (1, 17, 9, "relu"),
                                        (40, 32, 32, "relu")])
 def test_pwdw_fused_matches_two_kernels(B, H, W, act):
