@@ -261,8 +261,8 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
 }
 
 // Depthwise conv followed by squeeze-excitation of its output (InvertedResidual with use_se, mobilenetv3.py:43-96):
-// when the layer runs on the stride-1 row stream and the batch is large enough, the stream leaves the SE channel sums
-// in the workspace and the SE pooling pass is skipped (*pooled_out = 1); otherwise dn_dwconv + dn_se_inplace.
+// when the layer runs on a row-stream kernel (either stride) and the batch is large enough, the stream leaves the SE
+// channel sums in the workspace and the SE pooling pass is skipped (*pooled_out = 1); otherwise dn_dwconv + dn_se_inplace.
 extern "C" int dn_dwconv_se(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
                             int stride, int act, const float* se_w1, const float* se_b1, const float* se_w2t,
                             const float* se_b2, int Cs, void* workspace, size_t workspace_bytes, int* pooled_out,
@@ -288,7 +288,21 @@ extern "C" int dn_dwconv_se(const void* x, const float* w, const float* bias, vo
         if (rc) return rc;
         if (pooled_out) *pooled_out = pool.parts > 0;
         return se_inplace_pooled(y, se_w1, se_b1, se_w2t, se_b2, B, Ho * Wo, C, Cs, workspace, workspace_bytes, pool.parts,
-                                 pool.slots, H, s);
+                                 pool.slots, Ho, s);
+    }
+    if (C % 8 == 0 && dw_choose(H, W, C, k, stride) == DW_STREAM2) {
+        DwStream sp;
+        int tw = 0;
+        DN_REQUIRE(dw_stream2_plan(H, W, C, k, &sp, &tw), DN_ERR_UNSUPPORTED, "no stride-2 stream plan");
+        CUtensorMap tm;
+        int rc = dw_stream2_make_tmap(&tm, x, B, H, W, C, k, sp);
+        if (rc) return rc;
+        DwPool pool{(float*)workspace, se_max_pool_slots(), 0, 0};
+        rc = dwconv_stream2_launch(tm, sp, tw, w, bias, y, B, H, W, C, k, act, s, &pool);
+        if (rc) return rc;
+        if (pooled_out) *pooled_out = pool.parts > 0;
+        return se_inplace_pooled(y, se_w1, se_b1, se_w2t, se_b2, B, Ho * Wo, C, Cs, workspace, workspace_bytes, pool.parts,
+                                 pool.slots, Ho, s);
     }
     int rc = dn_dwconv(x, w, bias, y, B, H, W, C, k, stride, act, stream_);
     if (rc) return rc;

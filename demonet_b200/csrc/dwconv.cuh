@@ -50,7 +50,7 @@ int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float*
 bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out);
 int dw_stream2_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
 int dwconv_stream2_launch(const CUtensorMap& tm, const DwStream& sp, int tw, const float* w, const float* bias, void* y, int B,
-                          int H, int W, int C, int k, int act, cudaStream_t stream);
+                          int H, int W, int C, int k, int act, cudaStream_t stream, DwPool* pool = nullptr);
 // which depthwise kernel a layer shape runs on
 enum DwImpl { DW_DIRECT = 1, DW_TMA = 2, DW_STREAM = 4, DW_STREAM2 = 8 };
 DwImpl dw_choose(int H, int W, int C, int k, int stride);

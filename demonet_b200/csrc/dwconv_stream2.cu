@@ -49,15 +49,19 @@ __device__ __forceinline__ uint32_t dw2_lds32(uint32_t addr) {
 constexpr int DW2_MAX_STAGES = 8;
 constexpr int DW2_THREADS = 160;            // producer warp + four consumer warps, three CTAs per SM
 
-template <int KS, int TW, int ACT>
+// POOL: per-share channel sums of the stored outputs for the squeeze-excitation behind this layer, exactly as in the
+// stride-1 stream (dwconv_stream.cu): pool[b][slot][c], slot = index of this CTA among the shares of image b.
+template <int KS, int TW, int ACT, bool POOL>
 __global__ void __launch_bounds__(DW2_THREADS, 3)
 dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w, const float* __restrict__ bias,
-                      uint32_t* __restrict__ y, DwStream sp, int B, int H, int W, int C, int Ho, int Wo) {
+                      uint32_t* __restrict__ y, DwStream sp, int B, int H, int W, int C, int Ho, int Wo,
+                      float* __restrict__ pool, int pool_stride) {
     constexpr int P = KS / 2, R = (KS + 1) / 2, G = 2 * R, TWIN = 2 * TW + KS - 2;
     extern __shared__ __align__(128) unsigned char dw2_smem[];
     __shared__ uint64_t full[DW2_MAX_STAGES], empty[DW2_MAX_STAGES];
     unsigned char* stages = dw2_smem;
     float* wsm = reinterpret_cast<float*>(dw2_smem + (size_t)sp.nst * sp.stage_stride);     // [CB/2][KS*KS][2]
+    float* psm = wsm + KS * KS * sp.CB;                                                      // POOL: [ncb][CB]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_cons_warps = (blockDim.x >> 5) - 1;
@@ -119,6 +123,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
         const int c = i % sp.CB, t = i / sp.CB;
         wsm[((c >> 1) * (KS * KS) + t) * 2 + (c & 1)] = __ldg(w + t * C + cblk * sp.CB + c);
     }
+    __syncwarp();
     asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
     const uint32_t wq = dw2_u32(wsm + q * (KS * KS) * 2);
     const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + cblk * sp.CB + (active ? q : 0) * 2));
@@ -129,6 +134,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     for (int s2 = 0; s2 < R; ++s2)
 #pragma unroll
         for (int p = 0; p < TW; ++p) acc[s2][p] = bv;
+    float2 ps = make_float2(0.f, 0.f);              // POOL: this thread's output sums over the current image share
     uint32_t seq = 0;
     for (long long g = g_begin; g < g_end;) {
         const int b = (int)(g / Ho), o0 = (int)(g - (long long)b * Ho);
@@ -187,9 +193,11 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
                                 uint32_t* yrow = ybase + (long long)jc * Wo * cw;
 #pragma unroll
                                 for (int p = 0; p < TW; ++p)
-                                    if (ow0 + p < Wo)
-                                        yrow[(long long)p * cw] =
-                                            float2_to_bf16x2(dw2_act<ACT>(acc[sl][p].x), dw2_act<ACT>(acc[sl][p].y));
+                                    if (ow0 + p < Wo) {
+                                        const uint32_t v = float2_to_bf16x2(dw2_act<ACT>(acc[sl][p].x), dw2_act<ACT>(acc[sl][p].y));
+                                        yrow[(long long)p * cw] = v;
+                                        if (POOL) ps = __fadd2_rn(ps, bf16x2_to_float2(v));      // the stored values
+                                    }
                             }
                         }
                     }
@@ -197,6 +205,23 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
             }
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(dw2_u32(&empty[slot])) : "memory");
+        }
+        if (POOL) {
+            if (active) {
+                *reinterpret_cast<float2*>(psm + cb * sp.CB + q * 2) = ps;
+                ps = make_float2(0.f, 0.f);
+            }
+            __syncwarp();                           // bar.sync is warp-aligned: rejoin the idle lanes first
+            asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
+            const long long first = (((long long)b * Ho + 1) * parts + T - 1) / T - 1;       // first share with a row of image b
+            float* dst = pool + ((long long)b * pool_stride + (part - first)) * C + cblk * sp.CB;
+            for (int c = ct; c < sp.CB; c += n_cons) {
+                float s = 0.f;
+                for (int j = 0; j < sp.ncb; ++j) s += psm[j * sp.CB + c];
+                dst[c] = s;
+            }
+            __syncwarp();
+            asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
         }
         g += o1 - o0;
     }
@@ -242,48 +267,70 @@ int dw_stream2_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, i
     return dw_make_tmap(map, x, B, H, W, C, tl);
 }
 
-template <int KS, int TW, int ACT>
-static int dw2_launch_t(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
-                        int C, int Ho, int Wo, cudaStream_t stream) {
-    auto kern = dwconv_stream2_kernel<KS, TW, ACT>;
+template <int KS, int TW, int ACT, bool POOL>
+static int dw2_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, int Ho, int Wo, DwPool* pool, bool probe, cudaStream_t stream) {
+    auto kern = dwconv_stream2_kernel<KS, TW, ACT, POOL>;
+    const size_t smem = sp.smem + (POOL ? (size_t)sp.ncb * sp.CB * sizeof(float) : 0);
     static bool configured = false;
     if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 76 * 1024));
         configured = true;
     }
     int per_sm = 0;
-    DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, sp.smem));
+    DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;
     long long parts = (long long)per_sm * sm_count() / sp.ncblk;
     if (parts < 1) parts = 1;
     if (parts > (long long)B * Ho) parts = (long long)B * Ho;
+    if (POOL) {
+        // CTA shares that can touch one image: every share holds at least floor(B * Ho / parts) rows
+        const long long rmin = (long long)B * Ho / parts;
+        const long long slots = (Ho + rmin - 1) / rmin + 1;
+        pool->parts = slots <= pool->max_slots ? (int)parts : 0;
+        pool->slots = (int)slots;
+        if (probe) return DN_OK;
+    }
     const long long grid = parts * sp.ncblk;
-    launch_pdl(kern, (unsigned)grid, sp.threads, sp.smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C, Ho, Wo);
+    launch_pdl(kern, (unsigned)grid, sp.threads, smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C, Ho, Wo,
+               POOL ? pool->partial : (float*)nullptr, POOL ? pool->slots : 0);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
 
+template <int KS, int TW, int ACT>
+static int dw2_launch_t(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
+                        int C, int Ho, int Wo, DwPool* pool, cudaStream_t stream) {
+    if (pool && pool->partial) {
+        int rc = dw2_launch_p<KS, TW, ACT, true>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, true, stream);
+        if (rc) return rc;
+        if (pool->parts > 0) return dw2_launch_p<KS, TW, ACT, true>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, false, stream);
+    }
+    if (pool) pool->parts = 0;
+    return dw2_launch_p<KS, TW, ACT, false>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, nullptr, false, stream);
+}
+
 template <int KS, int TW>
 static int dw2_launch_a(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
-                        int C, int Ho, int Wo, int act, cudaStream_t stream) {
+                        int C, int Ho, int Wo, int act, DwPool* pool, cudaStream_t stream) {
     switch (act) {
-        case DN_ACT_NONE: return dw2_launch_t<KS, TW, DN_ACT_NONE>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, stream);
-        case DN_ACT_RELU: return dw2_launch_t<KS, TW, DN_ACT_RELU>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, stream);
-        case DN_ACT_RELU6: return dw2_launch_t<KS, TW, DN_ACT_RELU6>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, stream);
-        case DN_ACT_HSWISH: return dw2_launch_t<KS, TW, DN_ACT_HSWISH>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, stream);
+        case DN_ACT_NONE: return dw2_launch_t<KS, TW, DN_ACT_NONE>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, stream);
+        case DN_ACT_RELU: return dw2_launch_t<KS, TW, DN_ACT_RELU>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, stream);
+        case DN_ACT_RELU6: return dw2_launch_t<KS, TW, DN_ACT_RELU6>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, stream);
+        case DN_ACT_HSWISH: return dw2_launch_t<KS, TW, DN_ACT_HSWISH>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, stream);
     }
     DN_REQUIRE(false, DN_ERR_INVALID, "bad activation %d", act);
 }
 
 int dwconv_stream2_launch(const CUtensorMap& tm, const DwStream& sp, int tw, const float* w, const float* bias, void* y, int B,
-                          int H, int W, int C, int k, int act, cudaStream_t stream) {
+                          int H, int W, int C, int k, int act, cudaStream_t stream, DwPool* pool) {
     const int P = k / 2;
     const int Ho = (H + 2 * P - k) / 2 + 1, Wo = (W + 2 * P - k) / 2 + 1;
     DN_REQUIRE((long long)sp.ncblk * B * Ho < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
-    if (k == 3) return tw == 4 ? dw2_launch_a<3, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, stream)
-                               : dw2_launch_a<3, 2>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, stream);
-    return tw == 4 ? dw2_launch_a<5, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, stream)
-                   : dw2_launch_a<5, 2>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, stream);
+    if (k == 3) return tw == 4 ? dw2_launch_a<3, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream)
+                               : dw2_launch_a<3, 2>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream);
+    return tw == 4 ? dw2_launch_a<5, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream)
+                   : dw2_launch_a<5, 2>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream);
 }
 
 }  // namespace dn

@@ -376,13 +376,13 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
 }
 
 // DN_SE_POOL=0: squeeze-excitation layers pool with their own pass instead of taking the sums from the depthwise
-// row stream in front of them (measurement aid)
-static bool se_pool_fusion() {
-    static const bool on = [] {
+// row stream in front of them; 1: only the stride-1 streams pool (measurement aids)
+static int se_pool_fusion() {
+    static const int mode = [] {
         const char* v = getenv("DN_SE_POOL");
-        return !(v && atoi(v) == 0);
+        return v ? atoi(v) : 2;
     }();
-    return on;
+    return mode;
 }
 
 static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaStream_t s) {
@@ -396,22 +396,22 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                                   e->desc.image_std, buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_out, o.act, s);
                 break;
             case DN_OP_DW:
-                if (e->dw_ready && e->dw_tma[i] == 2) {
+                if (e->dw_ready && (e->dw_tma[i] == 2 || e->dw_tma[i] == 3)) {
                     // a squeeze-excitation right behind: let the row stream leave its channel sums in the SE workspace
                     DwPool pool{nullptr, se_max_pool_slots(), 0, 0};
                     const bool se_next = i + 1 < e->ops.size() && e->ops[i + 1].kind == DN_OP_SE &&
-                                         e->ops[i + 1].in_buf == o.out_buf && e->ops[i + 1].lane == o.lane && se_pool_fusion();
+                                         e->ops[i + 1].in_buf == o.out_buf && e->ops[i + 1].lane == o.lane &&
+                                         se_pool_fusion() >= (e->dw_tma[i] == 2 ? 1 : 2);
                     if (se_next) pool.partial = (float*)e->se_ws;
-                    rc = dwconv_stream_launch(e->tmap_dw[i], e->dw_stream[i], (const float*)(W + o.w_off),
-                                              (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
-                                              o.act, s, se_next ? &pool : nullptr);
+                    if (e->dw_tma[i] == 2)
+                        rc = dwconv_stream_launch(e->tmap_dw[i], e->dw_stream[i], (const float*)(W + o.w_off),
+                                                  (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in,
+                                                  o.ksize, o.act, s, se_next ? &pool : nullptr);
+                    else
+                        rc = dwconv_stream2_launch(e->tmap_dw[i], e->dw_stream[i], e->dw_tw[i], (const float*)(W + o.w_off),
+                                                   (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in,
+                                                   o.ksize, o.act, s, se_next ? &pool : nullptr);
                     if (se_next) e->dw_pool[i + 1] = pool;
-                    break;
-                }
-                if (e->dw_ready && e->dw_tma[i] == 3) {
-                    rc = dwconv_stream2_launch(e->tmap_dw[i], e->dw_stream[i], e->dw_tw[i], (const float*)(W + o.w_off),
-                                               (const float*)(W + o.b_off), buf_ptr(e, o.out_buf), B, o.h_in, o.w_in, o.c_in, o.ksize,
-                                               o.act, s);
                     break;
                 }
                 if (e->dw_ready && e->dw_tma[i] == 1) {

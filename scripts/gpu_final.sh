@@ -10,4 +10,4 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 600 python scripts/bench_configs.py --config 4 > gpurun_out/config4.json 2> gpurun_out/config4.err; echo "== config4 exit=$? $(cut -c1-200 gpurun_out/config4.json)"
 timeout 900 python scripts/bench_configs.py --config 5 > gpurun_out/config5.json 2> gpurun_out/config5.err; echo "== config5 exit=$? $(cut -c1-200 gpurun_out/config5.json)"
 timeout 600 python scripts/layers_config5.py 512 > gpurun_out/layers_c5.txt 2>&1
-bash scripts/gpu_launchlist.sh 126
+bash scripts/gpu_launchlist.sh 118

@@ -157,21 +157,24 @@ def test_se(C, Cs, HW):
     _close_bf16(y, ref, extra_abs=2e-3)
 
 
-@pytest.mark.parametrize("B,H,W,C,Cs,k,act,want_pooled", [
-    (64, 40, 40, 120, 32, 5, "relu", True),            # V3 blocks 4-5 at batch size
-    (48, 20, 20, 480, 120, 3, "hardswish", True),      # block 10
-    (37, 20, 20, 672, 168, 3, "hardswish", True),      # block 11; CTA shares cut the images at irregular rows
-    (96, 24, 22, 40, 16, 3, "relu", True),             # width not a multiple of the 4-column thread tile
-    (3, 40, 40, 120, 32, 5, "relu", False),            # small batch: > 16 shares per image, SE pools by itself
-    (16, 10, 10, 480, 120, 5, "hardswish", True),      # blocks 13-14
-    (16, 6, 6, 480, 120, 5, "hardswish", False),       # maps under 8 rows run on the direct kernel
-    (8, 40, 40, 240, 64, 3, "hardswish", False),       # stride 2 (below): no pooled variant
+@pytest.mark.parametrize("B,H,W,C,Cs,k,stride,act,want_pooled", [
+    (64, 40, 40, 120, 32, 5, 1, "relu", True),            # V3 blocks 4-5 at batch size
+    (48, 20, 20, 480, 120, 3, 1, "hardswish", True),      # block 10
+    (37, 20, 20, 672, 168, 3, 1, "hardswish", True),      # block 11; CTA shares cut the images at irregular rows
+    (96, 24, 22, 40, 16, 3, 1, "relu", True),             # width not a multiple of the 4-column thread tile
+    (16, 10, 10, 480, 120, 5, 1, "hardswish", True),      # blocks 13-14
+    (2, 10, 10, 480, 120, 5, 1, "hardswish", True),       # one row per CTA share, ten shares per image
+    (32, 80, 80, 72, 24, 5, 2, "relu", True),             # block 3 (stride-2 row stream)
+    (48, 20, 20, 672, 168, 5, 2, "hardswish", True),      # block 12 (stride-2 row stream, 2 columns per thread)
+    (61, 40, 40, 240, 64, 3, 2, "hardswish", True),       # stride 2, k 3, odd batch
+    (3, 40, 40, 120, 32, 5, 1, "relu", False),            # small batch: > 16 shares per image, SE pools by itself
+    (8, 40, 40, 240, 64, 3, 2, "hardswish", False),       # the same on the stride-2 stream
+    (16, 6, 6, 480, 120, 5, 1, "hardswish", False),       # maps under 8 rows run on the direct kernel
 ])
-def test_dwconv_se_pooled_by_the_row_stream(B, H, W, C, Cs, k, act, want_pooled):
-    """dn_dwconv_se (depthwise + SE; the row stream leaves the SE channel sums) against the two separate calls and
-    against fp32 PyTorch.  The sums are taken before the bf16 rounding of the outputs and in another order, so the
-    scales agree to fp32 round-off, the scaled tensor to one bf16 ulp."""
-    stride = 2 if (C == 240) else 1
+def test_dwconv_se_pooled_by_the_row_stream(B, H, W, C, Cs, k, stride, act, want_pooled):
+    """dn_dwconv_se (depthwise + SE; the row stream leaves the SE channel sums of the values it stores) against the two
+    separate calls and against fp32 PyTorch.  Only the order of the fp32 summation differs from the separate pooling
+    pass, and sums of bf16 values are all but exact in fp32: the two results agree bit for bit nearly everywhere."""
     g = torch.Generator().manual_seed(B * 1000 + C)
     x = torch.randn(B, H, W, C, generator=g).bfloat16().cuda()
     w = (torch.randn(C, k, k, generator=g) * 0.3).cuda()
@@ -189,7 +192,7 @@ def test_dwconv_se_pooled_by_the_row_stream(B, H, W, C, Cs, k, act, want_pooled)
     assert y.shape == two.shape
     d = (y.float() - two.float()).abs()
     assert float((d / two.float().abs().clamp_min(1e-2)).max()) <= 2.0 ** -7, "more than one bf16 ulp from the unfused pair"
-    assert float((d > 0).float().mean()) < 0.02                      # and nearly all elements identical
+    assert float((d > 0).float().mean()) < 1e-3                      # and nearly all elements identical
     conv = ACTS[act](F.conv2d(x.float().permute(0, 3, 1, 2), w[:, None], b, stride, (k - 1) // 2, 1, C))
     scale = F.hardsigmoid(F.relu(conv.mean((2, 3)) @ w1.t() + b1) @ w2.t() + b2)
     ref = (conv * scale[:, :, None, None]).permute(0, 2, 3, 1)
