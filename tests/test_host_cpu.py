@@ -206,3 +206,27 @@ def test_custom_ops_are_registered_with_fake_kernels():
         keep = torch.ops.demonet_b200.batched_nms(torch.empty(10, 4, device="cuda"), torch.empty(10, device="cuda"),
                                                   torch.empty(10, dtype=torch.int64, device="cuda"), 0.5)
         assert keep.dtype == torch.int64 and keep.dim() == 1          # data-dependent length
+
+
+def test_se_pool_slot_arithmetic():
+    """The integer arithmetic shared by the pooling depthwise row streams (dwconv_stream*.cu, POOL: slot = share index -
+    first share of the image), se_fc1_kernel (slots per image) and the launchers (slot bound): restated here and checked
+    by brute force over random (batch, rows per image, CTA shares) -- every image's shares are contiguous, the formulas
+    name the first and the last one, and their number never exceeds the bound the launcher sizes the workspace by."""
+    import random
+    rnd = random.Random(0)
+    for _ in range(3000):
+        B, H, parts = rnd.randint(1, 300), rnd.randint(1, 80), rnd.randint(1, 600)
+        T = B * H
+        parts = min(parts, T)
+        owner = [None] * T
+        for p in range(parts):
+            for r in range(T * p // parts, T * (p + 1) // parts):
+                owner[r] = p
+        rmin = T // parts
+        bound = (H + rmin - 1) // rmin + 1
+        for b in range(B):
+            first = ((b * H + 1) * parts + T - 1) // T - 1
+            last = ((b + 1) * H * parts + T - 1) // T - 1
+            assert first == owner[b * H] and last == owner[(b + 1) * H - 1]
+            assert last - first + 1 <= bound
