@@ -130,3 +130,28 @@ def test_decode_matches_torch_port():
     b = boxes_np.decode_single(big, anchors[:1])
     w = anchors[0, 2] - anchors[0, 0]
     assert abs((b[0, 2] - b[0, 0]) - np.float32(1000.0 / 16) * w) < 1e-2
+
+
+@pytest.mark.parametrize("n,classes,thr,seed", [(1, 1, 0.5, 0), (2, 1, 0.0, 1), (50, 3, 0.5, 2), (400, 7, 0.3, 3), (1200, 90, 0.55, 4),
+                                                (600, 2, 0.9, 5), (300, 1, 0.5, 6)])
+def test_nms_numpy_and_c_restatements_agree(n, classes, thr, seed):
+    """The two CPU restatements of torchvision's NMS (the NumPy one follows the reference call sites step by step, the C
+    one is what the GPU parity tests and the bench baseline run) on random boxes with heavy overlap, duplicated boxes and
+    tied scores -- the cases where an ordering or a >= / > slip would show."""
+    rng = np.random.default_rng(seed)
+    ctr = rng.uniform(0, 100, size=(n, 2)).astype(np.float32)
+    wh = rng.uniform(5, 60, size=(n, 2)).astype(np.float32)
+    boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], 1).astype(np.float32)
+    scores = rng.uniform(0, 1, size=n).astype(np.float32)
+    if n >= 50:
+        boxes[n // 2:n // 2 + 10] = boxes[:10]                   # exact duplicates (IoU = 1)
+        scores[n // 3:n // 3 + 20] = scores[0]                   # a run of tied scores
+        boxes[-3:] = [[10, 10, 10, 30], [5, 5, 5, 5], [0, 0, 50, 0]]    # zero-area boxes
+    idxs = rng.integers(0, classes, size=n).astype(np.int64)
+    assert np.array_equal(boxes_np.nms(boxes, scores, thr), nms_c.nms(boxes, scores, thr))
+    keep_np = boxes_np.batched_nms_vanilla(boxes, scores, idxs, thr)
+    assert np.array_equal(keep_np, nms_c.batched_nms(boxes, scores, idxs, thr))
+    # per-class NMS never suppresses across classes: running each class alone keeps the same set
+    alone = np.concatenate([np.flatnonzero(idxs == c)[boxes_np.nms(boxes[idxs == c], scores[idxs == c], thr)]
+                            for c in range(classes)] or [np.zeros(0, np.int64)])
+    assert sorted(alone.tolist()) == sorted(keep_np.tolist())
