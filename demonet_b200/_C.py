@@ -6,9 +6,15 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdemonet_b200.so")
+# One library per activation storage type (csrc/build.sh).  fp16 is the default: same bytes and tensor-core rate as
+# bf16, 6.6x closer to the fp32 reference end to end (DESIGN.md "Numerics"); DN_ACT_DTYPE=bf16 or the `act_dtype`
+# argument of the model builders selects the bfloat16 build.
+ACT_DTYPES = ("fp16", "bf16")
+DEFAULT_ACT_DTYPE = os.environ.get("DN_ACT_DTYPE", "fp16")
+LIB_PATHS = {dt: os.path.join(_HERE, "lib", "libdemonet_b200_%s.so" % dt) for dt in ACT_DTYPES}
+LIB_PATH = LIB_PATHS["fp16"]
 
-ABI_VERSION = 2          # include/demonet_b200.h DN_ABI_VERSION
+ABI_VERSION = 3          # include/demonet_b200.h DN_ABI_VERSION
 DN_OK = 0
 DN_ERR_INVALID = -1
 DN_ERR_CUDA = -2
@@ -42,6 +48,12 @@ class Buf(ctypes.Structure):
     _fields_ = [("elems_per_image", c_int64), ("elem_bytes", c_int32), ("reserved", c_int32)]
 
 
+class EngineStats(ctypes.Structure):
+    _fields_ = [("launches_per_forward", c_int32), ("fused_pwdw", c_int32), ("fused_dwpw", c_int32),
+                ("se_layers", c_int32), ("se_pooled", c_int32), ("pipeline_slots", c_int32), ("last_slot", c_int32),
+                ("act_dtype", c_int32), ("forwards", c_int64), ("graph_replays", c_int64)]
+
+
 class ModelDesc(ctypes.Structure):
     _fields_ = [("image_h", c_int32), ("image_w", c_int32), ("image_mean", c_float * 3), ("image_std", c_float * 3),
                 ("n_ops", c_int32), ("n_bufs", c_int32), ("ops_host", ctypes.POINTER(Op)),
@@ -70,6 +82,8 @@ _SIGNATURES = {
     "dn_postprocess_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(PostprocessParams)]),
     "dn_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p, c_size_t,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dn_postprocess_scored": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p, c_size_t,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dn_postprocess_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(PostprocessParams), c_void_p,
                                        c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_float),
                                        c_void_p]),
@@ -93,37 +107,58 @@ _SIGNATURES = {
     "dn_engine_copy_buffer": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "dn_engine_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_float), c_void_p]),
     "dn_engine_launches_per_forward": (c_int, [c_void_p]),
+    "dn_engine_get_stats": (c_int, [c_void_p, ctypes.POINTER(EngineStats)]),
     "dn_engine_device_bytes": (c_size_t, [c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    """Load the shared library (once). Raises if it has not been built -- there is no CPU path."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def torch_dtype(act_dtype=None):
+    import torch
+    return {"fp16": torch.float16, "bf16": torch.bfloat16}[act_dtype or DEFAULT_ACT_DTYPE]
+
+
+def dtype_name(torch_dt):
+    """"fp16" / "bf16" for a torch activation dtype (the stage-level wrappers in ops.py pick the library by it)."""
+    import torch
+    if torch_dt == torch.float16:
+        return "fp16"
+    if torch_dt == torch.bfloat16:
+        return "bf16"
+    raise TypeError("activations must be float16 or bfloat16, got %s" % torch_dt)
+
+
+def lib(act_dtype=None):
+    """Load the shared library of one activation storage type (once).  Raises if it has not been built -- there is
+    no CPU path."""
+    dt = act_dtype or DEFAULT_ACT_DTYPE
+    if dt not in LIB_PATHS:
+        raise ValueError("act_dtype must be one of %s, got %r" % (ACT_DTYPES, dt))
+    if dt not in _libs:
+        path = LIB_PATHS[dt]
+        if not os.path.exists(path):
             raise RuntimeError(
                 "demonet_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(or demonet_b200/csrc/build.sh); there is no CPU or PyTorch fallback." % LIB_PATH)
-        handle = ctypes.CDLL(LIB_PATH)
+                "(or demonet_b200/csrc/build.sh); there is no CPU or PyTorch fallback." % path)
+        handle = ctypes.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the ABI is incomplete
             fn.restype = res
             fn.argtypes = args
         if handle.dn_abi_version() != ABI_VERSION:
             raise RuntimeError("demonet_b200: ABI version mismatch (library %d, binding %d); rebuild with `python -c 'import __graft_entry__ as g; g.build()'`" % (handle.dn_abi_version(), ABI_VERSION))
-        _lib = handle
-    return _lib
+        _libs[dt] = handle
+    return _libs[dt]
 
 
-def check(rc):
-    """Map a dn_status to the exception type the reference would raise for the same mistake."""
+def check(rc, handle=None):
+    """Map a dn_status to the exception type the reference would raise for the same mistake.  `handle`: the library
+    the failing call went through (its thread-local message); default = the default-dtype library."""
     if rc == DN_OK:
         return
-    msg = lib().dn_last_error().decode("utf-8", "replace")
+    msg = (handle or lib()).dn_last_error().decode("utf-8", "replace")
     if rc == DN_ERR_INVALID:
         raise ValueError("demonet_b200: " + msg)
     if rc == DN_ERR_UNSUPPORTED:

@@ -1,12 +1,14 @@
 // Shared helpers for the demonet_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "../../include/demonet_b200.h"
 
@@ -52,16 +54,61 @@ int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2
         }                                                                                        \
     } while (0)
 
-inline int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+// ---- per-device launch state ------------------------------------------------------------------
+// One process may drive several GPUs (SSDLiteB200 keeps one engine per device), and both the SM count and the
+// opt-in dynamic shared-memory limit of a kernel are PER-DEVICE properties: everything cached here is keyed by
+// cudaGetDevice() and guarded by a mutex (engines of different devices may run on different host threads).
+constexpr int DN_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < DN_MAX_DEVICES) ? dev : 0;
 }
+
+inline int sm_count() {
+    static int n[DN_MAX_DEVICES] = {};
+    static std::mutex mu;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (n[dev] == 0) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
+    }
+    return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of one kernel (one `static SmemOptIn` per call site), raised on the
+// CURRENT device when a launch needs more than what that device was configured for.  `occupancy` caches one
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor answer per device for the call sites that size their grid by it.
+struct SmemOptIn {
+    size_t cfg[DN_MAX_DEVICES] = {};
+    int occupancy[DN_MAX_DEVICES] = {};
+    std::mutex mu;
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kern, size_t bytes, size_t set_to = 0) {
+        if (bytes <= 48 * 1024) return cudaSuccess;
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lock(mu);
+        if (bytes <= cfg[dev]) return cudaSuccess;
+        const size_t want = set_to > bytes ? set_to : bytes;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+        if (e == cudaSuccess) cfg[dev] = want;
+        return e;
+    }
+    template <typename Kernel>
+    cudaError_t blocks_per_sm(Kernel kern, int threads, size_t smem, int* out) {
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lock(mu);
+        if (occupancy[dev] == 0) {
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+            if (e != cudaSuccess) return e;
+            occupancy[dev] = n > 0 ? n : 1;
+        }
+        *out = occupancy[dev];
+        return cudaSuccess;
+    }
+};
 
 // ---- programmatic dependent launch ----------------------------------------------------------
 // Every kernel of the forward is launched with the programmatic-stream-serialization attribute and starts with
@@ -114,31 +161,91 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
-// ---- bf16 packing --------------------------------------------------------------------
-__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+// ---- 16-bit activation storage ----------------------------------------------------------
+// The library is built once per storage type (csrc/build.sh): DN_ACT_FP16=1 -> IEEE half (libdemonet_b200_fp16.so, the
+// default: same bytes and the same tcgen05 kind::f16 rate as bf16 with 3 more mantissa bits -- 6.6x lower end-to-end
+// error on this network, DESIGN.md "Numerics"), DN_ACT_FP16=0 -> bfloat16 (libdemonet_b200_bf16.so).  Stores saturate
+// to +-65504 in the fp16 build (F2FP.SATFINITE, one instruction either way) so that an outlier cannot turn into inf.
+#ifndef DN_ACT_FP16
+#define DN_ACT_FP16 1
+#endif
+#if DN_ACT_FP16
+typedef __half dn_half_t;
+typedef __half2 dn_half2_t;
+#define DN_ACT_DTYPE_ID 1
+#define DN_TMAP_HALF CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define DN_UMMA_AB_FORMAT 0u        // tcgen05 kind::f16 instruction descriptor, a_format / b_format: 0 = f16, 1 = bf16
+#else
+typedef __nv_bfloat16 dn_half_t;
+typedef __nv_bfloat162 dn_half2_t;
+#define DN_ACT_DTYPE_ID 0
+#define DN_TMAP_HALF CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define DN_UMMA_AB_FORMAT 1u
+#endif
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float2 h2_to_float2(uint32_t v) {
+#if DN_ACT_FP16
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+#else
     float2 r;
     r.x = __uint_as_float(v << 16);
     r.y = __uint_as_float(v & 0xffff0000u);
     return r;
+#endif
 }
-__device__ __forceinline__ uint32_t float2_to_bf16x2(float a, float b) {
+__device__ __forceinline__ uint32_t float2_to_h2(float a, float b) {
+#if DN_ACT_FP16
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+#else
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
+#endif
+}
+// the same pair as a typed value (for __hmax2 / __hmin2 on the packed result)
+__device__ __forceinline__ dn_half2_t floats_to_half2(float a, float b) {
+    const uint32_t r = float2_to_h2(a, b);
+    return *reinterpret_cast<const dn_half2_t*>(&r);
+}
+__device__ __forceinline__ dn_half2_t half2_const(float v) {
+#if DN_ACT_FP16
+    return __float2half2_rn(v);
+#else
+    return __float2bfloat162_rn(v);
+#endif
+}
+__device__ __forceinline__ float half_to_float(dn_half_t v) {
+#if DN_ACT_FP16
+    return __half2float(v);
+#else
+    return __bfloat162float(v);
+#endif
+}
+__device__ __forceinline__ dn_half_t float_to_half(float v) {
+#if DN_ACT_FP16
+    const uint32_t r = float2_to_h2(v, 0.f);
+    return *reinterpret_cast<const __half*>(&r);
+#else
+    return __float2bfloat16_rn(v);
+#endif
 }
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
     float2 t;
-    t = bf16x2_to_float2(v.x); f[0] = t.x; f[1] = t.y;
-    t = bf16x2_to_float2(v.y); f[2] = t.x; f[3] = t.y;
-    t = bf16x2_to_float2(v.z); f[4] = t.x; f[5] = t.y;
-    t = bf16x2_to_float2(v.w); f[6] = t.x; f[7] = t.y;
+    t = h2_to_float2(v.x); f[0] = t.x; f[1] = t.y;
+    t = h2_to_float2(v.y); f[2] = t.x; f[3] = t.y;
+    t = h2_to_float2(v.z); f[4] = t.x; f[5] = t.y;
+    t = h2_to_float2(v.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
     uint4 v;
-    v.x = float2_to_bf16x2(f[0], f[1]);
-    v.y = float2_to_bf16x2(f[2], f[3]);
-    v.z = float2_to_bf16x2(f[4], f[5]);
-    v.w = float2_to_bf16x2(f[6], f[7]);
+    v.x = float2_to_h2(f[0], f[1]);
+    v.y = float2_to_h2(f[2], f[3]);
+    v.z = float2_to_h2(f[4], f[5]);
+    v.w = float2_to_h2(f[6], f[7]);
     return v;
 }
+#endif  // __CUDACC__
 
 }  // namespace dn

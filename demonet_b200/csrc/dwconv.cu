@@ -71,10 +71,10 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
         for (int i = 0; i < NV; ++i) {
             const int iw = iw0 + i;
             const uint4 v = (interior_w || (iw >= 0 && iw < W)) ? __ldg(xr + i * CV) : make_uint4(0u, 0u, 0u, 0u);
-            in[i][0] = bf16x2_to_float2(v.x);
-            in[i][1] = bf16x2_to_float2(v.y);
-            in[i][2] = bf16x2_to_float2(v.z);
-            in[i][3] = bf16x2_to_float2(v.w);
+            in[i][0] = h2_to_float2(v.x);
+            in[i][1] = h2_to_float2(v.y);
+            in[i][2] = h2_to_float2(v.z);
+            in[i][3] = h2_to_float2(v.w);
         }
 #pragma unroll
         for (int kw = 0; kw < KS; ++kw) {
@@ -94,10 +94,10 @@ dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const fl
     for (int t = 0; t < TW; ++t) {
         if (ow0 + t < Wo) {
             uint4 o;
-            o.x = float2_to_bf16x2(dw_act<ACT>(acc[t][0].x), dw_act<ACT>(acc[t][0].y));
-            o.y = float2_to_bf16x2(dw_act<ACT>(acc[t][1].x), dw_act<ACT>(acc[t][1].y));
-            o.z = float2_to_bf16x2(dw_act<ACT>(acc[t][2].x), dw_act<ACT>(acc[t][2].y));
-            o.w = float2_to_bf16x2(dw_act<ACT>(acc[t][3].x), dw_act<ACT>(acc[t][3].y));
+            o.x = float2_to_h2(dw_act<ACT>(acc[t][0].x), dw_act<ACT>(acc[t][0].y));
+            o.y = float2_to_h2(dw_act<ACT>(acc[t][1].x), dw_act<ACT>(acc[t][1].y));
+            o.z = float2_to_h2(dw_act<ACT>(acc[t][2].x), dw_act<ACT>(acc[t][2].y));
+            o.w = float2_to_h2(dw_act<ACT>(acc[t][3].x), dw_act<ACT>(acc[t][3].y));
             yo[(long long)t * CV] = o;
         }
     }
@@ -177,10 +177,10 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 #pragma unroll
     for (int v = 0; v < COUT / 8; ++v) {
         uint4 o;
-        o.x = float2_to_bf16x2(apply_act(acc[v * 4 + 0].x, act), apply_act(acc[v * 4 + 0].y, act));
-        o.y = float2_to_bf16x2(apply_act(acc[v * 4 + 1].x, act), apply_act(acc[v * 4 + 1].y, act));
-        o.z = float2_to_bf16x2(apply_act(acc[v * 4 + 2].x, act), apply_act(acc[v * 4 + 2].y, act));
-        o.w = float2_to_bf16x2(apply_act(acc[v * 4 + 3].x, act), apply_act(acc[v * 4 + 3].y, act));
+        o.x = float2_to_h2(apply_act(acc[v * 4 + 0].x, act), apply_act(acc[v * 4 + 0].y, act));
+        o.y = float2_to_h2(apply_act(acc[v * 4 + 1].x, act), apply_act(acc[v * 4 + 1].y, act));
+        o.z = float2_to_h2(apply_act(acc[v * 4 + 2].x, act), apply_act(acc[v * 4 + 2].y, act));
+        o.w = float2_to_h2(apply_act(acc[v * 4 + 3].x, act), apply_act(acc[v * 4 + 3].y, act));
         yo[v] = o;
     }
 }

@@ -198,7 +198,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
 #pragma unroll
                         for (int j = 0; j < TWIN; ++j)
 #pragma unroll
-                            for (int h = 0; h < NP; ++h) in[j][h] = bf16x2_to_float2(raw[j][h]);
+                            for (int h = 0; h < NP; ++h) in[j][h] = h2_to_float2(raw[j][h]);
                         if (u + 1 < KS) {                              // next staged row, in flight during this row's math
 #pragma unroll
                             for (int j = 0; j < TWIN; ++j) dws_lds_px<NP>(st + (u + 1) * (uint32_t)row_bytes + j * cstep, raw[j]);
@@ -236,10 +236,10 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                                     uint32_t v[NP];
 #pragma unroll
                                     for (int h = 0; h < NP; ++h) {
-                                        v[h] = float2_to_bf16x2(dws_act<ACT>(acc[sl][p][h].x), dws_act<ACT>(acc[sl][p][h].y));
+                                        v[h] = float2_to_h2(dws_act<ACT>(acc[sl][p][h].x), dws_act<ACT>(acc[sl][p][h].y));
                                         // the STORED (bf16) values are pooled, as a separate pass over y would: their fp32
                                         // sums are (all but) exact, so the result does not depend on how the rows are shared
-                                        if (POOL) ps[h] = __fadd2_rn(ps[h], bf16x2_to_float2(v[h]));
+                                        if (POOL) ps[h] = __fadd2_rn(ps[h], h2_to_float2(v[h]));
                                     }
                                     if (NP == 2) *reinterpret_cast<uint2*>(yrow + (long long)p * cw) = make_uint2(v[0], v[NP - 1]);
                                     else yrow[(long long)p * cw] = v[0];
@@ -328,11 +328,8 @@ static int dws_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
                         int C, DwPool* pool, bool probe, cudaStream_t stream) {
     auto kern = dwconv_stream_kernel<KS, dws_tw<KS>(), dws_ch<KS>(), ACT, NT, POOL>;
     const size_t smem = sp.smem + (POOL ? (size_t)sp.ncb * sp.CB * sizeof(float) : 0);
-    static size_t configured = 0;
-    if (smem > configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(kern, smem > 48 * 1024 ? smem : 48 * 1024 + 1, 200 * 1024));
     int per_sm = 0;
     DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;

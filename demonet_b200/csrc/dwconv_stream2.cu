@@ -160,7 +160,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
                         const int ih = 2 * o0 - P + t;
                         float2 in[TWIN];
 #pragma unroll
-                        for (int j = 0; j < TWIN; ++j) in[j] = bf16x2_to_float2(raw[j]);
+                        for (int j = 0; j < TWIN; ++j) in[j] = h2_to_float2(raw[j]);
                         if (u + 1 < G) {                               // next staged row, in flight during this row's math
 #pragma unroll
                             for (int j = 0; j < TWIN; ++j) raw[j] = dw2_lds32(st + (u + 1) * (uint32_t)row_bytes + j * cstep);
@@ -194,9 +194,9 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
 #pragma unroll
                                 for (int p = 0; p < TW; ++p)
                                     if (ow0 + p < Wo) {
-                                        const uint32_t v = float2_to_bf16x2(dw2_act<ACT>(acc[sl][p].x), dw2_act<ACT>(acc[sl][p].y));
+                                        const uint32_t v = float2_to_h2(dw2_act<ACT>(acc[sl][p].x), dw2_act<ACT>(acc[sl][p].y));
                                         yrow[(long long)p * cw] = v;
-                                        if (POOL) ps = __fadd2_rn(ps, bf16x2_to_float2(v));      // the stored values
+                                        if (POOL) ps = __fadd2_rn(ps, h2_to_float2(v));      // the stored values
                                     }
                             }
                         }
@@ -272,11 +272,8 @@ static int dw2_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
                         int C, int Ho, int Wo, DwPool* pool, bool probe, cudaStream_t stream) {
     auto kern = dwconv_stream2_kernel<KS, TW, ACT, POOL>;
     const size_t smem = sp.smem + (POOL ? (size_t)sp.ncb * sp.CB * sizeof(float) : 0);
-    static bool configured = false;
-    if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 76 * 1024));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(kern, smem > 48 * 1024 ? smem : 48 * 1024 + 1, 76 * 1024));
     int per_sm = 0;
     DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;

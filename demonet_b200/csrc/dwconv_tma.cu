@@ -115,10 +115,10 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
                     const uint4 v = row[i * cvs];
-                    in[i][0] = bf16x2_to_float2(v.x);
-                    in[i][1] = bf16x2_to_float2(v.y);
-                    in[i][2] = bf16x2_to_float2(v.z);
-                    in[i][3] = bf16x2_to_float2(v.w);
+                    in[i][0] = h2_to_float2(v.x);
+                    in[i][1] = h2_to_float2(v.y);
+                    in[i][2] = h2_to_float2(v.z);
+                    in[i][3] = h2_to_float2(v.w);
                 }
 #pragma unroll
                 for (int kw = 0; kw < KS; ++kw) {
@@ -140,10 +140,10 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
                 for (int q = 0; q < TW; ++q) {
                     if (ow0 + q < Wo) {
                         uint4 o;
-                        o.x = float2_to_bf16x2(dwt_act<ACT>(acc[q][0].x), dwt_act<ACT>(acc[q][0].y));
-                        o.y = float2_to_bf16x2(dwt_act<ACT>(acc[q][1].x), dwt_act<ACT>(acc[q][1].y));
-                        o.z = float2_to_bf16x2(dwt_act<ACT>(acc[q][2].x), dwt_act<ACT>(acc[q][2].y));
-                        o.w = float2_to_bf16x2(dwt_act<ACT>(acc[q][3].x), dwt_act<ACT>(acc[q][3].y));
+                        o.x = float2_to_h2(dwt_act<ACT>(acc[q][0].x), dwt_act<ACT>(acc[q][0].y));
+                        o.y = float2_to_h2(dwt_act<ACT>(acc[q][1].x), dwt_act<ACT>(acc[q][1].y));
+                        o.z = float2_to_h2(dwt_act<ACT>(acc[q][2].x), dwt_act<ACT>(acc[q][2].y));
+                        o.w = float2_to_h2(dwt_act<ACT>(acc[q][3].x), dwt_act<ACT>(acc[q][3].y));
                         yo[(long long)q * CV] = o;
                     }
                 }
@@ -228,7 +228,7 @@ int dw_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, co
     cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)tl.CB, (cuuint32_t)tl.IWT, (cuuint32_t)tl.IHT, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstride, box, estr,
+    CUresult r = fn(map, DN_TMAP_HALF, 4, const_cast<void*>(x), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DN_REQUIRE(r == CUDA_SUCCESS, DN_ERR_CUDA, "cuTensorMapEncodeTiled (4D) failed (%d): C=%d W=%d H=%d B=%d box=%d,%d,%d",
@@ -241,11 +241,8 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
                   int Wo, cudaStream_t stream) {
     const int tile_bytes = tl.IHT * tl.IWT * tl.CB * 2;
     const size_t smem = 2 * (size_t)((tile_bytes + 127) & ~127) + (size_t)(KS * KS + 1) * tl.CB * 4 + 16;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<KS, S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(dwconv_tma_kernel<KS, S, ACT>, smem));
     const long long n_tiles = (long long)B * tl.tiles_x * tl.tiles_y;
     DN_REQUIRE(n_tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "depthwise problem too large");
     // persistent: about two CTAs per SM in total, spread over the channel chunks

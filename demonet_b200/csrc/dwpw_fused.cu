@@ -160,7 +160,7 @@ dwpw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         const uint2 xv = *reinterpret_cast<const uint2*>(win + ((r0 + wr) * FD_IW + col + kw) * (FD_C * 2) + cq * 8);
-                        in[kw][0] = bf16x2_to_float2(xv.x), in[kw][1] = bf16x2_to_float2(xv.y);
+                        in[kw][0] = h2_to_float2(xv.x), in[kw][1] = h2_to_float2(xv.y);
                     }
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {                    // output row r0 + o takes window row wr with kh = wr - o
@@ -177,8 +177,8 @@ dwpw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 for (int o = 0; o < 4; ++o) {
                     const int m = (r0 + o) * FD_TW + col;
                     uint2 av;
-                    av.x = float2_to_bf16x2(fd_act<ACT_DW>(acc[o][0].x), fd_act<ACT_DW>(acc[o][0].y));
-                    av.y = float2_to_bf16x2(fd_act<ACT_DW>(acc[o][1].x), fd_act<ACT_DW>(acc[o][1].y));
+                    av.x = float2_to_h2(fd_act<ACT_DW>(acc[o][0].x), fd_act<ACT_DW>(acc[o][0].y));
+                    av.y = float2_to_h2(fd_act<ACT_DW>(acc[o][1].x), fd_act<ACT_DW>(acc[o][1].y));
                     // SWIZZLE_32B: 16-byte chunk c of row m lives at chunk position c ^ ((m >> 2) & 1)
                     *reinterpret_cast<uint2*>(a_t + m * 32 + (((cq >> 1) ^ ((m >> 2) & 1)) << 4) + (cq & 1) * 8) = av;
                 }
@@ -190,7 +190,7 @@ dwpw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (it == 0) fd_wait(&bars->w_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // instruction descriptor: D = f32, A = B = bf16, K-major both, N = 16, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FD_C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc = (1u << 4) | (DN_UMMA_AB_FORMAT << 7) | (DN_UMMA_AB_FORMAT << 10) | ((uint32_t)(FD_C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint64_t dw = fd_desc_sw32(fd_u32(w_s));
 #pragma unroll
             for (int j = 0; j < FD_SUB; ++j)
@@ -260,7 +260,7 @@ int dwpw_fused_make_tmaps(CUtensorMap* tx, CUtensorMap* tw, const void* x, const
     tl.CB = FD_C, tl.IWT = FD_IW, tl.IHT = FD_IH;
     int rc = dw_make_tmap(tx, x, B, H, W, FD_C, tl);            // plain NHWC window, zero fill outside the image
     if (rc) return rc;
-    return make_tmap_bf16_2d(tw, w_pw, FD_C, FD_C, FD_C, FD_C);  // [N = 16, K = 16], SWIZZLE_32B
+    return make_tmap_h16_2d(tw, w_pw, FD_C, FD_C, FD_C, FD_C);  // [N = 16, K = 16], SWIZZLE_32B
 }
 
 template <int ACT_DW, bool RESIDUAL>
@@ -268,13 +268,10 @@ static int fd_launch_t(const CUtensorMap& tx, const CUtensorMap& tw, const float
                        int B, int H, int W, cudaStream_t stream) {
     auto kern = dwpw_fused_kernel<ACT_DW, RESIDUAL>;
     const size_t smem = dwpw_fused_smem();
-    static int per_sm = 0;
-    if (!per_sm) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int n = 0;
-        DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, FD_THREADS, smem));
-        per_sm = n > 0 ? n : 1;
-    }
+    static SmemOptIn optin;
+    int per_sm = 1;
+    DN_CHECK_CUDA(optin.ensure(kern, smem));
+    DN_CHECK_CUDA(optin.blocks_per_sm(kern, FD_THREADS, smem, &per_sm));
     const int tiles_x = ceil_div(W, FD_TW), tiles_y = ceil_div(H, FD_TH);
     const long long n_tiles = (long long)B * tiles_x * tiles_y;
     DN_REQUIRE(n_tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "fused depthwise + project problem too large");

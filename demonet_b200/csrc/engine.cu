@@ -72,6 +72,9 @@ struct dn_engine {
     // forward i (tiny layers, NMS rounds) overlaps the bandwidth-bound head of forward i+1
     dn_engine* twin = nullptr;
     int next_slot = 0;
+    int last_slot = 0;                              // slot of the forward issued last (dn_engine_copy_buffer reads it)
+    long long n_graph_replays = 0;                  // forwards that were one cudaGraphLaunch
+    long long n_forwards = 0;
     cudaStream_t slot_stream[2] = {nullptr, nullptr};
     cudaEvent_t slot_in[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
     bool slot_pending[2] = {false, false};
@@ -358,14 +361,14 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
             size_t smem;
             const long long m_max = (long long)e->max_batch * o.h_in * o.w_in;
             pwconv_tc_plan(m_max, o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
-            int rc = make_tmap_bf16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128, 64);
+            int rc = make_tmap_h16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128, 64);
             if (rc) return rc;
-            rc = make_tmap_bf16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn, 64);
+            rc = make_tmap_h16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn, 64);
             if (rc) return rc;
             // dense bf16 outputs without a residual are written by TMA (box 32 rows x 32 columns)
             if (!o.out_fp32 && o.res_buf == DN_BUF_NONE && o.out_batch_stride == 0 && o.out_row_stride == 0 &&
                 o.out_offset == 0 && o.c_out % 8 == 0) {
-                rc = make_tmap_bf16_2d(&e->tmap_y[i], buf_ptr(e, o.out_buf), m_max, o.c_out, 32, 32);
+                rc = make_tmap_h16_2d(&e->tmap_y[i], buf_ptr(e, o.out_buf), m_max, o.c_out, 32, 32);
                 if (rc) return rc;
                 e->has_tmap_y[i] = 1;
             }
@@ -426,7 +429,7 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 PwEpilogue ep;
                 const int hw = o.h_in * o.w_in;
                 ep.bias = (const float*)(W + o.b_off);
-                ep.residual = (const __nv_bfloat16*)buf_ptr(e, o.res_buf);
+                ep.residual = (const dn_half_t*)buf_ptr(e, o.res_buf);
                 ep.y = (unsigned char*)buf_ptr(e, o.out_buf) + (size_t)o.out_offset * (o.out_fp32 ? 4 : 2);
                 ep.N = o.c_out;
                 ep.act = o.act;
@@ -513,6 +516,7 @@ extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, f
     cudaStream_t s = (cudaStream_t)stream_;
     const int k = e->next_slot;
     e->next_slot ^= 1;
+    e->last_slot = k;
     DN_CHECK_CUDA(cudaEventRecord(e->slot_in[k], s));
     DN_CHECK_CUDA(cudaStreamWaitEvent(e->slot_stream[k], e->slot_in[k], 0));
     int rc = forward_one(k ? e->twin : e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, e->slot_stream[k]);
@@ -550,6 +554,7 @@ static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_
     DN_REQUIRE(B > 0 && B <= e->max_batch, DN_ERR_INVALID, "batch %d outside [1, %d]", B, e->max_batch);
     DN_REQUIRE(images_dev && out_boxes && out_scores && out_labels && out_counts, DN_ERR_INVALID, "NULL tensor pointer");
     cudaStream_t s = (cudaStream_t)stream_;
+    ++e->n_forwards;
     if (!e->desc.use_cuda_graph) return enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, s);
     GraphKey key{B, images_dev, out_boxes, out_scores, out_labels, out_counts};
     GraphEntry& g = e->graphs[key];
@@ -572,6 +577,7 @@ static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_
         DN_REQUIRE(ce == cudaSuccess, DN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
     }
     DN_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
+    ++e->n_graph_replays;
     return DN_OK;
 }
 
@@ -631,6 +637,7 @@ static int forward_host_slots(dn_engine* e, const void* images_host, bool u8, in
     if (!e->twin) return forward_host_impl(e, images_host, u8, B, ob, os, ol, oc, stream_);
     const int k = e->next_slot;
     e->next_slot ^= 1;
+    e->last_slot = k;
     int rc = forward_host_impl(k ? e->twin : e, images_host, u8, B, ob, os, ol, oc, e->slot_stream[k]);
     if (rc) return rc;
     DN_CHECK_CUDA(cudaEventRecord(e->slot_done[k], e->slot_stream[k]));
@@ -663,7 +670,13 @@ extern "C" int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, si
     DN_REQUIRE(buf_id >= 0 && buf_id < (int)e->bufs.size(), DN_ERR_INVALID, "bad buffer id %d", buf_id);
     const size_t cap = (size_t)e->bufs[buf_id].elems_per_image * e->bufs[buf_id].elem_bytes * e->max_batch;
     DN_REQUIRE(bytes <= cap, DN_ERR_INVALID, "copy of %zu bytes exceeds the buffer (%zu)", bytes, cap);
-    DN_CHECK_CUDA(cudaMemcpyAsync(dst_dev, buf_ptr(e, buf_id), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    // pipeline mode: the arena of the slot that ran the forward issued last, ordered behind that forward
+    dn_engine* src = e;
+    if (e->twin) {
+        if (e->last_slot == 1) src = e->twin;
+        if (e->slot_pending[e->last_slot]) DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[e->last_slot], 0));
+    }
+    DN_CHECK_CUDA(cudaMemcpyAsync(dst_dev, buf_ptr(src, buf_id), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
     return DN_OK;
 }
 
@@ -716,6 +729,25 @@ extern "C" int dn_engine_launches_per_forward(dn_engine* e) {
     for (const auto& o : e->ops) nop += (o.kind == DN_OP_NOP);
     return (int)e->ops.size() - nop + 3 * e->n_se - e->n_se_pooled + 14;
 }
+extern "C" int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out) {
+    DN_REQUIRE(e && out, DN_ERR_INVALID, "NULL argument");
+    *out = dn_engine_stats{};
+    const dn_engine* last = (e->twin && e->last_slot == 1) ? e->twin : e;
+    for (const auto& o : e->ops) {
+        out->fused_pwdw += (o.kind == DN_OP_PWDW);
+        out->fused_dwpw += (o.kind == DN_OP_DWPW);
+        out->se_layers += (o.kind == DN_OP_SE);
+    }
+    out->se_pooled = last->n_se_pooled;
+    out->launches_per_forward = dn_engine_launches_per_forward(const_cast<dn_engine*>(last));
+    out->pipeline_slots = e->twin ? 2 : 1;
+    out->last_slot = e->last_slot;
+    out->forwards = e->n_forwards + (e->twin ? e->twin->n_forwards : 0);
+    out->graph_replays = e->n_graph_replays + (e->twin ? e->twin->n_graph_replays : 0);
+    out->act_dtype = DN_ACT_DTYPE_ID;
+    return DN_OK;
+}
+
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) {
     return e ? e->device_bytes + (e->twin ? e->twin->device_bytes : 0) : 0;
 }

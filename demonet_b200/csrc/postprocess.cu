@@ -211,6 +211,10 @@ __device__ __forceinline__ float hist_bin_lower_edge(int b) {
     return b <= 0 ? 0.f : __uint_as_float((uint32_t)(b + HIST_BASE) << HIST_SHIFT);
 }
 
+// SCORED: `logits` already holds softmax scores and `bbox` decoded, clipped boxes (dn_postprocess_scored -- the
+// reference's own tensors at generalized_ssd.py:361-363); the kernel then only re-lays them out (class-major scores,
+// float4 boxes) and builds the histogram, so that everything downstream is the very code the engine runs.
+template <bool SCORED>
 __global__ void __launch_bounds__(P1_THREADS)
 softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict__ bbox,
                       const float* __restrict__ anchors, float* __restrict__ scores_t,
@@ -227,7 +231,12 @@ softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // decode + clip (BoxCoder.decode_single, _utils.py:187-224; clip_boxes_to_image)
-    if (threadIdx.x < rows) {
+    if (SCORED) {
+        if (threadIdx.x < rows) {
+            const int p = p0 + threadIdx.x;
+            boxes[(size_t)b * P + p] = reinterpret_cast<const float4*>(bbox)[(size_t)b * P + p];
+        }
+    } else if (threadIdx.x < rows) {
         const int p = p0 + threadIdx.x;
         const float4 r = reinterpret_cast<const float4*>(bbox)[(size_t)b * P + p];
         const float4 a = reinterpret_cast<const float4*>(anchors)[p];
@@ -252,7 +261,9 @@ softmax_decode_kernel(const float* __restrict__ logits, const float* __restrict_
     for (int r = warp; r < rows; r += P1_THREADS / 32) {
         const float* src = logits + ((size_t)b * P + p0 + r) * K;
         float* dst = s_tile + r * ld;
-        if (K <= 32 * P1_MAX_PER_LANE) {
+        if (SCORED) {
+            for (int k = lane; k < K; k += 32) dst[k] = src[k];
+        } else if (K <= 32 * P1_MAX_PER_LANE) {
             float v[P1_MAX_PER_LANE];
             float m = -FLT_MAX;
 #pragma unroll
@@ -650,8 +661,8 @@ constexpr int P3_SORT_CAP = 2048;      // kept entries per image that are staged
 __global__ void __launch_bounds__(P3_THREADS)
 merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ counts, const float* __restrict__ thr,
                   const float4* __restrict__ boxes, float4* __restrict__ out_boxes, float* __restrict__ out_scores,
-                  long long* __restrict__ out_labels, int* __restrict__ out_counts, int* __restrict__ done, int P, int K,
-                  int D, int round) {
+                  long long* __restrict__ out_labels, int* __restrict__ out_counts, int* __restrict__ out_priors,
+                  int* __restrict__ done, int P, int K, int D, int round) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.x;
@@ -710,10 +721,12 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
                 out_scores[(size_t)b * D + i] = e.score;
                 out_labels[(size_t)b * D + i] = (long long)((int)((key >> 24) & 0xffu) + 1);
                 out_boxes[(size_t)b * D + i] = boxes[(size_t)b * P + e.prior];
+                if (out_priors) out_priors[(size_t)b * D + i] = e.prior;
             } else {
                 out_scores[(size_t)b * D + i] = 0.f;
                 out_labels[(size_t)b * D + i] = 0;
                 out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (out_priors) out_priors[(size_t)b * D + i] = -1;
             }
         }
         if (threadIdx.x == 0) {
@@ -788,12 +801,20 @@ merge_topd_kernel(const Entry* __restrict__ entries, const int* __restrict__ cou
     for (int i = threadIdx.x; i < D; i += P3_THREADS) {
         if (i < nsel) {
             out_boxes[(size_t)b * D + i] = boxes[(size_t)b * P + s_sel_prior[i]];
+            if (out_priors) out_priors[(size_t)b * D + i] = s_sel_prior[i];
         } else {
             out_scores[(size_t)b * D + i] = 0.f;
             out_labels[(size_t)b * D + i] = 0;
             out_boxes[(size_t)b * D + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (out_priors) out_priors[(size_t)b * D + i] = -1;
         }
     }
+}
+
+// parity aid (dn_postprocess_scored): which lazy round made image b final (0, 1 or 2)
+__global__ void mark_rounds_kernel(const int* __restrict__ done, int* __restrict__ rounds, int B, int round) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B && (round == 0 || rounds[b] == round) ) rounds[b] = done[b] ? round : round + 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -884,11 +905,11 @@ static int validate_post(const dn_postprocess_params* p) {
 static int postprocess_impl(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
                             const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
                             float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
-                            float* ms3) {
+                            float* ms3, bool scored = false, int32_t* out_priors = nullptr, int32_t* out_rounds = nullptr) {
     int rc = validate_post(p);
     if (rc) return rc;
     DN_REQUIRE(B > 0, DN_ERR_INVALID, "batch must be positive");
-    DN_REQUIRE(cls_logits && bbox_regression && anchors && out_boxes && out_scores && out_labels && out_counts,
+    DN_REQUIRE(cls_logits && bbox_regression && (anchors || scored) && out_boxes && out_scores && out_labels && out_counts,
                DN_ERR_INVALID, "NULL tensor pointer");
     const PostLayout L = post_layout(B, p);
     DN_REQUIRE(workspace && workspace_bytes >= L.total, DN_ERR_WORKSPACE, "workspace too small: need %zu bytes", L.total);
@@ -905,25 +926,15 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
     int* done = (int*)(ws + L.done_off);
     const int cap = cand_cap(p);
     const size_t smem1 = (size_t)P1_ROWS * (K + 1) * sizeof(float);
-    if (smem1 > 48 * 1024)
-        DN_CHECK_CUDA(cudaFuncSetAttribute(softmax_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    static SmemOptIn optin_p1, optin_p1s, optin_sort, optin_warp, optin_cta;
+    DN_CHECK_CUDA(optin_p1.ensure(softmax_decode_kernel<false>, smem1));
+    DN_CHECK_CUDA(optin_p1s.ensure(softmax_decode_kernel<true>, smem1));
     const size_t smem_sort = (size_t)next_pow2(P) * 8;
     const int nms_warps = nms_warps_per_cta(D);
     const size_t smem_nms = (size_t)nms_warps * (D + 32) * 20;
-    static size_t cfg_sort = 48 * 1024, cfg_nms = 48 * 1024;
-    if (smem_sort > cfg_sort) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(class_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort));
-        cfg_sort = smem_sort;
-    }
-    static size_t cfg_cta = 48 * 1024;
-    if ((size_t)D * 20 > cfg_cta) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(class_nms_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 20));
-        cfg_cta = (size_t)D * 20;
-    }
-    if (smem_nms > cfg_nms) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(class_nms_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nms));
-        cfg_nms = smem_nms;
-    }
+    DN_CHECK_CUDA(optin_sort.ensure(class_sort_kernel, smem_sort));
+    DN_CHECK_CUDA(optin_cta.ensure(class_nms_cta_kernel, (size_t)D * 20));
+    DN_CHECK_CUDA(optin_warp.ensure(class_nms_warp_kernel, smem_nms));
     const float thr_up = threshold_up(p->nms_thresh);
     const RoundTargets targets = round_targets(D);
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -939,8 +950,12 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
             if (phase == 0 || !ms3) {
                 DN_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)B * HIST_BINS * sizeof(int), stream));
                 dim3 grid(ceil_div(P, P1_ROWS), B);
-                softmax_decode_kernel<<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors, scores_t,
-                                                                          boxes, hist, P, K, *p);
+                if (scored)
+                    softmax_decode_kernel<true><<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors,
+                                                                                    scores_t, boxes, hist, P, K, *p);
+                else
+                    softmax_decode_kernel<false><<<grid, P1_THREADS, smem1, stream>>>(cls_logits, bbox_regression, anchors,
+                                                                                     scores_t, boxes, hist, P, K, *p);
                 DN_CHECK_LAUNCH();
                 launch_pdl(pick_thresholds_kernel, B, 32, 0, stream, (const int*)hist, thr, targets);
                 DN_CHECK_LAUNCH();
@@ -962,8 +977,11 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
                 }
                 if (phase == 2 || !ms3) {
                     launch_pdl(merge_topd_kernel, B, P3_THREADS, 0, stream, entries, counts, thr, boxes, (float4*)out_boxes,
-                               out_scores, (long long*)out_labels, out_counts, done, P, K, D, r);
+                               out_scores, (long long*)out_labels, out_counts, out_priors, done, P, K, D, r);
                     DN_CHECK_LAUNCH();
+                    // parity aid: after round r, rounds[b] = r + 1 for every image that is still not final
+                    if (out_rounds)
+                        mark_rounds_kernel<<<ceil_div(B, 256), 256, 0, stream>>>(done, out_rounds, B, r);
                 }
             }
             if (!ms3) break;
@@ -990,6 +1008,14 @@ extern "C" int dn_postprocess(const float* cls_logits, const float* bbox_regress
                               void* stream_) {
     return postprocess_impl(cls_logits, bbox_regression, anchors, B, p, workspace, workspace_bytes, out_boxes, out_scores,
                             out_labels, out_counts, (cudaStream_t)stream_, 1, nullptr);
+}
+
+extern "C" int dn_postprocess_scored(const float* scores, const float* boxes, int B, const dn_postprocess_params* p,
+                                     void* workspace, size_t workspace_bytes, float* out_boxes, float* out_scores,
+                                     int64_t* out_labels, int32_t* out_counts, int32_t* out_priors, int32_t* out_rounds,
+                                     void* stream_) {
+    return postprocess_impl(scores, boxes, nullptr, B, p, workspace, workspace_bytes, out_boxes, out_scores, out_labels,
+                            out_counts, (cudaStream_t)stream_, 1, nullptr, true, out_priors, out_rounds);
 }
 
 // measurement aid used by dn_engine_profile / dn_postprocess_profile: mean ms of P1, P2, P3
@@ -1252,11 +1278,8 @@ extern "C" int dn_batched_nms(const float* boxes, const float* scores, const int
         DN_CHECK_LAUNCH();
     }
     const size_t smem = (size_t)BN_MAX_KEEP * (sizeof(float4) + sizeof(float));
-    static bool configured = false;
-    if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(bnms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemOptIn optin_bnms;
+    DN_CHECK_CUDA(optin_bnms.ensure(bnms_class_kernel, smem));
     bnms_class_kernel<<<BN_MAX_LABEL, BN_THREADS, smem, stream>>>((const float4*)boxes, (const long long*)idxs, keys, n,
                                                                 hist, flag, err, threshold_up(iou_threshold));
     DN_CHECK_LAUNCH();

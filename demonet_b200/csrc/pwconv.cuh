@@ -9,7 +9,7 @@ namespace dn {
 
 struct PwEpilogue {
     const float* bias;                 // [N]
-    const __nv_bfloat16* residual;     // [M, N] or nullptr
+    const dn_half_t* residual;     // [M, N] or nullptr
     void* y;
     int N;
     int act;
@@ -25,21 +25,21 @@ struct PwEpilogue {
     // y = act(acc + bias[n]) (+ residual[m][n]), single rounding at the end
     __device__ __forceinline__ float finish(int m, int n, float acc) const {
         float v = apply_act(acc + __ldg(bias + n), act);
-        if (residual) v += __bfloat162float(residual[(long long)m * N + n]);
+        if (residual) v += half_to_float(residual[(long long)m * N + n]);
         return v;
     }
     __device__ __forceinline__ void store(int m, int n, float acc) const {
         const float v = finish(m, n, acc);
         const long long o = row_offset(m) + n;
         if (out_fp32) reinterpret_cast<float*>(y)[o] = v;
-        else reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(v);
+        else reinterpret_cast<dn_half_t*>(y)[o] = float_to_half(v);
     }
 };
 
 int pwconv_simt(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream);
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream);
 // pieces of pwconv_tc that the engine caches per layer
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols);
+int make_tmap_h16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols);
 // m_plan: the row count the tile shape is planned for (the engine passes its max-batch M so that the weight tensor
 // map built at load time and every later launch agree)
 void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes);

@@ -11,7 +11,7 @@ namespace dn {
 constexpr int ST_BM = 64, ST_BN = 64, ST_BK = 16;
 
 __global__ void __launch_bounds__(256)
-pwconv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, PwEpilogue ep, int M,
+pwconv_simt_kernel(const dn_half_t* __restrict__ x, const dn_half_t* __restrict__ w, PwEpilogue ep, int M,
                    int K, int N) {
     __shared__ float As[ST_BK][ST_BM + 1];
     __shared__ float Ws[ST_BK][ST_BN + 1];
@@ -22,9 +22,9 @@ pwconv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         for (int i = threadIdx.x; i < ST_BM * ST_BK; i += 256) {
             const int r = i / ST_BK, c = i % ST_BK;
             const int m = m0 + r, k = k0 + c;
-            As[c][r] = (m < M && k < K) ? __bfloat162float(x[(long long)m * K + k]) : 0.f;
+            As[c][r] = (m < M && k < K) ? half_to_float(x[(long long)m * K + k]) : 0.f;
             const int n = n0 + r;
-            Ws[c][r] = (n < N && k < K) ? __bfloat162float(w[(long long)n * K + k]) : 0.f;
+            Ws[c][r] = (n < N && k < K) ? half_to_float(w[(long long)n * K + k]) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -55,7 +55,7 @@ pwconv_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 
 int pwconv_simt(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream) {
     dim3 grid(ceil_div(M, ST_BM), ceil_div(N, ST_BN));
-    pwconv_simt_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, ep, M, K, N);
+    pwconv_simt_kernel<<<grid, 256, 0, stream>>>((const dn_half_t*)x, (const dn_half_t*)w, ep, M, K, N);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

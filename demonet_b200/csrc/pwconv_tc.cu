@@ -145,7 +145,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
 __device__ __forceinline__ uint32_t make_idesc(int umma_m, int umma_n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+    return (1u << 4) | (DN_UMMA_AB_FORMAT << 7) | (DN_UMMA_AB_FORMAT << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
 struct __align__(8) TcBarriers {
@@ -309,9 +309,9 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const float2 bb = *reinterpret_cast<const float2*>(sbw + q * 8 + 2 * i);
                                 const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 2 * i]), __uint_as_float(v[q * 8 + 2 * i + 1])),
                                                             make_float2(1.f, 1.f), bb);
-                                __nv_bfloat162 h = __floats2bfloat162_rn(t.x, t.y);
-                                if constexpr (ACT == DN_ACT_RELU || ACT == DN_ACT_RELU6) h = __hmax2(h, __float2bfloat162_rn(0.f));
-                                if constexpr (ACT == DN_ACT_RELU6) h = __hmin2(h, __float2bfloat162_rn(6.f));
+                                dn_half2_t h = floats_to_half2(t.x, t.y);
+                                if constexpr (ACT == DN_ACT_RELU || ACT == DN_ACT_RELU6) h = __hmax2(h, half2_const(0.f));
+                                if constexpr (ACT == DN_ACT_RELU6) h = __hmin2(h, half2_const(6.f));
                                 w[i] = *reinterpret_cast<uint32_t*>(&h);
                             }
                             o = make_uint4(w[0], w[1], w[2], w[3]);
@@ -374,13 +374,13 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         float4 o = *reinterpret_cast<const float4*>(stg + r * TC_STAGE_PITCH + cg);
                         float f[4] = {o.x, o.y, o.z, o.w};
                         if (res_vec) {
-                            const float2 r0 = bf16x2_to_float2(rres[it].x), r1 = bf16x2_to_float2(rres[it].y);
+                            const float2 r0 = h2_to_float2(rres[it].x), r1 = h2_to_float2(rres[it].y);
                             f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
                         } else if (ep.residual) {
-                            const __nv_bfloat16* rp = ep.residual + (long long)mr * N + n;
+                            const dn_half_t* rp = ep.residual + (long long)mr * N + n;
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                if (i < cnt) f[i] += __bfloat162float(rp[i]);
+                                if (i < cnt) f[i] += half_to_float(rp[i]);
                         }
                         if (ep.out_fp32) {
                             float* dst = reinterpret_cast<float*>(ep.y) + orow + n;
@@ -395,16 +395,16 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     if (i < cnt) dst[i] = f[i];
                             }
                         } else {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.y) + orow + n;
+                            dn_half_t* dst = reinterpret_cast<dn_half_t*>(ep.y) + orow + n;
                             if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
                                 uint2 pk;
-                                pk.x = float2_to_bf16x2(f[0], f[1]);
-                                pk.y = float2_to_bf16x2(f[2], f[3]);
+                                pk.x = float2_to_h2(f[0], f[1]);
+                                pk.y = float2_to_h2(f[2], f[3]);
                                 *reinterpret_cast<uint2*>(dst) = pk;
                             } else {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i)
-                                    if (i < cnt) dst[i] = __float2bfloat16_rn(f[i]);
+                                    if (i < cnt) dst[i] = float_to_half(f[i]);
                             }
                         }
                     }
@@ -446,7 +446,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // 2D bf16 tensor map over a row-major [rows, cols] matrix, box = [box_rows, box_cols]; the swizzle span equals
 // the box row (64 cols -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B)
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols) {
+int make_tmap_h16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols) {
     PFN_encodeTiled fn = get_encode_fn();
     DN_REQUIRE(fn != nullptr, DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     DN_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, DN_ERR_INVALID, "GEMM operand must be 16-byte aligned");
@@ -458,7 +458,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
                                    : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+    CUresult r = fn(map, DN_TMAP_HALF, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DN_REQUIRE(r == CUDA_SUCCESS, DN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r,
@@ -519,12 +519,8 @@ template <int ACT, bool TMA_STORE>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
                           int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
                           cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(pwconv_tc_kernel<ACT, TMA_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem_cap(1)));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE>, smem_cap(1)));
     launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles, st, cols);
     DN_CHECK_LAUNCH();
     return DN_OK;
@@ -573,14 +569,14 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
     size_t smem;
     pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem);
     CUtensorMap ta, tw, ty;
-    int rc = make_tmap_bf16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
+    int rc = make_tmap_h16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tw, w, N, K, bn, TC_BLOCK_K);
+    rc = make_tmap_h16_2d(&tw, w, N, K, bn, TC_BLOCK_K);
     if (rc) return rc;
     const bool dense = !ep.out_fp32 && !ep.residual && N % 8 == 0 && ep.out_row_stride == N &&
                        (ep.hw >= M || ep.out_batch_stride == (long long)ep.hw * N);
     if (dense) {
-        rc = make_tmap_bf16_2d(&ty, ep.y, M, N, 32, 32);
+        rc = make_tmap_h16_2d(&ty, ep.y, M, N, 32, 32);
         if (rc) return rc;
     }
     return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, M, K, N, stream);
@@ -599,7 +595,7 @@ extern "C" int dn_pwconv(const void* x, const void* w, const float* bias, const 
     DN_REQUIRE(impl == 0 || impl == 1, DN_ERR_INVALID, "impl must be 0 (tcgen05) or 1 (SIMT self-check)");
     PwEpilogue ep;
     ep.bias = bias;
-    ep.residual = (const __nv_bfloat16*)residual;
+    ep.residual = (const dn_half_t*)residual;
     ep.y = y;
     ep.N = N;
     ep.act = act;

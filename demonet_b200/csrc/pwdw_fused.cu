@@ -121,7 +121,7 @@ pwdw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     };
     auto issue_mma = [&](int buf) {               // one thread: 3 MMAs over the 384 (289 used) pixel rows
         // instruction descriptor: D = f32, A = B = bf16, K-major both, N = 64, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FU_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | (DN_UMMA_AB_FORMAT << 7) | (DN_UMMA_AB_FORMAT << 10) | ((uint32_t)(FU_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t dw = fu_desc_sw32(fu_u32(w_s));
 #pragma unroll
         for (int i = 0; i < FU_MT; ++i) {
@@ -193,11 +193,11 @@ pwdw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                             const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1])),
                                                          make_float2(1.f, 1.f), bb);
                             if constexpr (ACT_PW == DN_ACT_HSWISH) {
-                                w[e] = float2_to_bf16x2(fu_act<ACT_PW>(tt.x), fu_act<ACT_PW>(tt.y));
+                                w[e] = float2_to_h2(fu_act<ACT_PW>(tt.x), fu_act<ACT_PW>(tt.y));
                             } else {               // ReLU / ReLU6 on the packed pair after the (monotone) rounding
-                                __nv_bfloat162 h = __floats2bfloat162_rn(tt.x, tt.y);
-                                if constexpr (ACT_PW == DN_ACT_RELU || ACT_PW == DN_ACT_RELU6) h = __hmax2(h, __float2bfloat162_rn(0.f));
-                                if constexpr (ACT_PW == DN_ACT_RELU6) h = __hmin2(h, __float2bfloat162_rn(6.f));
+                                dn_half2_t h = floats_to_half2(tt.x, tt.y);
+                                if constexpr (ACT_PW == DN_ACT_RELU || ACT_PW == DN_ACT_RELU6) h = __hmax2(h, half2_const(0.f));
+                                if constexpr (ACT_PW == DN_ACT_RELU6) h = __hmin2(h, half2_const(6.f));
                                 w[e] = *reinterpret_cast<uint32_t*>(&h);
                             }
                         }
@@ -238,7 +238,7 @@ pwdw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 for (int c = 0; c < 5; ++c) {
                     const int m = (4 * by + r) * FU_IT + 4 * bx + c;
                     const uint2 xv = *reinterpret_cast<const uint2*>(exp_t + m * (FU_N * 2) + (((cq >> 1) ^ (m & 7)) << 4) + (cq & 1) * 8);
-                    in[c][0] = bf16x2_to_float2(xv.x), in[c][1] = bf16x2_to_float2(xv.y);
+                    in[c][0] = h2_to_float2(xv.x), in[c][1] = h2_to_float2(xv.y);
                 }
 #pragma unroll
                 for (int a2 = 0; a2 < 2; ++a2) {                 // output row 2*by + a2 takes input rows 2*a2 .. 2*a2 + 2 of the window
@@ -263,8 +263,8 @@ pwdw_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     const int gy = ty * FU_TO + 2 * by + a2, gx = tx * FU_TO + 2 * bx + b2;
                     if (gy < Ho && gx < Wo) {
                         uint2 ov;
-                        ov.x = float2_to_bf16x2(fu_act<ACT_DW>(acc[a2][b2][0].x), fu_act<ACT_DW>(acc[a2][b2][0].y));
-                        ov.y = float2_to_bf16x2(fu_act<ACT_DW>(acc[a2][b2][1].x), fu_act<ACT_DW>(acc[a2][b2][1].y));
+                        ov.x = float2_to_h2(fu_act<ACT_DW>(acc[a2][b2][0].x), fu_act<ACT_DW>(acc[a2][b2][0].y));
+                        ov.y = float2_to_h2(fu_act<ACT_DW>(acc[a2][b2][1].x), fu_act<ACT_DW>(acc[a2][b2][1].y));
                         reinterpret_cast<uint2*>(y)[(((long long)b * Ho + gy) * Wo + gx) * (FU_N / 4) + cq] = ov;
                     }
                 }
@@ -303,11 +303,11 @@ int pwdw_fused_make_tmaps(CUtensorMap* tx, CUtensorMap* tw, const void* x, const
     cuuint64_t gstride[3] = {(cuuint64_t)FU_K * 2, (cuuint64_t)W * FU_K * 2, (cuuint64_t)H * W * FU_K * 2};
     cuuint32_t box[4] = {(cuuint32_t)FU_K, (cuuint32_t)FU_IT, (cuuint32_t)FU_IT, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstride, box, estr,
+    CUresult r = fn(tx, DN_TMAP_HALF, 4, const_cast<void*>(x), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DN_REQUIRE(r == CUDA_SUCCESS, DN_ERR_CUDA, "cuTensorMapEncodeTiled (fused expand input) failed (%d)", (int)r);
-    return make_tmap_bf16_2d(tw, w_pw, FU_N, FU_K, FU_N, FU_K);
+    return make_tmap_h16_2d(tw, w_pw, FU_N, FU_K, FU_N, FU_K);
 }
 
 template <int ACT_PW, int ACT_DW>
@@ -315,11 +315,8 @@ static int fu_launch_t(const CUtensorMap& tx, const CUtensorMap& tw, const float
                        int B, int H, int W, cudaStream_t stream) {
     auto kern = pwdw_fused_kernel<ACT_PW, ACT_DW>;
     const size_t smem = pwdw_fused_smem();
-    static bool configured = false;
-    if (!configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(kern, smem));
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int tiles_x = ceil_div(Wo, FU_TO), tiles_y = ceil_div(Ho, FU_TO);
     const long long n_tiles = (long long)B * tiles_x * tiles_y;

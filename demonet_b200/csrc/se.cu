@@ -311,12 +311,9 @@ int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2
     const size_t fc1_smem = (size_t)SE_GI * C * sizeof(float);
     const size_t fc2_smem = ((size_t)SE_GI * Cs + (size_t)SE_GI * C) * sizeof(float);
     DN_REQUIRE(pool_smem <= 48 * 1024 && fc2_smem <= 160 * 1024, DN_ERR_UNSUPPORTED, "SE block too large for shared memory");
-    static size_t fc_configured = 48 * 1024;
-    if (fc2_smem > fc_configured) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(se_fc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        DN_CHECK_CUDA(cudaFuncSetAttribute(se_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        fc_configured = 160 * 1024;
-    }
+    static SmemOptIn optin_fc1, optin_fc2;
+    DN_CHECK_CUDA(optin_fc1.ensure(se_fc1_kernel, fc2_smem, 160 * 1024));
+    DN_CHECK_CUDA(optin_fc2.ensure(se_fc2_kernel, fc2_smem, 160 * 1024));
     if (dw_parts == 0) {
         launch_pdl(se_pool_kernel, dim3(p.pool_chunks, B), SE_POOL_THREADS, pool_smem, s, (const uint4*)x, partial, HW, C, p.CV,
                    p.rows, p.pool_px);

@@ -169,10 +169,10 @@ stem_tma_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __res
 #pragma unroll
                     for (int v8 = 0; v8 < COUT / 8; ++v8) {
                         uint4 o;
-                        o.x = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 0].x), st_act<ACT>(acc[p][v8 * 4 + 0].y));
-                        o.y = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 1].x), st_act<ACT>(acc[p][v8 * 4 + 1].y));
-                        o.z = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 2].x), st_act<ACT>(acc[p][v8 * 4 + 2].y));
-                        o.w = float2_to_bf16x2(st_act<ACT>(acc[p][v8 * 4 + 3].x), st_act<ACT>(acc[p][v8 * 4 + 3].y));
+                        o.x = float2_to_h2(st_act<ACT>(acc[p][v8 * 4 + 0].x), st_act<ACT>(acc[p][v8 * 4 + 0].y));
+                        o.y = float2_to_h2(st_act<ACT>(acc[p][v8 * 4 + 1].x), st_act<ACT>(acc[p][v8 * 4 + 1].y));
+                        o.z = float2_to_h2(st_act<ACT>(acc[p][v8 * 4 + 2].x), st_act<ACT>(acc[p][v8 * 4 + 2].y));
+                        o.w = float2_to_h2(st_act<ACT>(acc[p][v8 * 4 + 3].x), st_act<ACT>(acc[p][v8 * 4 + 3].y));
                         yo[p * (COUT / 8) + v8] = o;
                     }
                 }
@@ -219,13 +219,10 @@ static int stem_launch_t(const CUtensorMap& tm, const float* w, const float* bia
                          int W, cudaStream_t stream) {
     constexpr int THREADS = ST_TH * (ST_TW / NPX);
     const size_t smem = (size_t)(ST_RAW_FLOATS + ST_NRM_FLOATS + 28 * COUT) * 4;
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-        DN_CHECK_CUDA(cudaFuncSetAttribute(stem_tma_kernel<COUT, NPX, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int n = 0;
-        DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_tma_kernel<COUT, NPX, ACT>, THREADS, smem));
-        ctas_per_sm = n > 0 ? n : 1;
-    }
+    static SmemOptIn optin;
+    int ctas_per_sm = 1;
+    DN_CHECK_CUDA(optin.ensure(stem_tma_kernel<COUT, NPX, ACT>, smem));
+    DN_CHECK_CUDA(optin.blocks_per_sm(stem_tma_kernel<COUT, NPX, ACT>, THREADS, smem, &ctas_per_sm));
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const int tiles_x = (Wo + ST_TW - 1) / ST_TW, tiles_y = (Ho + ST_TH - 1) / ST_TH;
     const long long n_tiles = (long long)B * tiles_x * tiles_y;

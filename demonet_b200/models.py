@@ -26,7 +26,17 @@ model_urls = {
 # are accepted and ignored because this build is inference only
 _SSD_KWARGS = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std"}
 _SSD_TRAIN_KWARGS = {"iou_thresh", "positive_fraction"}
-_ENGINE_KWARGS = {"gemm_impl", "use_cuda_graph", "keep_activations", "pipeline_slots"}
+_ENGINE_KWARGS = {"gemm_impl", "use_cuda_graph", "keep_activations", "pipeline_slots", "act_dtype"}
+
+
+def _reject_unknown(kwargs):
+    """The reference forwards **kwargs both to the backbone builder, which swallows anything (mobilenetv3.py:111,190),
+    and to SSD.__init__ (ssd_mobilenetv3.py:217-219), which does not: an unknown key ends in
+    `TypeError: SSD.__init__() got an unexpected keyword argument 'bogus'` [probed on the unmodified reference].
+    Same exception type and wording here."""
+    unknown = sorted(set(kwargs) - _SSD_KWARGS - _SSD_TRAIN_KWARGS - _ENGINE_KWARGS)
+    if unknown:
+        raise TypeError("SSD.__init__() got an unexpected keyword argument '%s'" % unknown[0])
 
 
 def ssdlite320_mobilenet_v3_large(pretrained: bool = False, progress: bool = True, num_classes: int = 91,
@@ -52,9 +62,7 @@ def ssdlite320_mobilenet_v3_large(pretrained: bool = False, progress: bool = Tru
     if pretrained_backbone and not pretrained:
         raise NotImplementedError("pretrained_backbone=True selects the non-reduced tail "
                                   "(ssd_mobilenetv3.py:192-193), which is not built; use pretrained=True")
-    unknown = set(kwargs) - _SSD_KWARGS - _SSD_TRAIN_KWARGS - _ENGINE_KWARGS
-    if unknown:
-        raise TypeError("unsupported arguments: %s" % sorted(unknown))
+    _reject_unknown(kwargs)
     defaults = {"score_thresh": 0.001, "nms_thresh": 0.55, "detections_per_img": 300, "topk_candidates": 300,
                 "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5]}
     cfg = {**defaults, **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _ENGINE_KWARGS}}
@@ -78,9 +86,7 @@ def ssd_lite_mobilenet_v2(pretrained: bool = False, image_size: int = 320, score
     surviving implementation.
     """
     flavour = kwargs.pop("postprocess", "legacy")
-    unknown = set(kwargs) - _SSD_KWARGS - _SSD_TRAIN_KWARGS - _ENGINE_KWARGS
-    if unknown:
-        raise TypeError("unsupported arguments: %s" % sorted(unknown))
+    _reject_unknown(kwargs)
     cfg = {"nms_thresh": 0.45, "detections_per_img": 100, "topk_candidates": 400,
            **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _ENGINE_KWARGS}}
     cfg["score_thresh"] = score_thresh

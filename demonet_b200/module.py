@@ -31,11 +31,16 @@ class _Engine:
         self._handle = ctypes.c_void_p()
         self._weights_token = None
         self._desc_kwargs = desc_kwargs
+        self.act_dtype = desc_kwargs.get("act_dtype") or _C.DEFAULT_ACT_DTYPE
+        self._lib = _C.lib(self.act_dtype)          # raises if that build is missing: no fallback
         self._ops = None
         self._created = False
 
+    def _check(self, rc):
+        self._check(rc, self._lib)
+
     def _create(self, offsets):
-        lib = _C.lib()
+        lib = self._lib
         plan, kw = self.plan, self._desc_kwargs
         fuse = not kw.get("keep_activations", False) and int(os.environ.get("DN_FUSE", "1")) != 0 and int(kw.get("gemm_impl", 0)) == 0
         self._ops = _plan.build_ops(plan, offsets, self.t2b, self.logits_buf, self.bbox_buf, fuse=fuse)
@@ -58,23 +63,23 @@ class _Engine:
         d.use_cuda_graph = int(kw.get("use_cuda_graph", 1))
         d.pipeline_slots = int(kw.get("pipeline_slots", 0))
         with torch.cuda.device(self.device):
-            _C.check(lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
+            self._check(lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
         self._created = True
 
     def load_weights(self, sd, token):
-        blob, offsets = _plan.pack_weights(self.plan, sd)
+        blob, offsets = _plan.pack_weights(self.plan, sd, self.act_dtype)
         if not self._created:
             self._create(offsets)
         buf = ctypes.create_string_buffer(blob, len(blob))
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_load_weights(self._handle, buf, len(blob)))
+            self._check(self._lib.dn_engine_load_weights(self._handle, buf, len(blob)))
         self._weights_token = token
 
     def forward(self, images: Tensor, out):
         B = images.shape[0]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_forward(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
+            self._check(self._lib.dn_engine_forward(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
                                                out["scores"].data_ptr(), out["labels"].data_ptr(),
                                                out["counts"].data_ptr(), stream))
 
@@ -85,18 +90,18 @@ class _Engine:
     def join(self):
         """Pipeline mode: order every forward issued so far before later work on the current stream."""
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_join(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
+            self._check(self._lib.dn_engine_join(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
 
     def join_previous(self):
         """Pipeline mode: order the forward issued BEFORE the most recent one before later work on the current stream."""
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_join_previous(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
+            self._check(self._lib.dn_engine_join_previous(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
 
     def forward_host(self, images: Tensor, out):
         B = images.shape[0]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_forward_host(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
+            self._check(self._lib.dn_engine_forward_host(self._handle, images.data_ptr(), B, out["boxes"].data_ptr(),
                                                     out["scores"].data_ptr(), out["labels"].data_ptr(),
                                                     out["counts"].data_ptr(), stream))
 
@@ -104,14 +109,14 @@ class _Engine:
         B = images_u8.shape[0]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_forward_host_u8(self._handle, images_u8.data_ptr(), B, out["boxes"].data_ptr(),
+            self._check(self._lib.dn_engine_forward_host_u8(self._handle, images_u8.data_ptr(), B, out["boxes"].data_ptr(),
                                                        out["scores"].data_ptr(), out["labels"].data_ptr(),
                                                        out["counts"].data_ptr(), stream))
 
     def buffer(self, tensor_name: str, batch: int) -> Tensor:
         """Copy of an intermediate activation as fp32 NCHW (for stage-by-stage parity tests)."""
         h, w, c = self.plan.tensors[tensor_name]
-        return self._read(self.t2b[tensor_name], batch, (h, w, c), torch.bfloat16).permute(0, 3, 1, 2).float()
+        return self._read(self.t2b[tensor_name], batch, (h, w, c), _C.torch_dtype(self.act_dtype)).permute(0, 3, 1, 2).float()
 
     def head_outputs(self, batch: int) -> Tuple[Tensor, Tensor]:
         P, K = self.plan.num_priors, self.plan.num_classes
@@ -119,26 +124,33 @@ class _Engine:
                 self._read(self.bbox_buf, batch, (P, 4), torch.float32))
 
     def _read(self, buf_id, batch, shape, dtype):
-        if self.pipelined:
-            raise RuntimeError("intermediate buffers are not addressable in pipeline mode (two arenas alternate)")
+        # pipeline mode: the C side reads the arena of the slot that ran the forward issued last
         n = batch * int(np.prod(shape))
         out = torch.empty(n, dtype=dtype, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _C.check(_C.lib().dn_engine_copy_buffer(self._handle, buf_id, out.data_ptr(), n * out.element_size(), stream))
+            self._check(self._lib.dn_engine_copy_buffer(self._handle, buf_id, out.data_ptr(), n * out.element_size(), stream))
         return out.view(batch, *shape)
+
+    def stats(self) -> dict:
+        """What the forward issued last ran: fused launches, pooled SE layers, graph replays, slots, storage type."""
+        st = _C.EngineStats()
+        self._check(self._lib.dn_engine_get_stats(self._handle, ctypes.byref(st)))
+        out = {name: int(getattr(st, name)) for name, _ in _C.EngineStats._fields_}
+        out["act_dtype"] = _C.ACT_DTYPES[1 - out["act_dtype"]]          # 1 = fp16, 0 = bf16
+        return out
 
     @property
     def launches_per_forward(self):
-        return _C.lib().dn_engine_launches_per_forward(self._handle)
+        return self._lib.dn_engine_launches_per_forward(self._handle)
 
     @property
     def device_bytes(self):
-        return _C.lib().dn_engine_device_bytes(self._handle)
+        return self._lib.dn_engine_device_bytes(self._handle)
 
     def close(self):
         if self._created and self._handle:
-            _C.lib().dn_engine_destroy(self._handle)
+            self._lib.dn_engine_destroy(self._handle)
             self._handle = ctypes.c_void_p()
             self._created = False
 
@@ -223,7 +235,7 @@ class SSDLiteB200(nn.Module):
 
     def __init__(self, plan: _plan.Plan, score_thresh=0.01, nms_thresh=0.45, detections_per_img=200,
                  topk_candidates=400, image_mean=None, image_std=None, postprocess="ssd", init="normal",
-                 gemm_impl=0, use_cuda_graph=True, keep_activations=False, pipeline_slots=0):
+                 gemm_impl=0, use_cuda_graph=True, keep_activations=False, pipeline_slots=0, act_dtype=None):
         super().__init__()
         if postprocess not in ("ssd", "legacy"):
             raise ValueError("postprocess must be 'ssd' or 'legacy'")
@@ -239,6 +251,9 @@ class SSDLiteB200(nn.Module):
         self._gemm_impl = gemm_impl
         self._use_cuda_graph = use_cuda_graph
         self._pipeline_slots = int(pipeline_slots)      # 2: consecutive batches overlap on two engine instances
+        self.act_dtype = act_dtype or _C.DEFAULT_ACT_DTYPE      # "fp16" (default) or "bf16": activation storage type
+        if self.act_dtype not in _C.ACT_DTYPES:
+            raise ValueError("act_dtype must be one of %s" % (_C.ACT_DTYPES,))
         self._keep_activations = keep_activations      # debug: one arena buffer per tensor
         self._engines: Dict[Tuple[str, int], _Engine] = {}
         self._io: Dict[Tuple[str, int], dict] = {}
@@ -294,7 +309,7 @@ class SSDLiteB200(nn.Module):
                       nms_thresh=self.nms_thresh, topk_candidates=self.topk_candidates,
                       detections_per_img=self.detections_per_img, gemm_impl=self._gemm_impl,
                       use_cuda_graph=int(self._use_cuda_graph), keep_activations=self._keep_activations,
-                      pipeline_slots=self._pipeline_slots,
+                      pipeline_slots=self._pipeline_slots, act_dtype=self.act_dtype,
                       min_box_size=1e-2 if self.postprocess_flavour == "legacy" else -1.0)
             eng = _Engine(self.plan, kw, max(batch, 1), device)
             self._engines[key] = eng

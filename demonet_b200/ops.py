@@ -26,6 +26,20 @@ def _stream(t: Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _CL:
+    """Call proxy: the library built for the activation dtype of `x`, with the status check on the same handle."""
+
+    def __init__(self, x):
+        self._h = _C.lib(_C.dtype_name(x.dtype))
+
+    def __getattr__(self, name):
+        fn, h = getattr(self._h, name), self._h
+
+        def call(*args):
+            _C.check(fn(*args), h)
+        return call
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -103,6 +117,37 @@ def postprocess_padded(cls_logits, bbox_regression, anchors, image_shape, score_
                         detections_per_img, topk_candidates, min_box_size)
 
 
+def postprocess_scored(scores, boxes, image_shape, score_thresh=0.001, nms_thresh=0.55, detections_per_img=300,
+                       topk_candidates=300, min_box_size=-1.0):
+    """SSD.postprocess_detections from the point where the reference holds softmax `scores` [B,P,K] and decoded, clipped
+    `boxes` [B,P,4] (generalized_ssd.py:361-396), through the kernels the engine runs (class sort, lazy warp / CTA NMS,
+    top-D merge).  Returns padded (boxes [B,D,4], scores [B,D], labels [B,D], counts [B], priors int32 [B,D], rounds
+    int32 [B]): (priors, labels) is the (anchor, class) identity of keep[:detections_per_img]."""
+    _require_cuda(scores, boxes)
+    if scores.dim() != 3 or boxes.dim() != 3 or boxes.shape[-1] != 4 or boxes.shape[:2] != scores.shape[:2]:
+        raise ValueError("expected scores [B,P,K] and boxes [B,P,4]")
+    B, P, K = scores.shape
+    scores = scores.detach().float().contiguous()
+    boxes = boxes.detach().float().contiguous()
+    dev = scores.device
+    prm = make_post_params(P, K, int(image_shape[0]), int(image_shape[1]), score_thresh, nms_thresh, topk_candidates,
+                           detections_per_img, min_box_size)
+    lib = _C.lib()
+    D = detections_per_img
+    ws = torch.empty(lib.dn_postprocess_workspace_bytes(B, ctypes.byref(prm)), dtype=torch.uint8, device=dev)
+    out_boxes = torch.empty(B, D, 4, dtype=torch.float32, device=dev)
+    out_scores = torch.empty(B, D, dtype=torch.float32, device=dev)
+    out_labels = torch.empty(B, D, dtype=torch.int64, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    priors = torch.empty(B, D, dtype=torch.int32, device=dev)
+    rounds = torch.zeros(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _C.check(lib.dn_postprocess_scored(scores.data_ptr(), boxes.data_ptr(), B, ctypes.byref(prm), ws.data_ptr(),
+                                           ws.numel(), out_boxes.data_ptr(), out_scores.data_ptr(), out_labels.data_ptr(),
+                                           counts.data_ptr(), priors.data_ptr(), rounds.data_ptr(), _stream(scores)))
+    return out_boxes, out_scores, out_labels, counts, priors, rounds
+
+
 def _to_dicts(boxes, scores, labels, counts) -> List[Dict[str, Tensor]]:
     out = []
     for i, n in enumerate(counts.tolist()):
@@ -172,112 +217,112 @@ class DefaultBoxGenerator(torch.nn.Module):
         return [t for _ in image_list.image_sizes]
 
 
-# ---- conv stages (NHWC bf16) -------------------------------------------------------------------
+# ---- conv stages (NHWC fp16 / bf16: the library is chosen by the dtype of x) -----------------
 def dwconv(x: Tensor, w: Tensor, bias: Tensor, k: int, stride: int, act: str) -> Tensor:
-    """x bf16 [B,H,W,C]; w fp32 [k*k,C]; bias fp32 [C] -> bf16 [B,Ho,Wo,C]."""
+    """x fp16/bf16 [B,H,W,C]; w fp32 [k*k,C]; bias fp32 [C] -> fp16/bf16 [B,Ho,Wo,C]."""
     _require_cuda(x, w, bias)
     B, H, W, C = x.shape
     pad = (k - 1) // 2
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    y = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_dwconv(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(),
-                                    y.data_ptr(), B, H, W, C, k, stride, _C.ACT[act], _stream(x)))
+        _CL(x).dn_dwconv(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(),
+                                    y.data_ptr(), B, H, W, C, k, stride, _C.ACT[act], _stream(x))
     return y
 
 
 def pwconv(x: Tensor, w: Tensor, bias: Tensor, act: str = "none", residual: Tensor = None, out_fp32: bool = False,
            impl: int = 0) -> Tensor:
-    """x bf16 [M,K]; w bf16 [N,K]; bias fp32 [N]; residual bf16 [M,N] -> [M,N] bf16 (or fp32)."""
+    """x fp16/bf16 [M,K]; w fp16/bf16 [N,K]; bias fp32 [N]; residual fp16/bf16 [M,N] -> [M,N] fp16/bf16 (or fp32)."""
     _require_cuda(x, w, bias, residual)
     M, K = x.shape
     N = w.shape[0]
-    y = torch.empty(M, N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=x.device)
+    y = torch.empty(M, N, dtype=torch.float32 if out_fp32 else x.dtype, device=x.device)
     x, w, bias = x.contiguous(), w.contiguous(), bias.contiguous()
     res = residual.contiguous() if residual is not None else None
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_pwconv(x.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
-                                    y.data_ptr(), M, K, N, _C.ACT[act], int(out_fp32), M, 0, N, impl, _stream(x)))
+        _CL(x).dn_pwconv(x.data_ptr(), w.data_ptr(), bias.data_ptr(), res.data_ptr() if res is not None else None,
+                                    y.data_ptr(), M, K, N, _C.ACT[act], int(out_fp32), M, 0, N, impl, _stream(x))
     return y
 
 
 def pwdw_fused(x: Tensor, w_pw: Tensor, b_pw: Tensor, w_dw: Tensor, b_dw: Tensor, k: int, stride: int, act_pw: str,
                act_dw: str) -> Tensor:
-    """x bf16 [B,H,W,K] -> act_dw(dw(act_pw(x . w_pw^T + b_pw))) bf16 [B,Ho,Wo,N] with the expanded tensor kept on chip.
-    w_pw bf16 [N,K]; w_dw fp32 [k*k,N]."""
+    """x fp16/bf16 [B,H,W,K] -> act_dw(dw(act_pw(x . w_pw^T + b_pw))) fp16/bf16 [B,Ho,Wo,N] with the expanded tensor kept on chip.
+    w_pw fp16/bf16 [N,K]; w_dw fp32 [k*k,N]."""
     _require_cuda(x, w_pw, b_pw, w_dw, b_dw)
     B, H, W, K = x.shape
     N = w_pw.shape[0]
     Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
-    y = torch.empty(B, Ho, Wo, N, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, Ho, Wo, N, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_pwdw_fused(x.contiguous().data_ptr(), w_pw.contiguous().data_ptr(), b_pw.contiguous().data_ptr(),
+        _CL(x).dn_pwdw_fused(x.contiguous().data_ptr(), w_pw.contiguous().data_ptr(), b_pw.contiguous().data_ptr(),
                                         w_dw.contiguous().data_ptr(), b_dw.contiguous().data_ptr(), y.data_ptr(), B, H, W, K, N,
-                                        k, stride, _C.ACT[act_pw], _C.ACT[act_dw], _stream(x)))
+                                        k, stride, _C.ACT[act_pw], _C.ACT[act_dw], _stream(x))
     return y
 
 
 def dwpw_fused(x: Tensor, w_dw: Tensor, b_dw: Tensor, w_pw: Tensor, b_pw: Tensor, k: int, stride: int, act_dw: str,
                residual: bool) -> Tensor:
-    """x bf16 [B,H,W,C] -> (act_dw(dw(x)) . w_pw^T + b_pw) (+ x) bf16 [B,H,W,N] with the depthwise output kept on chip."""
+    """x fp16/bf16 [B,H,W,C] -> (act_dw(dw(x)) . w_pw^T + b_pw) (+ x) fp16/bf16 [B,H,W,N] with the depthwise output kept on chip."""
     _require_cuda(x, w_dw, b_dw, w_pw, b_pw)
     B, H, W, C = x.shape
     N = w_pw.shape[0]
-    y = torch.empty(B, H, W, N, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, H, W, N, dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_dwpw_fused(x.contiguous().data_ptr(), w_dw.contiguous().data_ptr(), b_dw.contiguous().data_ptr(),
+        _CL(x).dn_dwpw_fused(x.contiguous().data_ptr(), w_dw.contiguous().data_ptr(), b_dw.contiguous().data_ptr(),
                                         w_pw.contiguous().data_ptr(), b_pw.contiguous().data_ptr(), y.data_ptr(), B, H, W, C, N,
-                                        k, stride, _C.ACT[act_dw], int(residual), _stream(x)))
+                                        k, stride, _C.ACT[act_dw], int(residual), _stream(x))
     return y
 
 
-def stem_conv(images: Tensor, w: Tensor, bias: Tensor, mean, std, act: str) -> Tensor:
-    """images fp32 [B,3,H,W]; w fp32 [27,Cout]; -> bf16 [B,Ho,Wo,Cout] (normalise + 3x3 s2 + act)."""
+def stem_conv(images: Tensor, w: Tensor, bias: Tensor, mean, std, act: str, act_dtype: str = None) -> Tensor:
+    """images fp32 [B,3,H,W]; w fp32 [27,Cout]; -> fp16 / fp16/bf16 [B,Ho,Wo,Cout] (normalise + 3x3 s2 + act)."""
     _require_cuda(images, w, bias)
     B, _, H, W = images.shape
     Cout = w.shape[1]
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    y = torch.empty(B, Ho, Wo, Cout, dtype=torch.bfloat16, device=images.device)
+    y = torch.empty(B, Ho, Wo, Cout, dtype=_C.torch_dtype(act_dtype), device=images.device)
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
     with torch.cuda.device(images.device):
-        _C.check(_C.lib().dn_stem_conv(images.contiguous().data_ptr(), w.contiguous().data_ptr(),
+        _CL(y).dn_stem_conv(images.contiguous().data_ptr(), w.contiguous().data_ptr(),
                                        bias.contiguous().data_ptr(), m, s, y.data_ptr(), B, H, W, Cout, _C.ACT[act],
-                                       _stream(images)))
+                                       _stream(images))
     return y
 
 
 def se_inplace(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor) -> Tensor:
-    """x bf16 [B,HW,C] scaled in place; w1 fp32 [Cs,C]; w2t fp32 [Cs,C] (fc2 transposed)."""
+    """x fp16/bf16 [B,HW,C] scaled in place; w1 fp32 [Cs,C]; w2t fp32 [Cs,C] (fc2 transposed)."""
     _require_cuda(x, w1, b1, w2t, b2)
     B, HW, C = x.shape
     ws_bytes = _C.lib().dn_se_workspace_bytes(B, HW, C)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_se_inplace(x.data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
+        _CL(x).dn_se_inplace(x.data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
                                         w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(), B, HW, C, w1.shape[0],
-                                        ws.data_ptr(), ws_bytes, _stream(x)))
+                                        ws.data_ptr(), ws_bytes, _stream(x))
     return x
 
 
 def dwconv_se(x: Tensor, w: Tensor, bias: Tensor, k: int, stride: int, act: str, w1: Tensor, b1: Tensor, w2t: Tensor,
               b2: Tensor):
     """Depthwise conv + squeeze-excitation of its output (the middle of an InvertedResidual with use_se,
-    mobilenetv3.py:43-96).  Returns (y bf16 [B,Ho,Wo,C], pooled): pooled tells whether the depthwise launch produced the
+    mobilenetv3.py:43-96).  Returns (y fp16/bf16 [B,Ho,Wo,C], pooled): pooled tells whether the depthwise launch produced the
     SE channel sums itself (stride-1 row stream, large batch) or the SE ran its own pooling pass."""
     _require_cuda(x, w, bias, w1, b1, w2t, b2)
     B, H, W, C = x.shape
     pad = (k - 1) // 2
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    y = torch.empty(B, Ho, Wo, C, dtype=torch.bfloat16, device=x.device)
+    y = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
     ws_bytes = _C.lib().dn_se_workspace_bytes(B, Ho * Wo, C)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
     pooled = ctypes.c_int(0)
     with torch.cuda.device(x.device):
-        _C.check(_C.lib().dn_dwconv_se(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(),
+        _CL(x).dn_dwconv_se(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(),
                                        y.data_ptr(), B, H, W, C, k, stride, _C.ACT[act], w1.contiguous().data_ptr(),
                                        b1.contiguous().data_ptr(), w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(),
-                                       w1.shape[0], ws.data_ptr(), ws_bytes, ctypes.byref(pooled), _stream(x)))
+                                       w1.shape[0], ws.data_ptr(), ws_bytes, ctypes.byref(pooled), _stream(x))
     return y, bool(pooled.value)
 
 

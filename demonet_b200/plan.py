@@ -12,7 +12,7 @@ that the reference's state_dict loads unchanged:
 
 BatchNorm folding (done once per weight update, float64 -> fp32):
     s = gamma / sqrt(running_var + eps);  W' = W * s;  b' = beta - running_mean * s (+ conv_bias * s)
-Pointwise weights are then rounded to bf16 (tensor-core operands); depthwise / stem / SE weights
+Pointwise weights are then rounded to the 16-bit activation type (fp16 by default, bf16 optional: tensor-core operands); depthwise / stem / SE weights
 stay fp32.
 """
 import math
@@ -287,9 +287,11 @@ def pw_pack_factor(L: Layer) -> int:
     return 1
 
 
-def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
-    """Fold + lay out every layer.  Returns (blob, per-layer offsets dict(w, b[, w2, b2]))."""
+def pack_weights(plan: Plan, sd, act_dtype: str = None) -> Tuple[bytes, List[Dict[str, int]]]:
+    """Fold + lay out every layer.  Returns (blob, per-layer offsets dict(w, b[, w2, b2])).  `act_dtype` ("fp16" /
+    "bf16"): the 16-bit type of the tensor-core operands = the activation storage type of the library that will run."""
     chunks, offs, pos = [], [], 0
+    h16 = _C.torch_dtype(act_dtype)
 
     def put(arr: np.ndarray):
         nonlocal pos
@@ -317,12 +319,12 @@ def pack_weights(plan: Plan, sd) -> Tuple[bytes, List[Dict[str, int]]]:
             w = wf.float().permute(1, 2, 3, 0).reshape(27, L.cout).contiguous().numpy()
         elif L.kind == "dw":      # [C,1,k,k] -> [k*k][C] fp32
             w = wf.float().reshape(L.cout, L.k * L.k).t().contiguous().numpy()
-        else:                     # pw: [N,K,1,1] -> [N][K] bf16 (block-diagonal when pixels are packed)
-            w2 = wf.float().reshape(L.cout, L.cin).to(torch.bfloat16)
+        else:                     # pw: [N,K,1,1] -> [N][K] fp16 / bf16 (block-diagonal when pixels are packed)
+            w2 = wf.float().reshape(L.cout, L.cin).to(h16)
             pf = pw_pack_factor(L)
             raw_w, raw_b = w2.contiguous().view(torch.int16).numpy(), bias
             if pf > 1:
-                w2 = torch.block_diag(*([w2.float()] * pf)).to(torch.bfloat16)
+                w2 = torch.block_diag(*([w2.float()] * pf)).to(h16)
                 bias = np.tile(bias, pf)
             w = w2.contiguous().view(torch.int16).numpy()
             entry = {"w": put(w), "b": put(bias)}

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 2          /* 2: dn_op.lane / act2, dn_model_desc.pipeline_slots, fused ops, SE workspace */
+#define DN_ABI_VERSION 3          /* 3: dn_postprocess_scored, dn_engine_get_stats, activation dtype builds */
 
 typedef enum {
     DN_OK = 0,
@@ -160,6 +160,20 @@ int dn_postprocess(const float* cls_logits, const float* bbox_regression, const 
                    const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
                    float* out_scores, int64_t* out_labels, int32_t* out_counts, void* stream);
 
+/* The same post-processing entered where the reference already holds softmax scores and decoded, clipped boxes
+ * (generalized_ssd.py:361-363): per-class threshold / top-k (:368-382), batched NMS (:389) and keep[:D] (:390-396) run
+ * through exactly the kernels dn_postprocess and the engine use (class sort, warp / CTA NMS with lazy rounds, top-D
+ * merge); only the softmax + decode arithmetic is skipped.  This is the parity entry of SURVEY.md 8(a) N1: fed the
+ * reference's own scores and boxes, (out_priors, out_labels) must equal the (anchor, class) identity of
+ * _batched_nms_vanilla(...)[:detections_per_img] bit for bit, and out_scores / out_boxes are copies of the inputs.
+ * scores fp32 [B,P,K] (column 0 = background, ignored); boxes fp32 [B,P,4] xyxy.
+ * out_priors (may be NULL): int32 [B,D], anchor index of every detection, -1 in the padding.
+ * out_rounds (may be NULL): int32 [B], the lazy-NMS round (0, 1, 2) that made the image final -- lets a test prove
+ * that the deeper rounds were exercised. */
+int dn_postprocess_scored(const float* scores, const float* boxes, int B, const dn_postprocess_params* p, void* workspace,
+                          size_t workspace_bytes, float* out_boxes, float* out_scores, int64_t* out_labels,
+                          int32_t* out_counts, int32_t* out_priors, int32_t* out_rounds, void* stream);
+
 /* measurement aid: same as dn_postprocess, each of its 3 kernels launched `iters` times between CUDA
  * events; ms3_host[0..3) = mean ms of softmax+decode, per-class top-k+NMS, top-D merge.  Synchronises. */
 int dn_postprocess_profile(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
@@ -264,7 +278,8 @@ int dn_engine_forward_host(dn_engine* e, const float* images_host, int B, float*
 int dn_engine_forward_host_u8(dn_engine* e, const uint8_t* images_host, int B, float* out_boxes_host,
                               float* out_scores_host, int64_t* out_labels_host, int32_t* out_counts_host,
                               void* stream);
-/* device pointers of intermediate arena buffers (valid after a forward), for stage-by-stage parity */
+/* device pointers of intermediate arena buffers (valid after a forward), for stage-by-stage parity; in pipeline mode
+ * dn_engine_copy_buffer reads the arena of the slot that ran the forward issued last */
 int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out);
 /* enqueue a device-to-device copy of the first `bytes` bytes of an arena buffer into dst_dev */
 int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, size_t bytes, void* stream);
@@ -273,6 +288,17 @@ int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, size_t bytes,
  * ms_out_host[0 .. n_ops + 3) (the n_ops layers in plan order, then the 3 post-processing kernels).
  * Synchronises the stream; a measurement aid for bench.py, not part of the hot path. */
 int dn_engine_profile(dn_engine* e, const float* images_dev, int B, int iters, float* ms_out_host, void* stream);
+/* What the forward issued last actually ran (parity tests assert that the benchmarked configuration -- fused blocks,
+ * pooled squeeze-excitation, graph replay, two slots -- is the one being compared with the oracle). */
+typedef struct {
+    int32_t launches_per_forward;
+    int32_t fused_pwdw, fused_dwpw;      /* fused expand+depthwise / depthwise+project launches in the plan          */
+    int32_t se_layers, se_pooled;        /* squeeze-excitation layers / those whose pooling the depthwise launch did */
+    int32_t pipeline_slots, last_slot;   /* 1 or 2 engine instances; the slot of the forward issued last             */
+    int32_t act_dtype;                   /* storage type of the activations: 0 = bf16, 1 = fp16                      */
+    int64_t forwards, graph_replays;     /* forwards enqueued so far / those that were one cudaGraphLaunch           */
+} dn_engine_stats;
+int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out);
 /* number of kernel launches one forward enqueues (for bench.py's gpu_launches) */
 int dn_engine_launches_per_forward(dn_engine* e);
 size_t dn_engine_device_bytes(dn_engine* e);

@@ -18,6 +18,9 @@ Modes
          BatchNorm folded into the conv in float64 then rounded to fp32, pointwise-GEMM
          weights rounded to bf16, every stored activation rounded to bf16, fp32 accumulate,
          head 1x1 outputs / softmax / decode kept in fp32.
+  fp16 : the bf16 contract with IEEE half instead of bfloat16 (stored activations and pointwise-GEMM weights
+         rounded to fp16: same bytes, 3 more mantissa bits, range 65504).
+  wf16 : like w16 with fp16 GEMM weights.
   w16  : like bf16 but WITHOUT rounding the activations (folded BN + bf16 GEMM weights only).  The
          bf16 chain is chaotic on a random-weight network (a different summation order alone moves
          the logits by rms 0.14, see DESIGN.md "Numerics"), so plan-wiring tests compare in this
@@ -55,6 +58,10 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def _fp16(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
 def _ident(x):
     return x
 
@@ -83,11 +90,13 @@ def fold_bn(w, gamma, beta, mean, var, eps, conv_bias=None):
 
 class _Net:
     def __init__(self, sd, mode, eps):
-        assert mode in ("fp32", "bf16", "w16")
+        assert mode in ("fp32", "bf16", "w16", "fp16", "wf16")
         self.sd = sd
         self.mode = mode
         self.eps = eps
-        self.rnd = _bf16 if mode == "bf16" else _ident          # rounding of stored activations
+        # rounding of stored activations / of the tensor-core (pointwise GEMM) weights
+        self.rnd = {"bf16": _bf16, "fp16": _fp16}.get(mode, _ident)
+        self.wrnd = _fp16 if mode in ("fp16", "wf16") else _bf16
 
     # ConvBNActivation: conv (no bias) -> BN -> act      mobilenetv2.py:32-55
     def cba(self, x, prefix, stride, act, depthwise=False, conv_key=".0", bn_key=".1", conv_bias=False,
@@ -106,7 +115,7 @@ class _Net:
             return y if residual is None else y + residual          # mobilenetv3.py:95-99
         wf, bf = fold_bn(w, g, b, m, v, self.eps, cb)
         if k == 1 and not depthwise:
-            wf = _bf16(wf)
+            wf = self.wrnd(wf)
         y = _act(F.conv2d(x, wf, bf, stride, pad, 1, groups), act)
         if residual is not None:        # the engine adds the residual in the GEMM epilogue: one rounding
             y = y + residual
@@ -116,7 +125,7 @@ class _Net:
     def conv_bias(self, x, prefix):
         w, b = self.sd[prefix + ".weight"], self.sd[prefix + ".bias"]
         if self.mode != "fp32":
-            w = _bf16(w)
+            w = self.wrnd(w)
         return F.conv2d(x, w, b)
 
     # SqueezeExcitation                                   mobilenetv3.py:22-40

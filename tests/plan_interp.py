@@ -3,7 +3,7 @@
 Executes exactly what the C engine is given -- the dn_op array, the packed weight blob and the arena
 buffer assignment -- with plain torch ops on the CPU, including the buffer reuse, so that plan wiring
 bugs (wrong key, wrong residual, wrong head offset, a buffer freed too early) are caught without a GPU.
-Numerics follow the engine contract (bf16 storage, fp32 accumulate)."""
+Numerics follow the engine contract (fp16 or bf16 storage, fp32 accumulate)."""
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -15,13 +15,10 @@ def _act(x, a):
     return {0: lambda v: v, 1: F.relu, 2: F.relu6, 3: F.hardswish}[a](x)
 
 
-def _round_bf16(x):
-    return x.to(torch.bfloat16).to(torch.float32)
-
-
-def run_plan(plan, blob, ops, bufs, logits_buf, bbox_buf, images, mean, std, round_activations=True):
+def run_plan(plan, blob, ops, bufs, logits_buf, bbox_buf, images, mean, std, round_activations=True, act_dtype=None):
     B = images.shape[0]
-    _bf16 = _round_bf16 if round_activations else (lambda v: v)
+    h16 = _C.torch_dtype(act_dtype)
+    _bf16 = (lambda v: v.to(h16).to(torch.float32)) if round_activations else (lambda v: v)
     raw = np.frombuffer(blob, dtype=np.uint8)
     arena = [torch.full((B * e,), float("nan")) for e, _ in bufs]
 
@@ -29,7 +26,7 @@ def run_plan(plan, blob, ops, bufs, logits_buf, bbox_buf, images, mean, std, rou
         return torch.from_numpy(raw[off:off + 4 * n].view(np.float32).copy())
 
     def bf16w(off, n):
-        return torch.from_numpy(raw[off:off + 2 * n].view(np.int16).copy()).view(torch.bfloat16).float()
+        return torch.from_numpy(raw[off:off + 2 * n].view(np.int16).copy()).view(h16).float()
 
     for op in ops:
         hi, wi, ci, ho, wo, co = op.h_in, op.w_in, op.c_in, op.h_out, op.w_out, op.c_out

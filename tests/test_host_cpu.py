@@ -67,33 +67,35 @@ def test_plan_shapes():
     assert np.array_equal(a, boxes_np.default_boxes(p.grid_sizes, (320, 320)))
 
 
-def _interp(plan, sd, x, mean, std, round_activations):
-    blob, offs = dplan.pack_weights(plan, sd)
+def _interp(plan, sd, x, mean, std, round_activations, act_dtype):
+    blob, offs = dplan.pack_weights(plan, sd, act_dtype)
     t2b, bufs, lb, bb = dplan.assign_buffers(plan)
     ops = dplan.build_ops(plan, offs, t2b, lb, bb)
-    return run_plan(plan, blob, ops, bufs, lb, bb, x, mean, std, round_activations)
+    return run_plan(plan, blob, ops, bufs, lb, bb, x, mean, std, round_activations, act_dtype)
 
 
-def _check_plan(model, sd, x, mean, std, forward_raw):
+def _check_plan(model, sd, x, mean, std, forward_raw, act_dtype="fp16"):
     """dn_op array + packed blob + arena reuse, interpreted on the CPU, against the oracle.
     Tight in `w16` mode (no activation rounding -> only fp32 summation noise); statistical in `bf16`
     mode, where rounding flips make the chain chaotic (the oracle itself moves by rms 0.14 on the
     logits when only its summation order changes)."""
     with torch.no_grad():
-        cls, reg = _interp(model.plan, sd, x, mean, std, False)
-        ocls, oreg, _ = forward_raw(sd, x, "w16")
+        cls, reg = _interp(model.plan, sd, x, mean, std, False, act_dtype)
+        ocls, oreg, _ = forward_raw(sd, x, "w16" if act_dtype == "bf16" else "wf16")
         assert not torch.isnan(cls).any() and not torch.isnan(reg).any()
         assert (cls - ocls).abs().max() < 2e-3 and (reg - oreg).abs().max() < 2e-3
-        cls, reg = _interp(model.plan, sd, x, mean, std, True)
-        ocls, oreg, _ = forward_raw(sd, x, "bf16")
-        assert (cls - ocls).pow(2).mean().sqrt() < 0.3 and (reg - oreg).pow(2).mean().sqrt() < 0.3
+        cls, reg = _interp(model.plan, sd, x, mean, std, True, act_dtype)
+        ocls, oreg, _ = forward_raw(sd, x, act_dtype)
+        tol = 0.3 if act_dtype == "bf16" else 0.05      # fp16 storage: 8x finer rounding
+        assert (cls - ocls).pow(2).mean().sqrt() < tol and (reg - oreg).pow(2).mean().sqrt() < tol
         assert ocls.std() > 3.0
 
 
-def test_v3_plan_reproduces_oracle():
+@pytest.mark.parametrize("act_dtype", ["fp16", "bf16"])
+def test_v3_plan_reproduces_oracle(act_dtype):
     model = demonet_b200.ssdlite320_mobilenet_v3_large()
     sd = weights.seeded_state_dict(model.state_dict())
-    _check_plan(model, sd, weights.synthetic_images(1, 320), [0.5] * 3, [0.5] * 3, net_ref.v3_forward_raw)
+    _check_plan(model, sd, weights.synthetic_images(1, 320), [0.5] * 3, [0.5] * 3, net_ref.v3_forward_raw, act_dtype)
 
 
 @pytest.mark.parametrize("S", [300, 512])
@@ -109,11 +111,12 @@ def test_c_abi_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "demonet_b200.h")).read()
     declared = set(re.findall(r"\b(dn_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
-    handle = ctypes.CDLL(_C.LIB_PATH)
-    for name in declared:
-        assert hasattr(handle, name), "missing export: " + name
+    for dt in _C.ACT_DTYPES:              # one library per activation storage type, same ABI
+        handle = ctypes.CDLL(_C.LIB_PATHS[dt])
+        for name in declared:
+            assert hasattr(handle, name), "missing export in the %s build: %s" % (dt, name)
+        assert _C.lib(dt).dn_abi_version() == _C.ABI_VERSION == 3
     assert declared == set(_C.EXPORTED_SYMBOLS)
-    assert _C.lib().dn_abi_version() == _C.ABI_VERSION == 2
 
 
 def test_c_abi_argument_validation_without_gpu():

@@ -1,5 +1,7 @@
-"""Fused post-processing (softmax + decode + threshold + top-k + NMS + top-D) on the GPU against the
-reference's results (golden) and the NumPy/C oracle."""
+"""Fused post-processing (softmax + decode + threshold + top-k + NMS + top-D) on the GPU, entered with LOGITS, against
+the reference's results (golden) and the NumPy/C oracle.  What is tested here is the floating-point front (softmax with
+ex2.approx, decode with expf) -- the index-level, bit-exact parity of everything behind it (class sort, lazy warp / CTA
+NMS, top-D merge) is tests/test_nms_engine_path_gpu.py, which feeds the reference's own scores and boxes."""
 import os
 
 import numpy as np
@@ -13,10 +15,12 @@ pytestmark = pytest.mark.gpu
 GRIDS_320 = [(20, 20), (10, 10), (5, 5), (3, 3), (2, 2), (1, 1)]
 
 
-def _match(det, want_labels, want_scores, want_boxes, score_tol=3e-6, box_tol=2e-2, min_frac=0.99):
-    """Detections must agree with the reference up to exp()-ulp effects: same count; position by
-    position same label and score within score_tol for >= min_frac of the rows (a 1-ulp score
-    difference can swap two neighbours), boxes within box_tol pixels on the matching rows."""
+def _match(det, want_labels, want_scores, want_boxes, score_tol=3e-6, box_tol=1e-3, min_frac=0.99):
+    """Detections must agree with the reference up to exp()-ulp effects: same count; position by position same label
+    and score within score_tol (ex2.approx: <= 1e-7 absolute on a score, plus the reduction order of the row sum) for
+    >= min_frac of the rows -- a last-bit score difference can swap two neighbours of a near-tie, or move a candidate
+    across the threshold / top-k cut and shift the tail -- and boxes within box_tol = 1e-3 px on the matching rows
+    (expf vs the host libm: 2 ulp of a <= 320 px coordinate is 8e-5 px)."""
     labels, scores, boxes = det["labels"].cpu().numpy(), det["scores"].cpu().numpy(), det["boxes"].cpu().numpy()
     assert labels.shape == want_labels.shape, (labels.shape, want_labels.shape)
     same = (labels == want_labels) & (np.abs(scores - want_scores) <= score_tol)
