@@ -1,14 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the SSDLite inference hot path (BASELINE.json metric: SSDLite320 images/sec).
+"""Benchmark of the SSDLite inference hot path (BASELINE.json metric: SSDLite320 images/sec at 1/2/4/8 B200 vs the
+host-CPU reference; decode+NMS us/img).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+  python bench.py --gpus N --steps K --warmup W              # this repo's CUDA engine, BASELINE.json configs[1]
+  python bench.py --config {2,3,4,5} ...                     # the other BASELINE.json configurations, same JSON schema
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port) on the host cores
 
-One "step" = forward + post-processing of one batch of synthetic 320x320 images per GPU
-(config 2 of BASELINE.json: ssdlite320_mobilenet_v3_large, 91 classes, batch 256, bf16).
-For N > 1 the driver launches this file under torch.distributed.run; the image batch is sharded
-(256 per GPU, weak scaling), there is no inter-GPU traffic on the hot path and one NCCL all-gather
-of the fixed-shape detections closes each step.  Prints ONE JSON line on rank 0.
+One "step" = forward + post-processing of one batch of synthetic images per GPU.
+  config 2 (default)  ssdlite320_mobilenet_v3_large, 91 classes, batch 256 per GPU (weak scaling over N GPUs)
+  config 3            the same network, GLOBAL batch 2048 split over the N GPUs (strong scaling) + detection gather
+  config 4            post-processing stress: 3234 anchors x 91 classes, thr .001, top-k 400, NMS .55, batch 1024 (us/img)
+  config 5            ssd_lite_mobilenet_v2, 21 classes, 512x512, batch 512 per GPU
+For N > 1 the driver launches this file under torch.distributed.run: images are sharded, there is no inter-GPU traffic on
+the hot path, and ONE NCCL all-gather of the fixed-shape detections closes each step.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -22,10 +26,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "ssdlite320_mobilenet_v3_large images/sec (forward + postprocess)"
-UNIT = "img/s"
-S = 320
-NUM_CLASSES = 91
+CONFIGS = {
+    2: dict(model="v3", S=320, K=91, batch=256, scaling="weak", D=300, unit="img/s", hib=True,
+            metric="ssdlite320_mobilenet_v3_large images/sec (forward + postprocess)",
+            name="ssdlite320_mobilenet_v3_large, 91 classes, 320x320, batch %d per GPU, %s activations, forward + "
+                 "softmax/decode/top-k/NMS/top-300 (BASELINE.json configs[1])"),
+    3: dict(model="v3", S=320, K=91, global_batch=2048, scaling="strong", D=300, unit="img/s", hib=True,
+            metric="ssdlite320_mobilenet_v3_large images/sec (forward + postprocess)",
+            name="ssdlite320_mobilenet_v3_large, 91 classes, 320x320, GLOBAL batch 2048 sharded (%d per GPU), %s activations, "
+                 "forward + postprocess + NCCL detection gather (BASELINE.json configs[2])"),
+    4: dict(model="post", S=320, K=91, batch=1024, scaling="weak", D=300, unit="us/img", hib=False,
+            metric="decode+NMS microseconds per image (softmax + decode + threshold + top-k + batched NMS + top-300)",
+            name="postprocess stress: 3234 anchors x 91 classes, logits N(0,4^2) seed 7, score_thresh 0.001, top-k 400, "
+                 "NMS IoU 0.55, D 300, batch %d per GPU (BASELINE.json configs[3])"),
+    5: dict(model="v2", S=512, K=21, batch=512, scaling="weak", D=100, unit="img/s", hib=True,
+            metric="ssd_lite_mobilenet_v2 512x512 images/sec (forward + postprocess)",
+            name="ssd_lite_mobilenet_v2, VOC 21 classes, 512x512, batch %d per GPU, %s activations, forward + legacy PostProcess "
+                 "(thr 0.5, NMS 0.45, top-100) (BASELINE.json configs[4])"),
+}
 
 
 def parse():
@@ -34,62 +52,132 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="images per CPU-baseline step")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (1-based)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the configuration's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images per CPU-baseline step (default 32, BASELINE.md section 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the e2e / API / per-kernel legs (timing runs only)")
     ap.add_argument("--layers", action="store_true", help="also print the per-layer time table to stderr")
+    ap.add_argument("--act-dtype", default=None, choices=["fp16", "bf16"],
+                    help="activation storage type (default: the library default, fp16)")
     ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
                     help="batches in flight per GPU (2 = the engine's pipeline mode, 1 = one forward at a time)")
     return ap.parse_args()
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU path: the oracle's torch port of the reference (conv stack through the same ATen CPU kernels
-# the reference uses + SSD.postprocess_detections restated with the same torch/torchvision calls)
+# CPU path: the oracle's torch port of the reference (conv stack through the same ATen CPU kernels the reference
+# uses + SSD.postprocess_detections restated with the same torch / torchvision calls and Python loops).
+# Protocol of BASELINE.md section 3: one process, all host cores, batch 32, warm-up + timed iterations, per-stage
+# milliseconds; plus the reference-as-shipped evaluation setting (1 thread, batch 1: engine.py:73-75, train.py:141-144).
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(n_images, steps, warmup):
+def cpu_reference(cfg_id, n_images, steps, warmup, threads=None):
+    import numpy as np
     import torch
-    from oracle import net_ref              # the CPU leg is the one place bench.py executes oracle/
+    from oracle import boxes_np, net_ref     # the CPU leg is the one place bench.py executes oracle/
     from demonet_b200 import plan as dplan, seeded as weights
     import demonet_b200
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    cfg = CONFIGS[cfg_id]
+    cores = threads or host_cores()
     torch.set_num_threads(cores)
-    model = demonet_b200.ssdlite320_mobilenet_v3_large()          # only for the state_dict template / plan
-    sd = weights.seeded_state_dict(model.state_dict())
-    anchors = torch.from_numpy(dplan.default_boxes(model.plan))
-    x = weights.synthetic_images(n_images, S)
+    S, K = cfg["S"], cfg["K"]
+    stages = {}
+    if cfg["model"] == "post":
+        g = torch.Generator().manual_seed(7)
+        logits = torch.randn(n_images, 3234, K, generator=g) * 4.0
+        bbox = torch.randn(n_images, 3234, 4, generator=g) * 1.5
+        anchors = torch.from_numpy(dplan.default_boxes(dplan.plan_ssdlite320_mobilenet_v3_large()))
 
-    def step():
-        with torch.no_grad():
-            cls, reg, _ = net_ref.v3_forward_raw(sd, x, "fp32", NUM_CLASSES)
-            return net_ref.postprocess_detections_torch(cls, reg, anchors, (S, S))
+        def step():
+            t0 = time.perf_counter()
+            net_ref.postprocess_detections_torch(logits, bbox, anchors, (S, S), 0.001, 0.55, 300, 400)
+            stages["postprocess"] = stages.get("postprocess", 0.0) + time.perf_counter() - t0
+    else:
+        if cfg["model"] == "v3":
+            model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=K)      # state_dict template / plan only
+            fwd = net_ref.v3_forward_raw
+        else:
+            model = demonet_b200.ssd_lite_mobilenet_v2(image_size=S, num_classes=K)
+            fwd = net_ref.v2_forward_raw
+        sd = weights.seeded_state_dict(model.state_dict())
+        x = weights.synthetic_images(n_images, S)
+
+        def step():
+            with torch.no_grad():
+                cls, reg, _ = fwd(sd, x, "fp32", K, times=stages)
+                t0 = time.perf_counter()
+                anchors = dplan.default_boxes(model.plan)          # DefaultBoxGenerator runs every forward in the reference
+                stages["anchors"] = stages.get("anchors", 0.0) + time.perf_counter() - t0
+                t0 = time.perf_counter()
+                if cfg["model"] == "v3":
+                    net_ref.postprocess_detections_torch(cls, reg, torch.from_numpy(anchors), (S, S))
+                else:
+                    sc = torch.softmax(cls, -1).numpy()
+                    for i in range(cls.shape[0]):
+                        boxes_np.legacy_postprocess(None, reg[i].numpy(), anchors, (S, S), score_thresh=0.5, scores=sc[i])
+                stages["postprocess"] = stages.get("postprocess", 0.0) + time.perf_counter() - t0
     for _ in range(warmup):
         step()
+    stages.clear()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return n_images * steps / dt, dt / steps * 1e3, cores
+    per_img = {k: round(v / (steps * n_images) * 1e3, 3) for k, v in stages.items()}
+    return {"img_per_s": n_images * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": cores,
+            "stage_ms_per_img": per_img, "batch": n_images, "steps": steps}
+
+
+def cpu_value(cfg_id, r):
+    """the configuration's metric from a cpu_reference() result"""
+    return 1e6 / r["img_per_s"] if CONFIGS[cfg_id]["unit"] == "us/img" else r["img_per_s"]
+
+
+def cpu_baseline_block(cfg_id, n_images, steps, warmup, as_shipped=True):
+    r = cpu_reference(cfg_id, n_images, steps, warmup)
+    blk = {"value": cpu_value(cfg_id, r), "unit": CONFIGS[cfg_id]["unit"], "cores": r["cores"], "kind": "port",
+           "sample": "%d images/step x %d timed steps (+%d warm-up), fp32, %d threads, one process; oracle torch port of "
+                     "SSD.forward (the reference is pure Python/PyTorch: same ATen CPU kernels, same image x class loops); "
+                     "%.0f ms/step" % (n_images, steps, warmup, r["cores"], r["ms_per_step"]),
+           "stage_ms_per_img": r["stage_ms_per_img"]}
+    if as_shipped:
+        # the reference's own evaluation loop pins ONE thread and feeds batch 1 (engine.py:73-75, train.py:141-144)
+        n1 = 3 if CONFIGS[cfg_id]["model"] != "post" else 2
+        r1 = cpu_reference(cfg_id, 1, n1, 1, threads=1)
+        blk["as_shipped"] = {"value": cpu_value(cfg_id, r1), "unit": CONFIGS[cfg_id]["unit"], "cores": 1,
+                             "sample": "batch 1, 1 thread, %d timed images (reference-as-shipped: engine.py:73-75, "
+                                       "train.py:141-144)" % n1, "stage_ms_per_img": r1["stage_ms_per_img"]}
+    return blk
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, ms, cores = cpu_reference_rate(args.cpu_sample, args.steps, args.warmup)
-    sample = "%d images/step, fp32, %d threads; oracle port of SSD.forward (reference is pure Python/PyTorch)" % (
-        args.cpu_sample, cores)
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ssdlite320_mobilenet_v3_large 91 classes 320x320 forward+postprocess on the host CPU",
-                       "batch_per_step": args.cpu_sample, "weights": "seeded re-init 1234", "images": "torch.rand seed 1"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cfg = CONFIGS[args.config]
+    n = args.cpu_sample or (8 if cfg["model"] == "post" else (8 if cfg["model"] == "v2" else 32))
+    steps = max(1, min(args.steps, 10 if cfg["model"] == "v3" else 4))     # bounded: the whole run ends within minutes
+    warm = max(1, min(args.warmup, 3))
+    blk = cpu_baseline_block(args.config, n, steps, warm)
+    workload = {"v3": "ssdlite320_mobilenet_v3_large 91 classes 320x320 forward+postprocess on the host CPU",
+                "v2": "ssd_lite_mobilenet_v2 21 classes 512x512 forward+legacy PostProcess on the host CPU",
+                "post": "postprocess stress (3234 anchors x 91 classes, thr .001, top-k 400, NMS .55) on the host CPU"}[cfg["model"]]
+    line = {"impl": "reference", "metric": cfg["metric"], "value": blk["value"], "unit": cfg["unit"], "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": None, "higher_is_better": cfg["hib"], "scaling": cfg["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "baseline_config": args.config, "batch_per_step": n,
+                       "weights": "seeded re-init 1234", "images": "torch.rand seed 1",
+                       "protocol": "BASELINE.md section 3 (bounded: %d timed steps)" % steps},
+            "cpu_baseline": blk,
+            "e2e": {"value": blk["value"], "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["ms_per_step"] = 1e3 * n / blk["value"] if cfg["unit"] == "img/s" else blk["value"] * n / 1e3
     print(json.dumps(line), file=_claim_stdout(), flush=True)
 
 
@@ -187,20 +275,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # roofline bookkeeping: algorithmic bytes / flops of every launch of the plan
 # ------------------------------------------------------------------------------------------------
-def layer_costs(plan, B):
-    """[(kernel_name, bytes, flops)] per launch, in plan order, then the 3 post-processing kernels.
+def layer_costs(plan, B, D):
+    """[(kernel_name, bytes, flops)] per launch, in plan order, then the 3 post-processing entries of dn_engine_profile.
     Algorithmic bytes = input + output activations at their stored width + weights."""
     out = []
     P, K = plan.num_priors, plan.num_classes
     from demonet_b200 import plan as dplan
-    fused = set(dplan.fused_pairs(plan)) if int(os.environ.get("DN_FUSE", "1")) else set()
-    fused_dp = set(dplan.fused_dwpw_pairs(plan)) if int(os.environ.get("DN_FUSE", "1")) and dplan.dwpw_fusion_enabled() else set()
+    fuse = int(os.environ.get("DN_FUSE", "1"))
+    fused = set(dplan.fused_pairs(plan)) if fuse else set()
+    fused_dp = set(dplan.fused_dwpw_pairs(plan)) if fuse and dplan.dwpw_fusion_enabled() else set()
     for i, L in enumerate(plan.layers):
         hi, wi, ho, wo = L.h_in, L.w_in, L.h_out, L.w_out
         if i in fused:            # expand + depthwise in one launch: the expanded tensor is not algorithmic traffic any more
-            D = plan.layers[i + 1]
-            out.append(("pwdw_fused_kernel", B * (hi * wi * L.cin + D.h_out * D.w_out * D.cout) * 2 + L.cin * L.cout * 2 + D.k * D.k * D.cout * 4,
-                        2 * B * (hi * wi * L.cin * L.cout + D.h_out * D.w_out * D.cout * D.k * D.k)))
+            Dn = plan.layers[i + 1]
+            out.append(("pwdw_fused_kernel", B * (hi * wi * L.cin + Dn.h_out * Dn.w_out * Dn.cout) * 2 + L.cin * L.cout * 2 + Dn.k * Dn.k * Dn.cout * 4,
+                        2 * B * (hi * wi * L.cin * L.cout + Dn.h_out * Dn.w_out * Dn.cout * Dn.k * Dn.k)))
             continue
         if i - 1 in fused or i - 1 in fused_dp:
             out.append(("(fused into the previous launch)", 0, 0))
@@ -211,26 +300,54 @@ def layer_costs(plan, B):
                         2 * B * hi * wi * (L.cin * L.k * L.k + L.cin * Pj.cout)))
             continue
         if L.kind == "stem":
-            out.append(("stem_conv_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
+            out.append(("stem_tma_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
         elif L.kind == "dw":
-            out.append(("dwconv_kernel", B * (hi * wi + ho * wo) * L.cin * 2 + L.k * L.k * L.cin * 4,
+            out.append(("dwconv kernels (stream / stream2 / tma / direct)", B * (hi * wi + ho * wo) * L.cin * 2 + L.k * L.k * L.cin * 4,
                         2 * B * ho * wo * L.cin * L.k * L.k))
         elif L.kind == "se":
-            out.append(("se_pool+fc1+fc2+scale kernels", B * hi * wi * L.cin * 2 * 2 + 2 * L.cin * L.se_mid * 4,
+            out.append(("se kernels (fc1 + fc2 + scale)", B * hi * wi * L.cin * 2 * 2 + 2 * L.cin * L.se_mid * 4,
                         2 * B * 2 * L.cin * L.se_mid))
         else:
             ob = 4 if L.head else 2
             res = B * hi * wi * L.cout * 2 if L.res else 0
             out.append(("pwconv_tc_kernel", B * hi * wi * (L.cin * 2 + L.cout * ob) + res + L.cin * L.cout * 2,
                         2 * B * hi * wi * L.cin * L.cout))
-    out.append(("softmax_decode_kernel", B * (P * K * 4 + P * 16) + P * 16 + B * (P * (K - 1) * 4 + P * 16), 0))
-    out.append(("class_sort+select+nms kernels", B * (K - 1) * P * 4, 0))
-    out.append(("merge_topd_kernel", B * plan_D(plan) * 28, 0))
+    out.append(("softmax_decode_kernel (+ histogram, thresholds)", B * (P * K * 4 + P * 16) + P * 16 + B * (P * (K - 1) * 4 + P * 16), 0))
+    out.append(("class_sort + nms + merge kernels (lazy rounds)", B * (K - 1) * P * 4 + B * D * 28, 0))
+    out.append(("(empty event bracket)", 0, 0))
     return out
 
 
-def plan_D(plan):
-    return 300
+NCU_FAMILIES = {"dwconv kernels (stream / stream2 / tma / direct)": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
+                "pwconv_tc_kernel": ["pwconv_tc_kernel"], "pwdw_fused_kernel": ["pwdw_fused_kernel"],
+                "dwpw_fused_kernel": ["dwpw_fused_kernel"], "stem_tma_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
+                "se kernels (fc1 + fc2 + scale)": ["se_pool_kernel", "se_fc1_kernel", "se_fc2_kernel", "se_scale_kernel", "se_fc_kernel"],
+                "softmax_decode_kernel (+ histogram, thresholds)": ["softmax_decode_kernel", "pick_thresholds_kernel"],
+                "class_sort + nms + merge kernels (lazy rounds)": ["class_sort_kernel", "class_nms_warp_kernel", "class_nms_cta_kernel", "merge_topd_kernel"]}
+
+
+def ncu_traffic(family, B):
+    """DRAM bytes per launch of a kernel family from the newest committed ncu launch list of this command
+    (profiles/rNN_ncu_launches_vM.json: dram__bytes_read.sum + dram__bytes_write.sum), or (None, None)."""
+    try:
+        import glob
+        import re
+
+        def _ver(path):
+            m = re.search(r"r(\d+)_ncu_launches_v(\d+)", os.path.basename(path))
+            return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")), key=_ver)
+        if not cands or B != 256:
+            return None, None
+        doc = json.load(open(cands[-1]))
+        nl = doc["kernels"]
+        names = NCU_FAMILIES.get(family, [family])
+        names = names + ["dn::" + n for n in names]
+        tb = sum(nl[n]["dram_bytes"] for n in names if n in nl)
+        tl = sum(nl[n]["launches"] for n in names if n in nl)
+        return (tb / tl, os.path.basename(cands[-1])) if tl else (None, None)
+    except Exception:
+        return None, None
 
 
 _JSON_OUT = None
@@ -247,19 +364,32 @@ def _claim_stdout():
     return _JSON_OUT
 
 
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": float(mp["hbm_gbs"]), "bf16_tflops": float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])),
+                 "src": "measured (MEASURED_PEAKS.json hbm_gbs)"}
+    except Exception:
+        pass
+    return peaks
+
+
 def main():
     args = parse()
     _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
+    import ctypes
     import torch
     import torch.distributed as dist
     import demonet_b200
-    from demonet_b200 import _C
+    from demonet_b200 import _C, dist as ddist, plan as dplan
     from demonet_b200 import seeded as weights      # seeded re-init recipe + synthetic images
-    import ctypes
+    from demonet_b200.module import make_post_params
 
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,70 +398,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION/INFO prints to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    B, D = args.batch, 300
-
-    # --pipeline 2 (default): two batches in flight on two engine instances (dn_model_desc.pipeline_slots): the
-    # latency-bound tail of batch i (small layers, NMS rounds) overlaps the bandwidth-bound head of batch i+1
-    model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=NUM_CLASSES, pipeline_slots=args.pipeline)
-    model.load_state_dict(weights.seeded_state_dict(model.state_dict()))
-    model = model.to(dev)
-    eng = model.reserve(B, dev)
-    lib = _C.lib()
+    S, K, D = cfg["S"], cfg["K"], cfg["D"]
+    if "global_batch" in cfg:
+        lo, hi = ddist.shard_range(cfg["global_batch"], rank, world)
+        B = args.batch or (hi - lo)
+    else:
+        B = args.batch or cfg["batch"]
     stream = torch.cuda.current_stream(dev)
     nslot = 2 if args.pipeline == 2 else 1
-
-    # inputs resident in HBM (value) and in pinned host memory (e2e); different images per rank
-    imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
-    imgs = imgs_host.to(dev)
-    # one packed output buffer per rank and slot so that the gather of a batch is ONE collective
-    from demonet_b200 import dist as ddist
-    packed_det = [ddist.PackedDetections(B, D, dev) for _ in range(nslot)]
-    io = [p.as_io() for p in packed_det]
-    gathered = torch.empty(world * packed_det[0].buffer.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
-    host_outs = [{"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
-                  "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
-                  "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
-                  "counts": torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(nslot)]
-    host_out = host_outs[0]
-    tick = {"dev": 0, "host": 0, "u8": 0, "gather_owed": False}
-
-    def step_device():
-        # forward of batch i on slot i % nslot; with N > 1 every step closes with ONE all-gather of detections: those
-        # of this batch, or in pipeline mode those of the previous batch (its forward is joined, this one keeps running)
-        k = tick["dev"] % nslot
-        tick["dev"] += 1
-        eng.forward(imgs, io[k])
-        if world > 1:
-            if nslot == 1:
-                ddist.gather_detections(packed_det[0], gathered)
-            else:
-                if tick["gather_owed"]:
-                    eng.join_previous()
-                    ddist.gather_detections(packed_det[k ^ 1], gathered)
-                tick["gather_owed"] = True
-
-    def finish_device():
-        # drain the pipeline inside the timed region: join the last forward(s) and gather the batch still owed
-        if nslot == 2:
-            eng.join()
-            if world > 1 and tick["gather_owed"]:
-                ddist.gather_detections(packed_det[(tick["dev"] - 1) % nslot], gathered)
-                tick["gather_owed"] = False
-
-    def step_host():
-        k = tick["host"] % nslot
-        tick["host"] += 1
-        eng.forward_host(imgs_host, host_outs[k])   # results land in each rank's own host memory: no gather
-
-    imgs_u8_host = (imgs_host * 255).round().to(torch.uint8).pin_memory()      # what an image decoder hands over
-
-    def step_host_u8():
-        k = tick["u8"] % nslot
-        tick["u8"] += 1
-        eng.forward_host_u8(imgs_u8_host, host_outs[k])
+    peaks = load_peaks()
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
 
     def timed(fn, steps, warmup, sampler=None, finish=None):
         for _ in range(warmup):
@@ -361,118 +440,226 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), clocks
 
-    warm = max(args.warmup, 3)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    total_ms, clocks = timed(step_device, args.steps, warm, sampler, finish_device)
-    ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms * 1e-3)
+    def to_metric(total_ms, steps):
+        """the configuration's metric over all ranks from a timed region"""
+        return (total_ms * 1e3 / (steps * B)) if cfg["unit"] == "us/img" else (world * B * steps / (total_ms * 1e-3))
 
-    e2e_ms, _ = timed(step_host, args.steps, warm)
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    counts_ok = all(int(h["counts"].min()) >= 0 for h in host_outs)
-    u8_ms, _ = timed(step_host_u8, args.steps, warm)
-    u8_value = world * B * args.steps / (u8_ms * 1e-3)
+    line = {"metric": cfg["metric"], "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "higher_is_better": cfg["hib"], "scaling": cfg["scaling"], "vs_baseline": None, "data": "synthetic"}
 
-    # per-launch device times, live, with CUDA events on the launching stream
-    n_launch = eng.launches_per_forward
-    ms = (ctypes.c_float * (len(model.plan.layers) + 3))()
-    with torch.cuda.device(dev):
-        _C.check(lib.dn_engine_profile(eng._handle, imgs.data_ptr(), B, 10, ms, stream.cuda_stream))
-    costs = layer_costs(model.plan, B)
-    per_kernel = {}
-    for (name, nbytes, flops), t in zip(costs, list(ms)):
-        if nbytes == 0 and flops == 0 and name.startswith("(fused"):
-            continue
-        k = per_kernel.setdefault(name, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
-        k["ms"] += t; k["bytes"] += nbytes; k["flops"] += flops; k["launches"] += 1
-    sum_ms = sum(k["ms"] for k in per_kernel.values())
-    dominant = max(per_kernel, key=lambda n: per_kernel[n]["ms"])
-    peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
-    try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peaks = {"hbm_gbs": float(mp["hbm_gbs"]), "bf16_tflops": float(mp.get("bf16_tflops_sustained", mp["bf16_tflops"])),
-                 "src": "measured"}
-    except Exception:
-        pass
-    dk = per_kernel[dominant]
-    achieved = dk["bytes"] / (dk["ms"] * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed ncu launch list of this same command
-    # (profiles/r01_ncu_launches_*.json, dram__bytes_read.sum + dram__bytes_write.sum), per launch like `achieved`
-    traffic, traffic_src = None, None
-    try:
-        import glob
-        import re
+    if cfg["model"] == "post":
+        # ---------------- config 4: the post-processing entry point alone --------------------------------------
+        P = 3234
+        g = torch.Generator().manual_seed(7 + rank)
+        logits_h = (torch.randn(B, P, K, generator=g) * 4.0).pin_memory()
+        bbox_h = (torch.randn(B, P, 4, generator=g) * 1.5).pin_memory()
+        logits, bbox = logits_h.to(dev), bbox_h.to(dev)
+        anchors = torch.from_numpy(dplan.default_boxes(dplan.plan_ssdlite320_mobilenet_v3_large())).to(dev)
+        prm = make_post_params(P, K, S, S, 0.001, 0.55, 400, D)
+        lib = _C.lib()
+        ws = torch.empty(lib.dn_postprocess_workspace_bytes(B, ctypes.byref(prm)), dtype=torch.uint8, device=dev)
+        out = ddist.PackedDetections(B, D, dev)
+        host = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in out.as_io().items()}
+        st_logits, st_bbox = torch.empty_like(logits), torch.empty_like(bbox)
 
-        def _ver(path):                         # r01_ncu_launches_v14.json -> (1, 14): newest round / version last
-            m = re.search(r"r(\d+)_ncu_launches_v(\d+)", os.path.basename(path))
-            return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
-        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_launches_*.json")), key=_ver)
-        if cands and B == 256:
-            nl = json.load(open(cands[-1]))["kernels"]
-            fam = {"dwconv_kernel": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
-                   "pwconv_tc_kernel": ["pwconv_tc_kernel"], "pwdw_fused_kernel": ["pwdw_fused_kernel"],
-                   "dwpw_fused_kernel": ["dwpw_fused_kernel"], "stem_conv_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
-                   "se_pool+fc1+fc2+scale kernels": ["se_pool_kernel", "se_fc1_kernel", "se_fc2_kernel", "se_scale_kernel"]}
-            names = fam.get(dominant, [dominant])
-            names = names + ["dn::" + n for n in names]              # ncu reports the name with or without the namespace
-            tb = sum(nl[n]["dram_bytes"] for n in names if n in nl)
-            tl = sum(nl[n]["launches"] for n in names if n in nl)
-            if dominant.startswith("se_pool"):
-                tl //= 4                                             # four launches per squeeze-excitation layer
-            if tl:
-                traffic, traffic_src = tb / tl, os.path.basename(cands[-1])
-    except Exception:
-        pass
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        def post(lg, bb):
+            with torch.cuda.device(dev):
+                _C.check(lib.dn_postprocess(lg.data_ptr(), bb.data_ptr(), anchors.data_ptr(), B, ctypes.byref(prm), ws.data_ptr(),
+                                            ws.numel(), out.boxes.data_ptr(), out.scores.data_ptr(), out.labels.data_ptr(),
+                                            out.counts.data_ptr(), stream.cuda_stream), lib)
+
+        def step_device():
+            post(logits, bbox)
+
+        def step_host():          # pinned host head outputs in, detections out
+            st_logits.copy_(logits_h, non_blocking=True)
+            st_bbox.copy_(bbox_h, non_blocking=True)
+            post(st_logits, st_bbox)
+            for k2, v in out.as_io().items():
+                host[k2].copy_(v, non_blocking=True)
+
+        total_ms, clocks = timed(step_device, args.steps, warm, sampler)
+        value = to_metric(total_ms, args.steps)
+        alg = B * (P * K * 4 + P * 16) + P * 16
+        line.update(value=value, ms_per_step=total_ms / args.steps, dtype="f32", clocks=clocks,
+                    config={"workload": cfg["name"] % B, "baseline_config": args.config, "batch_per_gpu": B,
+                            "l2": "inputs larger than L2 (%.0f MB of logits per step)" % (B * P * K * 4 / 1e6),
+                            "detections_per_img_min": int(out.counts.min()), "images_per_s": world * B * args.steps / (total_ms * 1e-3)},
+                    gpu_launches=14 * args.steps, gpu_launches_per_step=14)
+        if not args.no_extras:
+            e2e_ms, _ = timed(step_host, args.steps, warm)
+            line["e2e"] = {"value": to_metric(e2e_ms, args.steps), "unit": cfg["unit"], "ms_per_step": e2e_ms / args.steps,
+                           "h2d_bytes_per_step": B * P * (K + 4) * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                           "api": "dn_postprocess with pinned host head outputs in (H2D inside the timed region), detections out"}
+            ms3 = (ctypes.c_float * 3)()
+            with torch.cuda.device(dev):
+                _C.check(lib.dn_postprocess_profile(logits.data_ptr(), bbox.data_ptr(), anchors.data_ptr(), B, ctypes.byref(prm),
+                                                    ws.data_ptr(), ws.numel(), out.boxes.data_ptr(), out.scores.data_ptr(),
+                                                    out.labels.data_ptr(), out.counts.data_ptr(), 5, ms3, stream.cuda_stream), lib)
+            step_ms = total_ms / args.steps
+            line["roofline"] = {"kernel": "postprocess kernels (softmax_decode + class_sort + class_nms_warp/cta + merge_topd)",
+                                "bound": "hbm", "achieved": alg / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": alg / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                "algorithmic_bytes_per_launch": alg, "peak_source": peaks["src"],
+                                "phase_ms": {"softmax_decode_hist": ms3[0], "sort_nms_rounds": ms3[1], "merge": ms3[2]},
+                                "note": "1.229 MB algorithmic bytes per image (SURVEY 8(d) config 4) over the whole step time"}
+    else:
+        # ---------------- configs 2 / 3 / 5: the whole detector -------------------------------------------------
+        if cfg["model"] == "v3":
+            model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=K, pipeline_slots=args.pipeline, act_dtype=args.act_dtype)
+        else:
+            model = demonet_b200.ssd_lite_mobilenet_v2(image_size=S, num_classes=K, score_thresh=0.5,
+                                                       pipeline_slots=args.pipeline, act_dtype=args.act_dtype)
+        model.load_state_dict(weights.seeded_state_dict(model.state_dict()))
+        model = model.to(dev)
+        eng = model.reserve(B, dev)
+        lib = eng._lib
+        # inputs resident in HBM (value) and in pinned host memory (e2e); different images per rank
+        imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
+        imgs = imgs_host.to(dev)
+        # one packed output buffer per rank and slot so that the gather of a batch is ONE collective
+        packed_det = [ddist.PackedDetections(B, D, dev) for _ in range(nslot)]
+        io = [p.as_io() for p in packed_det]
+        gathered = torch.empty(world * packed_det[0].buffer.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+        host_outs = [{"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
+                      "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
+                      "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
+                      "counts": torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(nslot)]
+        tick = {"dev": 0, "host": 0, "u8": 0, "gather_owed": False}
+
+        def step_device():
+            # forward of batch i on slot i % nslot; with N > 1 every step closes with ONE all-gather of detections: those
+            # of this batch, or in pipeline mode those of the previous batch (its forward is joined, this one keeps running)
+            k = tick["dev"] % nslot
+            tick["dev"] += 1
+            eng.forward(imgs, io[k])
+            if world > 1:
+                if nslot == 1:
+                    ddist.gather_detections(packed_det[0], gathered)
+                else:
+                    if tick["gather_owed"]:
+                        eng.join_previous()
+                        ddist.gather_detections(packed_det[k ^ 1], gathered)
+                    tick["gather_owed"] = True
+
+        def finish_device():
+            # drain the pipeline inside the timed region: join the last forward(s) and gather the batch still owed
+            if nslot == 2:
+                eng.join()
+                if world > 1 and tick["gather_owed"]:
+                    ddist.gather_detections(packed_det[(tick["dev"] - 1) % nslot], gathered)
+                    tick["gather_owed"] = False
+
+        def step_host():
+            k = tick["host"] % nslot
+            tick["host"] += 1
+            eng.forward_host(imgs_host, host_outs[k])   # results land in each rank's own host memory: no gather
+
+        imgs_u8_host = (imgs_host * 255).round().to(torch.uint8).pin_memory()      # what an image decoder hands over
+
+        def step_host_u8():
+            k = tick["u8"] % nslot
+            tick["u8"] += 1
+            eng.forward_host_u8(imgs_u8_host, host_outs[k])
+
+        total_ms, clocks = timed(step_device, args.steps, warm, sampler, finish_device)
+        n_launch = eng.launches_per_forward
+        st = eng.stats()
+        line.update(value=to_metric(total_ms, args.steps), ms_per_step=total_ms / args.steps, dtype=model.act_dtype, clocks=clocks,
+                    config={"workload": cfg["name"] % (B, model.act_dtype), "baseline_config": args.config, "batch_per_gpu": B,
+                            "global_batch": B * world, "parallelism": "dp%d (image shards, final NCCL all-gather of detections)" % world,
+                            "weights": "seeded re-init 1234 (demonet_b200/seeded.py)", "images": "torch.rand seed 1+rank",
+                            "l2": "inputs larger than L2 (%.0f MB fp32 images per step; device memory %.1f GB)"
+                                  % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
+                            "cuda_graph": True, "batches_in_flight": nslot, "engine": st},
+                    gpu_launches=n_launch * args.steps, gpu_launches_per_step=n_launch)
+        if not args.no_extras:
+            e2e_ms, _ = timed(step_host, args.steps, warm)
+            counts_ok = all(int(h["counts"].min()) >= 0 for h in host_outs)
+            u8_ms, _ = timed(step_host_u8, args.steps, warm)
+            line["e2e"] = {"value": to_metric(e2e_ms, args.steps), "unit": cfg["unit"], "ms_per_step": e2e_ms / args.steps,
+                           "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                           "api": "dn_engine_forward_host (pinned fp32 images in, detections out: the reference's input contract)",
+                           "ok": counts_ok,
+                           "u8": {"value": to_metric(u8_ms, args.steps), "unit": cfg["unit"], "ms_per_step": u8_ms / args.steps,
+                                  "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                                  "api": "dn_engine_forward_host_u8 (pinned uint8 pixels in, x/255 on the device, detections out)"}}
+            line["e2e_u8"] = line["e2e"]["u8"]
+            # the reference's Python API itself: model(List[Tensor[3,S,S]]) -> List[Dict], one call (and one host sync) per step
+            img_list = [t.clone() for t in imgs]            # B separate device tensors, as a data loader hands them over
+            holder = {}
+
+            def step_api():
+                holder["d"] = model(img_list)
+            api_ms, _ = timed(step_api, args.steps, warm)
+            one = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=K, act_dtype=args.act_dtype) if cfg["model"] == "v3" else \
+                demonet_b200.ssd_lite_mobilenet_v2(image_size=S, num_classes=K, score_thresh=0.5, act_dtype=args.act_dtype)
+            one.load_state_dict(weights.seeded_state_dict(one.state_dict()))
+            one = one.to(dev)
+            eng1 = one.reserve(B, dev)
+            io1 = ddist.PackedDetections(B, D, dev).as_io()
+
+            def step_plain():
+                eng1.forward(imgs, io1)
+                stream.synchronize()
+            plain_ms, _ = timed(step_plain, args.steps, warm)
+            line["api_list"] = {"value": to_metric(api_ms, args.steps), "unit": cfg["unit"], "ms_per_step": api_ms / args.steps,
+                                "api": "SSDLiteB200.forward(List[Tensor]) -> List[Dict] on %d separate CUDA tensors (one call + one host "
+                                       "sync per step, like the reference's model(images))" % B,
+                                "engine_forward_synchronous": {"value": to_metric(plain_ms, args.steps), "ms_per_step": plain_ms / args.steps,
+                                                               "api": "dn_engine_forward + stream sync per step, one batch in flight"},
+                                "detections_first_image": int(holder["d"][0]["scores"].numel())}
+            del one, eng1
+            # per-launch device times measured inside a CUDA graph (event-record nodes between consecutive ops)
+            ms = (ctypes.c_float * (len(model.plan.layers) + 3))()
+            with torch.cuda.device(dev):
+                _C.check(lib.dn_engine_profile(eng._handle, imgs.data_ptr(), B, 10, ms, stream.cuda_stream), lib)
+            costs = layer_costs(model.plan, B, D)
+            per_kernel = {}
+            for (name, nbytes, flops), t in zip(costs, list(ms)):
+                if name.startswith("("):
+                    continue
+                k = per_kernel.setdefault(name, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+                k["ms"] += t; k["bytes"] += nbytes; k["flops"] += flops; k["launches"] += 1
+            sum_ms = sum(k["ms"] for k in per_kernel.values())
+            dominant = max(per_kernel, key=lambda n: per_kernel[n]["ms"])
+            dk = per_kernel[dominant]
+            achieved = dk["bytes"] / (dk["ms"] * 1e-3) / 1e9
+            traffic, traffic_src = ncu_traffic(dominant, B)
+            total_bytes = sum(k["bytes"] for k in per_kernel.values())
+            line["roofline"] = {
+                "kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": dk["bytes"] / dk["launches"], "peak_source": peaks["src"] + " (MEASURED_PEAKS.json hbm_gbs)",
-                "launches_per_step": dk["launches"], "avg_launch_ms": dk["ms"] / dk["launches"],
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": dk["bytes"] / dk["launches"],
+                "peak_source": peaks["src"], "launches_per_step": dk["launches"], "avg_launch_ms": dk["ms"] / dk["launches"],
                 "share_of_step": dk["ms"] / sum_ms,
                 "tensor_tflops": dk["flops"] / (dk["ms"] * 1e-3) / 1e12 if dk["flops"] else None,
+                "timing": "in-graph: one CUDA graph of the plan on one stream with event-record nodes between consecutive ops, "
+                          "10 replays, empty-bracket cost (%.1f us) subtracted (dn_engine_profile); sum over ops %.3f ms vs %.3f ms "
+                          "per pipelined step" % (list(ms)[-1] * 1e3, sum_ms, total_ms / args.steps),
+                "whole_step": {"algorithmic_GB": total_bytes / 1e9, "GBps": total_bytes / (total_ms / args.steps * 1e-3) / 1e9,
+                               "frac": total_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peaks["hbm_gbs"]},
                 "per_kernel": {n: {"ms": round(k["ms"], 4), "share": round(k["ms"] / sum_ms, 4),
-                                   "GBps": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1),
-                                   "TFLOPs": round(k["flops"] / (k["ms"] * 1e-3) / 1e12, 2), "launches": k["launches"]}
+                                   "GBps": round(k["bytes"] / (max(k["ms"], 1e-9) * 1e-3) / 1e9, 1),
+                                   "frac_of_hbm_peak": round(k["bytes"] / (max(k["ms"], 1e-9) * 1e-3) / 1e9 / peaks["hbm_gbs"], 3),
+                                   "TFLOPs": round(k["flops"] / (max(k["ms"], 1e-9) * 1e-3) / 1e12, 2), "launches": k["launches"]}
                                for n, k in per_kernel.items()}}
-    if args.layers and rank == 0:
-        for i, ((name, nbytes, flops), t) in enumerate(zip(costs, list(ms))):
-            L = model.plan.layers[i] if i < len(model.plan.layers) else None
-            desc = "%s %dx%d c%d->%d k%d s%d" % (L.kind, L.h_in, L.w_in, L.cin, L.cout, L.k, L.stride) if L else name
-            tt = max(t, 1e-9)
-            if name == "pwdw_fused_kernel":
-                desc = "pw+dw fused " + desc[3:]
-            if name == "dwpw_fused_kernel":
-                desc = "dw+pw fused " + desc[3:]
-            print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (tt * 1e-3) / 1e9,
-                                                             flops / (tt * 1e-3) / 1e12), file=sys.stderr)
+            if args.layers and rank == 0:
+                for i, ((name, nbytes, flops), t) in enumerate(zip(costs, list(ms))):
+                    L = model.plan.layers[i] if i < len(model.plan.layers) else None
+                    desc = "%s %dx%d c%d->%d k%d s%d" % (L.kind, L.h_in, L.w_in, L.cin, L.cout, L.k, L.stride) if L else name
+                    tt = max(t, 1e-9)
+                    if name == "pwdw_fused_kernel":
+                        desc = "pw+dw fused " + desc[3:]
+                    if name == "dwpw_fused_kernel":
+                        desc = "dw+pw fused " + desc[3:]
+                    print("%3d %-34s %8.4f ms %8.1f GB/s %7.2f TF/s" % (i, desc, t, nbytes / (tt * 1e-3) / 1e9,
+                                                                     flops / (tt * 1e-3) / 1e12), file=sys.stderr)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": "ssdlite320_mobilenet_v3_large, 91 classes, 320x320, batch %d per GPU, bf16 activations, "
-                                   "forward + softmax/decode/top-k/NMS/top-300 (BASELINE.json configs[1])" % B,
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (image shards, final NCCL "
-                       "all-gather of detections)" % world, "weights": "seeded re-init 1234 (demonet_b200/seeded.py)",
-                       "images": "torch.rand seed 1+rank", "l2": "inputs larger than L2 (%.0f MB fp32 images per step; "
-                       "activation arena %.1f GB)" % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
-                       "cuda_graph": True,
-                       "batches_in_flight": nslot},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
-                    "api": "dn_engine_forward_host (pinned fp32 images in, detections out)", "ok": counts_ok},
-            "e2e_u8": {"value": u8_value, "unit": UNIT, "ms_per_step": u8_ms / args.steps,
-                       "h2d_bytes_per_step": B * 3 * S * S, "d2h_bytes_per_step": B * D * 28 + B * 4,
-                       "api": "dn_engine_forward_host_u8 (pinned uint8 pixels in, x/255 on the device, detections out); "
-                              "the e2e entry above keeps the reference's fp32 input contract and is PCIe-bound"},
-            "gpu_launches": n_launch * args.steps,
-            "gpu_launches_per_step": n_launch,
-            "roofline": roofline}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, cpu_ms, cores = cpu_reference_rate(args.cpu_sample, 3, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d images x 3 steps, fp32, oracle torch port of SSD.forward (%.0f ms/step)"
-                                          % (args.cpu_sample, cpu_ms)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_extras:
+        # bounded sample of the same workload on the host cores (BASELINE.md section 3 protocol, fewer timed steps)
+        n = args.cpu_sample or (4 if cfg["model"] == "post" else (4 if cfg["model"] == "v2" else 32))
+        line["cpu_baseline"] = cpu_baseline_block(args.config, n, 3, 1)
     if rank == 0:
         print(json.dumps(line), file=_claim_stdout(), flush=True)
     if world > 1:

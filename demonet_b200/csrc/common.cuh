@@ -18,6 +18,13 @@ int dn_postprocess_timed(const float* cls_logits, const float* bbox_regression, 
                          float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
                          float* ms3);
 
+// dn_postprocess with one external event recorded (cudaEventRecordExternal: legal under stream capture) between the
+// softmax / decode front and the sort / NMS / merge rounds -- the in-graph timing of dn_engine_profile
+int dn_postprocess_marked(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                          const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                          float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream,
+                          cudaEvent_t after_front);
+
 namespace dn {
 
 void set_error(const char* fmt, ...);

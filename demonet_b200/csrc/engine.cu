@@ -26,7 +26,9 @@ struct GraphKey {
 struct GraphEntry {
     bool warm = false;
     cudaGraphExec_t exec = nullptr;
+    unsigned long long last_use = 0;
 };
+constexpr size_t DN_MAX_GRAPHS = 16;      // per engine instance; least recently used entries are dropped beyond this
 
 struct dn_engine {
     dn_model_desc desc;
@@ -58,6 +60,7 @@ struct dn_engine {
     bool dw_ready = false;
     bool tmaps_ready = false;
     std::map<GraphKey, GraphEntry> graphs;
+    unsigned long long graph_tick = 0;
     cudaStream_t capture_stream = nullptr;
     // side lanes (dn_op.lane > 0): head branches forked off the main chain.  lane_stream[l-1] carries lane l;
     // op_done[j] is recorded after op j when an op of another lane reads its output (deps[i] lists those j)
@@ -557,7 +560,17 @@ static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_
     ++e->n_forwards;
     if (!e->desc.use_cuda_graph) return enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, s);
     GraphKey key{B, images_dev, out_boxes, out_scores, out_labels, out_counts};
+    if (e->graphs.find(key) == e->graphs.end() && e->graphs.size() >= DN_MAX_GRAPHS) {
+        // a caller that keeps handing in new addresses (a data loader's fresh batches) must not grow the cache without
+        // bound: drop the least recently used entry (an executing graph is released by the driver once it has finished)
+        auto lru = e->graphs.begin();
+        for (auto it = e->graphs.begin(); it != e->graphs.end(); ++it)
+            if (it->second.last_use < lru->second.last_use) lru = it;
+        if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+        e->graphs.erase(lru);
+    }
     GraphEntry& g = e->graphs[key];
+    g.last_use = ++e->graph_tick;
     if (!g.warm) {      // first call with these buffers runs eagerly (also configures kernel attributes)
         g.warm = true;
         return enqueue_forward(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, s);
@@ -680,6 +693,10 @@ extern "C" int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, si
     return DN_OK;
 }
 
+// Per-launch device time measured INSIDE a CUDA graph: the plan is captured on one stream (no side lanes, so that the
+// brackets are meaningful) with an event-record node between consecutive ops, the graph is replayed `iters` times and
+// the elapsed times of consecutive events are averaged.  Every op therefore runs once per replay, in plan order, with the
+// cache state the real step gives it (its input was written by the op in front of it, not by its own previous launch).
 extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, int iters, float* ms_out_host, void* stream_) {
     DN_REQUIRE(e && images_dev && ms_out_host, DN_ERR_INVALID, "NULL argument");
     DN_REQUIRE(e->weights != nullptr, DN_ERR_INVALID, "weights have not been loaded");
@@ -690,35 +707,79 @@ extern "C" int dn_engine_profile(dn_engine* e, const float* images_dev, int B, i
     float* os = (float*)(so + e->so_scores);
     int64_t* ol = (int64_t*)(so + e->so_labels);
     int32_t* oc = (int32_t*)(so + e->so_counts);
-    int rc = enqueue_forward(e, images_dev, B, ob, os, ol, oc, s);          // valid inputs for every layer
+    int rc = enqueue_forward(e, images_dev, B, ob, os, ol, oc, s);          // valid inputs for every layer, attributes set
     if (rc) return rc;
-    cudaEvent_t ev0, ev1;
-    DN_CHECK_CUDA(cudaEventCreate(&ev0));
-    DN_CHECK_CUDA(cudaEventCreate(&ev1));
+    DN_CHECK_CUDA(cudaStreamSynchronize(s));
     const size_t n = e->ops.size();
-    for (size_t i = 0; i < n; ++i) {
-        // SE runs in place: re-running it rescales its input again, which does not change its cost
-        DN_CHECK_CUDA(cudaEventRecord(ev0, s));
-        for (int it = 0; it < iters; ++it) {
-            rc = enqueue_op(e, i, images_dev, B, s);
-            if (rc) return rc;
+    std::vector<cudaEvent_t> ev(n + 5, nullptr);       // n + 3 op boundaries, then an EMPTY bracket (ev[n+3], ev[n+4])
+    auto cleanup = [&]() {
+        for (auto x : ev)
+            if (x) cudaEventDestroy(x);
+    };
+    for (auto& x : ev)
+        if (cudaEventCreate(&x) != cudaSuccess) {
+            cleanup();
+            set_error("cudaEventCreate failed");
+            return DN_ERR_CUDA;
         }
-        DN_CHECK_CUDA(cudaEventRecord(ev1, s));
-        DN_CHECK_CUDA(cudaEventSynchronize(ev1));
-        float ms = 0.f;
-        DN_CHECK_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-        ms_out_host[i] = ms / iters;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStream_t cs = e->capture_stream;
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+        e->dw_pool.assign(n, DwPool{nullptr, 0, 0, 0});
+        for (size_t i = 0; i < n && !rc; ++i) {
+            cudaEventRecordWithFlags(ev[i], cs, cudaEventRecordExternal);
+            rc = enqueue_op(e, i, images_dev, B, cs);
+        }
+        cudaEventRecordWithFlags(ev[n], cs, cudaEventRecordExternal);
+        if (!rc)
+            rc = dn_postprocess_marked((const float*)buf_ptr(e, e->desc.logits_buf), (const float*)buf_ptr(e, e->desc.bbox_buf),
+                                       e->anchors_dev, B, &e->desc.post, e->post_ws, e->post_ws_bytes, ob, os, ol, oc, cs, ev[n + 1]);
+        cudaEventRecordWithFlags(ev[n + 2], cs, cudaEventRecordExternal);
+        // two event nodes with nothing in between: what one bracket costs by itself (subtracted from every op below)
+        cudaEventRecordWithFlags(ev[n + 3], cs, cudaEventRecordExternal);
+        cudaEventRecordWithFlags(ev[n + 4], cs, cudaEventRecordExternal);
+        ce = cudaStreamEndCapture(cs, &graph);
     }
-    // the three post-processing kernels are bracketed inside postprocess.cu
-    rc = dn_postprocess_timed((const float*)buf_ptr(e, e->desc.logits_buf), (const float*)buf_ptr(e, e->desc.bbox_buf),
-                              e->anchors_dev, B, &e->desc.post, e->post_ws, e->post_ws_bytes, ob, os, ol, oc, s, iters,
-                              ms_out_host + n);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    // leave the arena in a consistent state (SE layers were re-applied)
-    if (!rc) rc = enqueue_forward(e, images_dev, B, ob, os, ol, oc, s);
-    if (!rc) DN_CHECK_CUDA(cudaStreamSynchronize(s));
-    return rc;
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cleanup();
+        if (!rc) set_error("profile capture failed: %s", cudaGetErrorString(ce));
+        return rc ? rc : DN_ERR_CUDA;
+    }
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        cleanup();
+        set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        return DN_ERR_CUDA;
+    }
+    std::vector<double> acc(n + 2, 0.0);
+    double empty = 0.0;
+    for (int it = -1; it < iters && ce == cudaSuccess; ++it) {              // replay -1 is a warm-up
+        ce = cudaGraphLaunch(exec, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        for (size_t i = 0; i < n + 2 && ce == cudaSuccess && it >= 0; ++i) {
+            float ms = 0.f;
+            ce = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            acc[i] += ms;
+        }
+        if (ce == cudaSuccess && it >= 0) {
+            float ms = 0.f;
+            ce = cudaEventElapsedTime(&ms, ev[n + 3], ev[n + 4]);
+            empty += ms;
+        }
+    }
+    cudaGraphExecDestroy(exec);
+    cleanup();
+    DN_REQUIRE(ce == cudaSuccess, DN_ERR_CUDA, "profile replay failed: %s", cudaGetErrorString(ce));
+    auto net = [&](double a) { return (float)std::max(0.0, (a - empty) / iters); };
+    for (size_t i = 0; i < n; ++i) ms_out_host[i] = e->ops[i].kind == DN_OP_NOP ? 0.f : net(acc[i]);
+    ms_out_host[n] = net(acc[n]);                        // softmax + decode (+ histogram, round thresholds)
+    ms_out_host[n + 1] = net(acc[n + 1]);                // class sort + NMS + top-D merge, all rounds
+    ms_out_host[n + 2] = (float)(empty / iters);         // the cost of an empty event bracket (already subtracted above)
+    return DN_OK;
 }
 
 // layers (a squeeze-excitation is 4 launches, 3 when the depthwise launch before it pooled) + softmax/decode + round

@@ -905,7 +905,8 @@ static int validate_post(const dn_postprocess_params* p) {
 static int postprocess_impl(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
                             const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
                             float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream, int iters,
-                            float* ms3, bool scored = false, int32_t* out_priors = nullptr, int32_t* out_rounds = nullptr) {
+                            float* ms3, bool scored = false, int32_t* out_priors = nullptr, int32_t* out_rounds = nullptr,
+                            cudaEvent_t after_front = nullptr) {
     int rc = validate_post(p);
     if (rc) return rc;
     DN_REQUIRE(B > 0, DN_ERR_INVALID, "batch must be positive");
@@ -959,6 +960,7 @@ static int postprocess_impl(const float* cls_logits, const float* bbox_regressio
                 DN_CHECK_LAUNCH();
                 launch_pdl(pick_thresholds_kernel, B, 32, 0, stream, (const int*)hist, thr, targets);
                 DN_CHECK_LAUNCH();
+                if (after_front) DN_CHECK_CUDA(cudaEventRecordWithFlags(after_front, stream, cudaEventRecordExternal));
             }
             for (int r = 0; r < NMS_ROUNDS; ++r) {
                 if (phase == 1 || !ms3) {
@@ -1016,6 +1018,14 @@ extern "C" int dn_postprocess_scored(const float* scores, const float* boxes, in
                                      void* stream_) {
     return postprocess_impl(scores, boxes, nullptr, B, p, workspace, workspace_bytes, out_boxes, out_scores, out_labels,
                             out_counts, (cudaStream_t)stream_, 1, nullptr, true, out_priors, out_rounds);
+}
+
+int dn_postprocess_marked(const float* cls_logits, const float* bbox_regression, const float* anchors, int B,
+                          const dn_postprocess_params* p, void* workspace, size_t workspace_bytes, float* out_boxes,
+                          float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream,
+                          cudaEvent_t after_front) {
+    return postprocess_impl(cls_logits, bbox_regression, anchors, B, p, workspace, workspace_bytes, out_boxes, out_scores,
+                            out_labels, out_counts, stream, 1, nullptr, false, nullptr, nullptr, after_front);
 }
 
 // measurement aid used by dn_engine_profile / dn_postprocess_profile: mean ms of P1, P2, P3

@@ -37,16 +37,17 @@ class _Engine:
         self._created = False
 
     def _check(self, rc):
-        self._check(rc, self._lib)
+        _C.check(rc, self._lib)
 
-    def _create(self, offsets):
-        lib = self._lib
+    def describe(self, offsets):
+        """The dn_model_desc the C engine is created from (ops / buffer arrays are kept alive on self)."""
         plan, kw = self.plan, self._desc_kwargs
         fuse = not kw.get("keep_activations", False) and int(os.environ.get("DN_FUSE", "1")) != 0 and int(kw.get("gemm_impl", 0)) == 0
         self._ops = _plan.build_ops(plan, offsets, self.t2b, self.logits_buf, self.bbox_buf, fuse=fuse)
         bufs = (_C.Buf * len(self.bufs))()
         for i, (elems, nbytes) in enumerate(self.bufs):
             bufs[i].elems_per_image, bufs[i].elem_bytes = elems, nbytes
+        self._bufs_c = bufs
         d = _C.ModelDesc()
         d.image_h = d.image_w = plan.size
         d.image_mean = (ctypes.c_float * 3)(*kw["image_mean"])
@@ -62,8 +63,12 @@ class _Engine:
         d.gemm_impl = int(kw.get("gemm_impl", 0))
         d.use_cuda_graph = int(kw.get("use_cuda_graph", 1))
         d.pipeline_slots = int(kw.get("pipeline_slots", 0))
+        return d
+
+    def _create(self, offsets):
+        d = self.describe(offsets)
         with torch.cuda.device(self.device):
-            self._check(lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
+            self._check(self._lib.dn_engine_create(ctypes.byref(self._handle), ctypes.byref(d), self.max_batch))
         self._created = True
 
     def load_weights(self, sd, token):
@@ -257,6 +262,8 @@ class SSDLiteB200(nn.Module):
         self._keep_activations = keep_activations      # debug: one arena buffer per tensor
         self._engines: Dict[Tuple[str, int], _Engine] = {}
         self._io: Dict[Tuple[str, int], dict] = {}
+        self._weights_epoch = 0                        # bumped whenever the parameters may have changed
+        self._last_input_ptr = None
         self._register_parameters(init)
         self.eval()
 
@@ -295,8 +302,22 @@ class SSDLiteB200(nn.Module):
         return super().train(False)
 
     # ---- engine management -----------------------------------------------------------------
-    def _weights_token(self):
-        return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values())
+    # The engine holds BN-folded, re-laid-out copies of the parameters.  They are refreshed when the weights change
+    # through the nn.Module API (load_state_dict, .to() / .cuda() / .half() ... via _apply); after editing parameters in
+    # place (p.data.mul_(...), optimiser steps) call refresh_weights().  A forward only compares one integer.
+    def refresh_weights(self):
+        """Fold and upload the current parameters again on the next forward."""
+        self._weights_epoch += 1
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._weights_epoch += 1
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._weights_epoch += 1
+        return out
 
     def _engine_for(self, device: torch.device, batch: int) -> _Engine:
         key = str(device)
@@ -313,9 +334,8 @@ class SSDLiteB200(nn.Module):
                       min_box_size=1e-2 if self.postprocess_flavour == "legacy" else -1.0)
             eng = _Engine(self.plan, kw, max(batch, 1), device)
             self._engines[key] = eng
-        token = self._weights_token()
-        if eng._weights_token != token:
-            eng.load_weights(self.state_dict(), token)
+        if eng._weights_token != self._weights_epoch:
+            eng.load_weights(self.state_dict(), self._weights_epoch)
         return eng
 
     def _io_buffers(self, device: torch.device, batch: int, host: bool):
@@ -369,11 +389,32 @@ class SSDLiteB200(nn.Module):
         # with such images is assembled on the device; an all-S x S host batch takes the pinned-staging path
         io = self._io_buffers(device, B, host and not resized)
         batch = io["images"]
-        for i, img in enumerate(images):
-            if tuple(img.shape[-2:]) != (S, S):
-                resize_bilinear(img.to(device), (S, S), out=batch[i])
+        if not resized:
+            # one launch (or none) for the whole list instead of one copy per image: a list that is the unbind() of one
+            # contiguous fp32 batch is used in place; anything else is packed by a single torch.stack into the staging batch
+            first = images[0]
+            step = 3 * S * S * 4
+            if (not host and first.dtype == torch.float32
+                    and first.untyped_storage().nbytes() - first.storage_offset() * 4 >= B * step and all(
+                    im.dtype == torch.float32 and im.is_contiguous() and im.shape[0] == 3 and im.device == in_dev
+                    and im.data_ptr() == first.data_ptr() + i * step for i, im in enumerate(images))):
+                # in place only for a buffer the caller keeps reusing (same address as in the previous call): the engine
+                # keys its CUDA graphs by address, so a fresh address every call would mean an eager run every call
+                if self._last_input_ptr == first.data_ptr():
+                    batch = torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1))
+                else:
+                    batch.copy_(torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1)))
+                self._last_input_ptr = first.data_ptr()
             else:
-                batch[i].copy_(img)
+                if any(im.shape[0] != 3 for im in images):
+                    raise ValueError("images must have 3 channels")
+                torch.stack([im if im.dtype == torch.float32 else im.float() for im in images], 0, out=batch)
+        else:
+            for i, img in enumerate(images):
+                if tuple(img.shape[-2:]) != (S, S):
+                    resize_bilinear(img.to(device), (S, S), out=batch[i])
+                else:
+                    batch[i].copy_(img)
         if host and not resized:
             eng.forward_host(batch, io)
             torch.cuda.current_stream(device).synchronize()
@@ -386,16 +427,17 @@ class SSDLiteB200(nn.Module):
         return self._detections(io, B, in_dev if host else None)
 
     def _detections(self, io, B, to_device=None):
-        counts = io["counts"].tolist()            # the one host sync: data-dependent output shapes
-        detections = []
-        for i in range(B):
-            n = counts[i]
-            det = {"boxes": io["boxes"][i, :n].clone(), "scores": io["scores"][i, :n].clone(),
-                   "labels": io["labels"][i, :n].clone()}
-            if to_device is not None:
-                det = {k: v.to(to_device) for k, v in det.items()}
-            detections.append(det)
-        return detections
+        # The padded outputs are copied ONCE (three launches for the whole batch -- they are the engine's reusable output
+        # buffers) and every image gets views of the copies: fresh tensors as the reference returns, without 3 B clones
+        # and, for full rows, without 3 B slicing calls either.
+        D = self.detections_per_img
+        boxes, scores, labels = io["boxes"][:B].clone(), io["scores"][:B].clone(), io["labels"][:B].clone()
+        counts = io["counts"][:B].tolist()        # the one host sync: data-dependent output shapes
+        if to_device is not None:
+            boxes, scores, labels = boxes.to(to_device), scores.to(to_device), labels.to(to_device)
+        bl, sl, ll = boxes.unbind(0), scores.unbind(0), labels.unbind(0)
+        return [{"boxes": bl[i], "scores": sl[i], "labels": ll[i]} if n == D else
+                {"boxes": bl[i][:n], "scores": sl[i][:n], "labels": ll[i][:n]} for i, n in enumerate(counts)]
 
     def forward_uint8(self, images: Tensor):
         """uint8 ingest: `images` is a [B,3,S,S] uint8 batch as a decoder produces it; the ToTensor
@@ -453,6 +495,12 @@ class SSDLiteB200(nn.Module):
             if images.dim() != 4 or tuple(images.shape[1:]) != (3, self.plan.size, self.plan.size) or not images.is_cuda:
                 raise ValueError("forward_batches expects fp32 CUDA batches of shape [B,3,%d,%d]" % (self.plan.size, self.plan.size))
             B = images.shape[0]
+            cur = self._engines.get(str(images.device))
+            if pending is not None and cur is not None and cur.max_batch < B:
+                # a larger batch re-creates the engine: finish and hand out what is still in flight on the old one first
+                pending[2].join()
+                yield self._detections(pending[0], pending[1])
+                pending = None
             eng = self._engine_for(images.device, B)
             key = (str(images.device) + "/slot%d" % slot, B)
             io = self._io.get(key)
@@ -462,12 +510,13 @@ class SSDLiteB200(nn.Module):
                 io.update(boxes=torch.empty(B, D, 4, device=images.device), scores=torch.empty(B, D, device=images.device),
                           labels=torch.empty(B, D, dtype=torch.int64, device=images.device),
                           counts=torch.empty(B, dtype=torch.int32, device=images.device))
-            eng.forward(images.contiguous(), io)
+            src = images if images.dtype == torch.float32 and images.is_contiguous() else images.float().contiguous()
+            eng.forward(src, io)
             if pending is not None:
                 if eng.pipelined:
                     eng.join_previous()
                 yield self._detections(pending[0], pending[1])
-            pending = (io, B, eng)
+            pending = (io, B, eng, src)            # `src` (possibly a temporary) stays alive until its batch was joined
             slot ^= 1
         if pending is not None:
             pending[2].join()

@@ -372,6 +372,13 @@ def assign_buffers(plan: Plan, reuse: bool = True):
                     pinned.add(t)
         if lanes[i] and L.dst:
             pinned.add(L.dst)
+    # A fused launch (pw+dw or dw+pw) reads layers[i].src while it writes layers[i+1].dst, and its CTAs read halo pixels
+    # that other CTAs' output tiles cover: the input must stay live until the SECOND layer of the pair, or best-fit could
+    # hand its buffer to the fused output and the stencil would run in place.
+    for i in list(fused_pairs(plan)) + list(fused_dwpw_pairs(plan)):
+        src = plan.layers[i].src
+        if src and src != "images":
+            last_use[src] = max(last_use.get(src, i), i + 1)
     bufs: List[List[int]] = []      # [elems, bytes]
     free: List[int] = []
     t2b: Dict[str, int] = {}
@@ -482,6 +489,7 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True)
             op.ksize, op.stride, op.lane = L.k, L.stride, lanes[i]
             op.w_off, op.b_off = off["w"], off["b"]
             op.w2_off, op.b2_off = offsets[i + 1]["w_raw"], offsets[i + 1]["b_raw"]
+            assert op.in_buf != op.out_buf, "fused depthwise + project would run in place"
             continue
         if i - 1 in fused_dp:
             op.kind = _C.OP_NOP
@@ -498,6 +506,7 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True)
             op.ksize, op.stride, op.lane = D.k, D.stride, lanes[i]
             op.w_off, op.b_off = off["w_raw"], off["b_raw"]
             op.w2_off, op.b2_off = offsets[i + 1]["w"], offsets[i + 1]["b"]
+            assert op.in_buf != op.out_buf, "fused expand + depthwise would run in place"
             continue
         if i - 1 in fused:
             op.kind = _C.OP_NOP

@@ -283,10 +283,12 @@ int dn_engine_forward_host_u8(dn_engine* e, const uint8_t* images_host, int B, f
 int dn_engine_buffer(dn_engine* e, int buf_id, void** ptr_out, int64_t* elems_per_image_out);
 /* enqueue a device-to-device copy of the first `bytes` bytes of an arena buffer into dst_dev */
 int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, size_t bytes, void* stream);
-/* Per-launch device time: runs one eager forward, then re-launches every step of the plan `iters`
- * times bracketed by CUDA events on `stream` and writes the mean milliseconds of each into
- * ms_out_host[0 .. n_ops + 3) (the n_ops layers in plan order, then the 3 post-processing kernels).
- * Synchronises the stream; a measurement aid for bench.py, not part of the hot path. */
+/* Per-launch device time measured inside a CUDA graph: the plan is captured on one stream with an event-record node
+ * between consecutive ops, replayed `iters` times, and the mean milliseconds between consecutive events are written to
+ * ms_out_host[0 .. n_ops + 3): the n_ops layers in plan order (0 for layers fused into their predecessor), then
+ * softmax + decode, then class sort + NMS + top-D merge (all rounds), then the cost of an EMPTY bracket (two event nodes
+ * with nothing in between, about 2.6 us on B200), which has already been subtracted from every entry.  Every op runs
+ * once per replay, in plan order, on the cache state the real step leaves it.  Synchronises; a measurement aid. */
 int dn_engine_profile(dn_engine* e, const float* images_dev, int B, int iters, float* ms_out_host, void* stream);
 /* What the forward issued last actually ran (parity tests assert that the benchmarked configuration -- fused blocks,
  * pooled squeeze-excitation, graph replay, two slots -- is the one being compared with the oracle). */

@@ -144,18 +144,30 @@ def _score_layout(results, num_columns):
     return r.reshape(N, -1, num_columns)
 
 
+def _tick(times, key, t0):
+    """Accumulate wall time since t0 under times[key] (per-stage CPU timing of the baseline run); returns now."""
+    import time
+    t1 = time.perf_counter()
+    if times is not None:
+        times[key] = times.get(key, 0.0) + (t1 - t0)
+    return t1
+
+
 def v3_forward_raw(sd, images, mode="fp32", num_classes=91, image_mean=(0.5, 0.5, 0.5),
-                   image_std=(0.5, 0.5, 0.5), return_features=False):
+                   image_std=(0.5, 0.5, 0.5), return_features=False, times=None):
     """ssdlite320_mobilenet_v3_large up to the head outputs.
 
     images: f32[B,3,S,S] in [0,1] already at the model size (the transform's resize is then an
     identity, transform.py:150-160).  Returns (cls_logits f32[B,P,K], bbox_regression f32[B,P,4],
     [feature H,W per level]).  Follows generalized_ssd.py:296-313, ssd_mobilenetv3.py:121-132.
     """
+    import time
+    t0 = time.perf_counter()
     net = _Net(sd, mode, V3_BN_EPS)
     mean = torch.as_tensor(image_mean, dtype=torch.float32)[None, :, None, None]
     std = torch.as_tensor(image_std, dtype=torch.float32)[None, :, None, None]
     x = (images - mean) / std                                  # transform.py:129-138
+    t0 = _tick(times, "transform", t0)
     p = "backbone.features.0."
     x = net.cba(x, p + "0", 2, "HS")                           # stem, mobilenetv3.py:141-142
     feats = []
@@ -199,6 +211,7 @@ def v3_forward_raw(sd, images, mode="fp32", num_classes=91, image_mean=(0.5, 0.5
         x = net.cba(x, q + "1", 2, "R6", depthwise=True)
         x = net.cba(x, q + "2", 1, "R6")
         feats.append(x)
+    t0 = _tick(times, "backbone", t0)
     cls, reg = [], []
     for l, f in enumerate(feats):                              # _prediction_block, :27-36
         for name, cols, dst in (("classification_head", num_classes, cls), ("regression_head", 4, reg)):
@@ -206,6 +219,7 @@ def v3_forward_raw(sd, images, mode="fp32", num_classes=91, image_mean=(0.5, 0.5
             h = net.cba(f, q + "0", 1, "R6", depthwise=True)
             dst.append(_score_layout(net.conv_bias(h, q + "1"), cols))
     out = (torch.cat(cls, 1), torch.cat(reg, 1), [tuple(f.shape[-2:]) for f in feats])
+    _tick(times, "head", t0)
     return out + (feats,) if return_features else out
 
 
@@ -234,11 +248,14 @@ def _v2_ir(net, x, prefix, inp, oup, stride, hidden, expand):
 
 
 def v2_forward_raw(sd, images, mode="fp32", num_classes=21, image_mean=(0.485, 0.456, 0.406),
-                   image_std=(0.229, 0.224, 0.225), bp="backbone.", hp="head.", return_features=False):
+                   image_std=(0.229, 0.224, 0.225), bp="backbone.", hp="head.", return_features=False, times=None):
+    import time
+    t0 = time.perf_counter()
     net = _Net(sd, mode, V2_BN_EPS)
     mean = torch.as_tensor(image_mean, dtype=torch.float32)[None, :, None, None]
     std = torch.as_tensor(image_std, dtype=torch.float32)[None, :, None, None]
     x = (images - mean) / std
+    t0 = _tick(times, "transform", t0)
     x = net.cba(x, bp + "body.0", 2, "R6")                     # mobilenetv2.py:157
     feats = []
     idx = 1
@@ -256,6 +273,7 @@ def v2_forward_raw(sd, images, mode="fp32", num_classes=21, image_mean=(0.485, 0
     for e, (inp, oup, t) in enumerate(V2_EXTRAS):
         x = _v2_ir(net, x, bp + "extra_blocks.%d" % e, inp, oup, 2, int(round(inp * t)), True)
         feats.append(x)
+    t0 = _tick(times, "backbone", t0)
     cls, reg = [], []
     for l, f in enumerate(feats):
         for name, cols, dst in (("cls_logits", num_classes, cls), ("bbox_pred", 4, reg)):
@@ -267,6 +285,7 @@ def v2_forward_raw(sd, images, mode="fp32", num_classes=21, image_mean=(0.485, 0
                 o = net.conv_bias(f, q)
             dst.append(_score_layout(o, cols))
     out = (torch.cat(cls, 1), torch.cat(reg, 1), [tuple(f.shape[-2:]) for f in feats])
+    _tick(times, "head", t0)
     return out + (feats,) if return_features else out
 
 
