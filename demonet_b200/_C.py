@@ -40,7 +40,7 @@ class Op(ctypes.Structure):
     _fields_ = [("kind", c_int32), ("act", c_int32), ("in_buf", c_int32), ("out_buf", c_int32), ("res_buf", c_int32),
                 ("h_in", c_int32), ("w_in", c_int32), ("c_in", c_int32), ("h_out", c_int32), ("w_out", c_int32),
                 ("c_out", c_int32), ("ksize", c_int32), ("stride", c_int32), ("c_mid", c_int32), ("out_fp32", c_int32),
-                ("lane", c_int32), ("act2", c_int32), ("reserved", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
+                ("lane", c_int32), ("act2", c_int32), ("se_fold", c_int32), ("w_off", c_int64), ("b_off", c_int64), ("w2_off", c_int64), ("b2_off", c_int64),
                 ("out_batch_stride", c_int64), ("out_row_stride", c_int64), ("out_offset", c_int64)]
 
 
@@ -50,7 +50,8 @@ class Buf(ctypes.Structure):
 
 class EngineStats(ctypes.Structure):
     _fields_ = [("launches_per_forward", c_int32), ("fused_pwdw", c_int32), ("fused_dwpw", c_int32),
-                ("se_layers", c_int32), ("se_pooled", c_int32), ("pipeline_slots", c_int32), ("last_slot", c_int32),
+                ("se_layers", c_int32), ("se_pooled", c_int32), ("se_folded", c_int32), ("reserved", c_int32),
+                ("pipeline_slots", c_int32), ("last_slot", c_int32),
                 ("act_dtype", c_int32), ("forwards", c_int64), ("graph_replays", c_int64)]
 
 
@@ -77,6 +78,8 @@ _SIGNATURES = {
     "dn_se_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dn_se_inplace": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                               c_size_t, c_void_p]),
+    "dn_se_project": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "dn_dwconv_se": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, ctypes.POINTER(c_int), c_void_p]),
     "dn_postprocess_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(PostprocessParams)]),

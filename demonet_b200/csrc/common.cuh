@@ -33,7 +33,9 @@ int u8_to_f32_launch(const unsigned char* src, float* dst, size_t n, cudaStream_
 // squeeze-excitation whose pooling was done by the producing depthwise launch (se.cu)
 int se_max_pool_slots();
 int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW, int C, int Cs,
-                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s);
+                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s,
+                      bool apply = true);
+float* se_scales_ptr(void* workspace, int B, int C);
 
 #define DN_CHECK_CUDA(expr)                                                                      \
     do {                                                                                         \

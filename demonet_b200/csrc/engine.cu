@@ -123,6 +123,14 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
         DN_REQUIRE(o.in_buf == DN_BUF_IMAGES || (o.in_buf >= 0 && o.in_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad in_buf", i);
         DN_REQUIRE(o.kind == DN_OP_SE || (o.out_buf >= 0 && o.out_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad out_buf", i);
         DN_REQUIRE(o.res_buf == DN_BUF_NONE || (o.res_buf >= 0 && o.res_buf < d->n_bufs), DN_ERR_INVALID, "op %d: bad res_buf", i);
+        if (o.se_fold && o.kind == DN_OP_PW) {
+            DN_REQUIRE(i > 0 && d->ops_host[i - 1].kind == DN_OP_SE && d->ops_host[i - 1].se_fold && d->ops_host[i - 1].in_buf == o.in_buf &&
+                           d->ops_host[i - 1].lane == o.lane && o.act == DN_ACT_NONE && o.c_in % d->ops_host[i - 1].c_in == 0,
+                       DN_ERR_INVALID, "op %d: se_fold needs the squeeze-excitation of its input directly in front", i);
+        }
+        if (o.se_fold && o.kind == DN_OP_SE)
+            DN_REQUIRE(i + 1 < d->n_ops && d->ops_host[i + 1].kind == DN_OP_PW && d->ops_host[i + 1].se_fold, DN_ERR_INVALID,
+                       "op %d: a folded squeeze-excitation needs its project GEMM directly behind", i);
     }
     dn_engine* e = new dn_engine();
     e->desc = *d;
@@ -440,6 +448,13 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 ep.hw = hw;
                 ep.out_batch_stride = o.out_batch_stride ? o.out_batch_stride : (long long)hw * o.c_out;
                 ep.out_row_stride = o.out_row_stride ? o.out_row_stride : o.c_out;
+                if (o.se_fold && e->desc.gemm_impl == 0) {
+                    // the squeeze-excitation in front left its [B][C] scales in the SE workspace: this GEMM applies them to
+                    // its A operand in shared memory (C = the SE layer's channel count; K = p * C for pixel-packed layers)
+                    const dn_op& se = e->ops[i - 1];
+                    ep.a_scale = se_scales_ptr(e->se_ws, B, se.c_in);
+                    ep.a_scale_c = se.c_in;
+                }
                 const int M = B * hw;
                 if (e->desc.gemm_impl == 0)
                     rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], e->has_tmap_y[i] ? &e->tmap_y[i] : nullptr, ep, M,
@@ -463,7 +478,8 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 const DwPool& pool = e->dw_pool[i];      // parts > 0: the depthwise launch just before pooled for us
                 rc = se_inplace_pooled(buf_ptr(e, o.in_buf), (const float*)(W + o.w_off), (const float*)(W + o.b_off),
                                        (const float*)(W + o.w2_off), (const float*)(W + o.b2_off), B, o.h_in * o.w_in, o.c_in,
-                                       o.c_mid, e->se_ws, e->se_ws_bytes, pool.parts, pool.slots, o.h_in, s);
+                                       o.c_mid, e->se_ws, e->se_ws_bytes, pool.parts, pool.slots, o.h_in, s,
+                                       !(o.se_fold && e->desc.gemm_impl == 0));
                 e->n_se_pooled += pool.parts > 0;
                 break;
             }
@@ -788,8 +804,35 @@ extern "C" int dn_engine_launches_per_forward(dn_engine* e) {
     if (!e) return 0;
     int nop = 0;
     for (const auto& o : e->ops) nop += (o.kind == DN_OP_NOP);
-    return (int)e->ops.size() - nop + 3 * e->n_se - e->n_se_pooled + 14;
+    int folded = 0;
+    for (const auto& o : e->ops) folded += (o.kind == DN_OP_SE && o.se_fold && e->desc.gemm_impl == 0);
+    return (int)e->ops.size() - nop + 3 * e->n_se - e->n_se_pooled - folded + 14;
 }
+// Stage-level entry of the folded squeeze-excitation (parity tests): SE scales of x, then the project GEMM with the
+// scales applied to its A operand in shared memory.  Equals dn_se_inplace followed by dn_pwconv bit for bit.
+extern "C" int dn_se_project(const void* x, const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2,
+                             const void* w_pw, const float* b_pw, const void* residual, void* y, int B, int HW, int C, int Cs,
+                             int N, void* workspace, size_t workspace_bytes, void* stream_) {
+    DN_REQUIRE(x && w_pw && b_pw && y, DN_ERR_INVALID, "NULL tensor pointer");
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = se_inplace_pooled(const_cast<void*>(x), se_w1, se_b1, se_w2t, se_b2, B, HW, C, Cs, workspace, workspace_bytes, 0, 0, 0, s,
+                               false);
+    if (rc) return rc;
+    PwEpilogue ep;
+    ep.bias = b_pw;
+    ep.residual = (const dn_half_t*)residual;
+    ep.y = y;
+    ep.N = N;
+    ep.act = DN_ACT_NONE;
+    ep.out_fp32 = 0;
+    ep.hw = HW;
+    ep.out_batch_stride = (long long)HW * N;
+    ep.out_row_stride = N;
+    ep.a_scale = se_scales_ptr(workspace, B, C);
+    ep.a_scale_c = C;
+    return pwconv_tc(x, w_pw, ep, B * HW, C, N, s);
+}
+
 extern "C" int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out) {
     DN_REQUIRE(e && out, DN_ERR_INVALID, "NULL argument");
     *out = dn_engine_stats{};
@@ -800,6 +843,7 @@ extern "C" int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out) {
         out->se_layers += (o.kind == DN_OP_SE);
     }
     out->se_pooled = last->n_se_pooled;
+    for (const auto& o : e->ops) out->se_folded += (o.kind == DN_OP_SE && o.se_fold && e->desc.gemm_impl == 0);
     out->launches_per_forward = dn_engine_launches_per_forward(const_cast<dn_engine*>(last));
     out->pipeline_slots = e->twin ? 2 : 1;
     out->last_slot = e->last_slot;

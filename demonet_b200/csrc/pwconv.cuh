@@ -10,6 +10,8 @@ namespace dn {
 struct PwEpilogue {
     const float* bias;                 // [N]
     const dn_half_t* residual;     // [M, N] or nullptr
+    const float* a_scale = nullptr;    // [M / hw][a_scale_c] per-(image, input channel) scale of the A operand (folded SE)
+    int a_scale_c = 0;                 // channels of the scale vector; K is a multiple of it (pixel-packed layers: K = p * C)
     void* y;
     int N;
     int act;

@@ -31,6 +31,7 @@ constexpr int TC_UMMA_K = 16;
 constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SCALE_WARPS = TC_EPI_WARPS;    // SCALE_A variant: the epilogue warps also rescale the A tiles in shared memory
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;      // 16 KiB
 constexpr int TC_STAGE_PITCH = 36;                                 // floats; 144-B rows keep 16-B smem accesses conflict-free
 constexpr int TC_STAGE_BYTES = 5120;                               // >= 32*36*4 and a multiple of 1024
@@ -153,6 +154,7 @@ struct __align__(8) TcBarriers {
     uint64_t empty[TC_MAX_STAGES];       // MMA -> TMA: smem stage consumed
     uint64_t tmem_full[2];               // MMA -> epilogue: accumulator buffer complete
     uint64_t tmem_empty[2];              // epilogue -> MMA: accumulator buffer drained
+    uint64_t scaled[TC_MAX_STAGES];      // SCALE_A: scaler warps -> MMA: the A tile of the stage has been rescaled
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -172,8 +174,14 @@ __device__ __forceinline__ float act_fn(float v) {
     return v;
 }
 
-template <int ACT, bool TMA_STORE>
-__global__ void __launch_bounds__(TC_THREADS)
+// SCALE_A (squeeze-excitation folded into the project GEMM): before they wait for the accumulator of a tile, the eight
+// epilogue warps (idle during the K loop anyway) multiply the A tile of every stage, in shared memory, by the
+// per-(image, input channel) scale -- a[m][k] <- round16(a[m][k] * scale[m / hw][k]), exactly what se_scale_kernel writes
+// to HBM in the unfused path -- between the TMA completion and the MMA issue.  The scaled tensor never exists in HBM:
+// one read and one write of every SE tensor disappear.  (The K loop of tile i + 1 then starts behind the epilogue of
+// tile i; these GEMMs have long K and narrow N, and the other CTAs of the SM fill the gap.)
+template <int ACT, bool TMA_STORE, bool SCALE_A>
+__global__ void __launch_bounds__(TC_THREADS, SCALE_A ? 2 : 1)
 pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
                  int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols) {
@@ -199,6 +207,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
             mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->scaled[s], TC_SCALE_WARPS);            // one arrival per scaler warp (SCALE_A only)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1);
@@ -241,7 +250,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n;
             for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                 const int s = it % num_stages;
-                mbar_wait(&bars->full[s], (it / num_stages) & 1u);
+                mbar_wait(SCALE_A ? &bars->scaled[s] : &bars->full[s], (it / num_stages) & 1u);
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint64_t da = make_smem_desc(smem_u32(smem_a + s * TC_A_STAGE_BYTES));
@@ -264,11 +273,76 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        uint32_t lt = 0, stores = 0;
+        uint32_t lt = 0, stores = 0, sit = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1u;
             const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
             const int m = m0 + row;
+            if constexpr (SCALE_A) {
+                // ---- A-operand scaling.  A stage holds 128 rows of 128 bytes (SWIZZLE_128B: the 16-byte chunk at position
+                // p of row r carries the k-chunk p ^ (r & 7)).  Warp w owns rows 16 w .. 16 w + 15; one warp instruction
+                // covers 4 rows x 8 chunks = 512 contiguous bytes (conflict-free), four instructions per stage.
+                constexpr int SC_ROWS = TC_BLOCK_M / TC_SCALE_WARPS, SC_IT = SC_ROWS / 4;
+                const int sw = warp - 2, p = lane & 7, rsub = lane >> 3;
+                int bimg[SC_IT];
+#pragma unroll
+                for (int i = 0; i < SC_IT; ++i) {
+                    const int mr = m0 + sw * SC_ROWS + i * 4 + rsub;
+                    bimg[i] = (mr < M) ? mr / ep.hw : -1;             // rows past M are zero-filled by TMA: nothing to scale
+                }
+                // rows of one image share their scales, and a lane only ever meets two k-chunks per k-block (p ^ rsub and
+                // p ^ (rsub + 4)): when its rows lie inside one image the scales are loaded once per k-block, ahead of the
+                // barrier wait (rows grow with i, so first == last means every row; the vote keeps the branch uniform)
+                const bool one_image = __all_sync(0xffffffffu, bimg[0] >= 0 && bimg[0] == bimg[SC_IT - 1]);
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++sit) {
+                    const int s = sit % num_stages;
+                    float4 sc[2][2];
+                    if (one_image) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = kb * TC_BLOCK_K + ((p ^ (rsub + 4 * h)) << 3);
+                            const float* sp = ep.a_scale + (long long)bimg[0] * ep.a_scale_c + (k % ep.a_scale_c);
+                            sc[h][0] = (k < K) ? __ldg(reinterpret_cast<const float4*>(sp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            sc[h][1] = (k < K) ? __ldg(reinterpret_cast<const float4*>(sp) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    mbar_wait(&bars->full[s], (sit / num_stages) & 1u);
+                    uint8_t* a_tile = smem_a + s * TC_A_STAGE_BYTES;
+                    if (one_image) {
+#pragma unroll
+                        for (int i = 0; i < SC_IT; ++i) {
+                            const int r = sw * SC_ROWS + i * 4 + rsub;      // r & 7 == rsub + 4 * (i & 1)
+                            uint4* q = reinterpret_cast<uint4*>(a_tile + r * 128 + (p << 4));
+                            const float4 s0 = sc[i & 1][0], s1 = sc[i & 1][1];
+                            float f[8];
+                            unpack8(*q, f);
+                            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+                            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+                            *q = pack8(f);                                  // zero-filled K tail: 0 * 0 = 0
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < SC_IT; ++i) {
+                            const int r = sw * SC_ROWS + i * 4 + rsub;
+                            const int k = kb * TC_BLOCK_K + ((p ^ (r & 7)) << 3);
+                            if (bimg[i] >= 0 && k < K) {                // K % 8 == 0: a chunk is inside K or entirely in the zero tail
+                                const float* sp = ep.a_scale + (long long)bimg[i] * ep.a_scale_c + (k % ep.a_scale_c);
+                                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp));
+                                const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+                                uint4* q = reinterpret_cast<uint4*>(a_tile + r * 128 + (p << 4));
+                                float f[8];
+                                unpack8(*q, f);
+                                f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+                                f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+                                *q = pack8(f);
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->scaled[s]);
+                }
+            }
             const int n_valid = min(block_n, N - n0);
             float* sbw = s_bias[warp - 2];
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
@@ -515,13 +589,14 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     *smem_bytes = need(st);
 }
 
-template <int ACT, bool TMA_STORE>
+template <int ACT, bool TMA_STORE, bool SCALE_A = false>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
                           int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
                           cudaStream_t stream) {
     static SmemOptIn optin;
-    DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE>, smem_cap(1)));
-    launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles, st, cols);
+    DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, smem_cap(1)));
+    launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles,
+               st, cols);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
@@ -550,6 +625,14 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
     if (grid > tiles) grid = tiles;
     const bool tma_store = ty != nullptr && ep.residual == nullptr && !ep.out_fp32;
     const CUtensorMap& tyr = tma_store ? *ty : ta;
+    if (ep.a_scale) {           // squeeze-excitation folded into its project GEMM (no activation there: mobilenetv3.py:88-89)
+        DN_REQUIRE(ep.act == DN_ACT_NONE && ep.a_scale_c > 0 && ep.a_scale_c % 8 == 0 && K % ep.a_scale_c == 0, DN_ERR_UNSUPPORTED,
+                   "A-operand scaling needs a linear GEMM whose K is a multiple of the scale width");
+        return tma_store ? launch_variant<DN_ACT_NONE, true, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
+                                                                   (unsigned)grid, smem_req, stream)
+                         : launch_variant<DN_ACT_NONE, false, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
+                                                                    (unsigned)grid, smem_req, stream);
+    }
 #define DN_PW_CASE(ACT)                                                                                                   \
     return tma_store ? launch_variant<ACT, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid,  \
                                                  smem_req, stream)                                                        \

@@ -282,7 +282,7 @@ extern "C" size_t dn_se_workspace_bytes(int B, int HW, int C) {
 
 extern "C" int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
                              int C, int Cs, void* workspace, size_t workspace_bytes, void* stream_) {
-    return dn::se_inplace_pooled(x, w1, b1, w2t, b2, B, HW, C, Cs, workspace, workspace_bytes, 0, 0, 0, (cudaStream_t)stream_);
+    return dn::se_inplace_pooled(x, w1, b1, w2t, b2, B, HW, C, Cs, workspace, workspace_bytes, 0, 0, 0, (cudaStream_t)stream_, true);
 }
 
 namespace dn {
@@ -292,8 +292,12 @@ int se_max_pool_slots() { return SE_MAX_CHUNKS; }
 // dw_parts > 0: the channel sums are already in the workspace, written by the depthwise row stream that produced x
 // (dwconv_stream.cu, POOL) as [B][dw_slots][C] over dw_parts CTA shares of a B * dw_rows row stream; the pooling pass is
 // skipped.
+// apply == false: stop after fc2 -- the [B][C] scales stay in the workspace (se_scales_ptr) for the project GEMM that
+// applies them to its A operand in shared memory (pwconv_tc.cu, SCALE_A); x is not touched.
+float* se_scales_ptr(void* workspace, int B, int C) { return (float*)workspace + (size_t)B * SE_MAX_CHUNKS * C; }
+
 int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW, int C, int Cs,
-                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s) {
+                      void* workspace, size_t workspace_bytes, int dw_parts, int dw_slots, int dw_rows, cudaStream_t s, bool apply) {
     DN_REQUIRE(x && w1 && b1 && w2t && b2, DN_ERR_INVALID, "NULL tensor pointer");
     DN_REQUIRE(B > 0 && HW > 0 && C > 0 && Cs > 0, DN_ERR_INVALID, "bad shape");
     DN_REQUIRE(C % 8 == 0 && C / 8 <= SE_POOL_THREADS && C <= 2048, DN_ERR_UNSUPPORTED,
@@ -324,6 +328,7 @@ int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2
     DN_CHECK_LAUNCH();
     launch_pdl(se_fc2_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)hidden, w2t, b2, scale, B, C, Cs);
     DN_CHECK_LAUNCH();
+    if (!apply) return DN_OK;
     launch_pdl(se_scale_kernel, dim3(p.scale_chunks, B), SE_POOL_THREADS, 0, s, (uint4*)x, (const float*)scale, HW, C, p.CV, p.rows,
                p.scale_px);
     DN_CHECK_LAUNCH();

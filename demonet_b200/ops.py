@@ -305,6 +305,26 @@ def se_inplace(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor) -> Te
     return x
 
 
+def se_project(x: Tensor, w1: Tensor, b1: Tensor, w2t: Tensor, b2: Tensor, w_pw: Tensor, b_pw: Tensor,
+               residual: Tensor = None) -> Tensor:
+    """Squeeze-excitation of x [B,HW,C] folded into the project GEMM behind it: y [B*HW,N] = (x * scale) . w_pw^T + b_pw
+    (+ residual), the scaling done on the GEMM's A operand in shared memory; x is not modified.  Bit-identical to
+    se_inplace followed by pwconv."""
+    _require_cuda(x, w1, b1, w2t, b2, w_pw, b_pw, residual)
+    B, HW, C = x.shape
+    N = w_pw.shape[0]
+    y = torch.empty(B * HW, N, dtype=x.dtype, device=x.device)
+    ws_bytes = _C.lib().dn_se_workspace_bytes(B, HW, C)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+    res = residual.contiguous() if residual is not None else None
+    with torch.cuda.device(x.device):
+        _CL(x).dn_se_project(x.contiguous().data_ptr(), w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
+                             w2t.contiguous().data_ptr(), b2.contiguous().data_ptr(), w_pw.contiguous().data_ptr(),
+                             b_pw.contiguous().data_ptr(), res.data_ptr() if res is not None else None, y.data_ptr(), B, HW, C,
+                             w1.shape[0], N, ws.data_ptr(), ws_bytes, _stream(x))
+    return y
+
+
 def dwconv_se(x: Tensor, w: Tensor, bias: Tensor, k: int, stride: int, act: str, w1: Tensor, b1: Tensor, w2t: Tensor,
               b2: Tensor):
     """Depthwise conv + squeeze-excitation of its output (the middle of an InvertedResidual with use_se,

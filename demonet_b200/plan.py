@@ -464,6 +464,30 @@ def fused_dwpw_pairs(plan: Plan) -> List[int]:
     return out
 
 
+def se_fold_enabled() -> bool:
+    """DN_SE_FOLD=0 keeps the in-place scaling pass of every squeeze-excitation (measurement aid)."""
+    import os
+    return os.environ.get("DN_SE_FOLD", "1") != "0"
+
+
+def se_folded_layers(plan: Plan) -> List[int]:
+    """Indices i of squeeze-excitation layers whose scaling pass is folded into the project GEMM layers[i + 1]: the SE
+    output feeds only that 1x1 convolution (InvertedResidual, mobilenetv3.py:85-89), which has no activation."""
+    uses: Dict[str, int] = {}
+    for L in plan.layers:
+        for t in (L.src, L.res):
+            if t:
+                uses[t] = uses.get(t, 0) + 1
+    out = []
+    for i in range(len(plan.layers) - 1):
+        a, b = plan.layers[i], plan.layers[i + 1]
+        # uses: the depthwise layer wrote it, the SE layer (src == dst) and the project GEMM read it
+        if a.kind == "se" and b.kind == "pw" and b.src == a.src and b.act == "none" and not b.head and uses.get(a.src, 0) == 2 \
+                and a.src not in plan.feature_names and b.res != a.src:
+            out.append(i)
+    return out
+
+
 def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True):
     """ctypes dn_op array for the engine (fuse=False keeps every layer a launch of its own)."""
     level_off, o = [], 0
@@ -476,9 +500,11 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True)
     kinds = {"stem": _C.OP_STEM, "dw": _C.OP_DW, "pw": _C.OP_PW, "se": _C.OP_SE}
     fused = set(fused_pairs(plan)) if fuse else set()
     fused_dp = set(fused_dwpw_pairs(plan)) if fuse and dwpw_fusion_enabled() else set()
+    folded = set(se_folded_layers(plan)) if fuse and se_fold_enabled() else set()
     for i, (L, off) in enumerate(zip(plan.layers, offsets)):
         op = ops[i]
         op.kind, op.act = kinds[L.kind], _C.ACT[L.act]
+        op.se_fold = 1 if (i in folded or i - 1 in folded) else 0
         if i in fused_dp:               # depthwise + project (+ residual) in one launch
             Pj = plan.layers[i + 1]
             op.kind = _C.OP_DWPW

@@ -97,6 +97,16 @@ size_t dn_se_workspace_bytes(int B, int HW, int C);
 int dn_se_inplace(void* x, const float* w1, const float* b1, const float* w2t, const float* b2, int B, int HW,
                   int C, int Cs, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Squeeze-excitation folded into the project GEMM behind it (InvertedResidual.block[-2:], mobilenetv3.py:85-89): the
+ * scales hardsigmoid(fc2(relu(fc1(avgpool(x))))) are computed as in dn_se_inplace, but instead of rewriting x the 1x1
+ * convolution multiplies its A operand by them in shared memory, rounding to the storage type exactly like the in-place
+ * pass -- the result equals dn_se_inplace followed by dn_pwconv(act = none) bit for bit, with one read and one write
+ * of x less.  x: [B,HW,C] (NOT modified); w_pw: [N,C]; b_pw: fp32 [N]; residual: [B*HW,N] or NULL; y: [B*HW,N];
+ * workspace as for dn_se_inplace. */
+int dn_se_project(const void* x, const float* se_w1, const float* se_b1, const float* se_w2t, const float* se_b2,
+                  const void* w_pw, const float* b_pw, const void* residual, void* y, int B, int HW, int C, int Cs, int N,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* Depthwise convolution (dn_dwconv) followed by the squeeze-excitation of its output (dn_se_inplace), the pair an
  * InvertedResidual with use_se runs between its expand and project convolutions (mobilenetv3.py:43-96).  When the
  * layer runs on the stride-1 row-stream kernel and the batch is large enough for every image to be covered by at most
@@ -222,7 +232,9 @@ typedef struct {
     int32_t lane;                          /* launch lane: 0 = main chain, > 0 = a side branch (head) that may run
                                               concurrently; its tensors never share arena buffers with other lanes */
     int32_t act2;                          /* second activation of a fused op               */
-    int32_t reserved;
+    int32_t se_fold;                       /* squeeze-excitation folded into its project GEMM: set on the DN_OP_SE (it then
+                                              only produces the [B][C] scales) AND on the DN_OP_PW directly behind it (which
+                                              applies them to its A operand in shared memory); x itself is never rescaled */
     int64_t w_off, b_off, w2_off, b2_off;  /* byte offsets into the weight blob             */
     int64_t out_batch_stride, out_row_stride, out_offset;   /* PW output addressing (elements) */
 } dn_op;
@@ -296,6 +308,7 @@ typedef struct {
     int32_t launches_per_forward;
     int32_t fused_pwdw, fused_dwpw;      /* fused expand+depthwise / depthwise+project launches in the plan          */
     int32_t se_layers, se_pooled;        /* squeeze-excitation layers / those whose pooling the depthwise launch did */
+    int32_t se_folded, reserved;         /* ... / those whose scaling pass is folded into the project GEMM           */
     int32_t pipeline_slots, last_slot;   /* 1 or 2 engine instances; the slot of the forward issued last             */
     int32_t act_dtype;                   /* storage type of the activations: 0 = bf16, 1 = fp16                      */
     int64_t forwards, graph_replays;     /* forwards enqueued so far / those that were one cudaGraphLaunch           */

@@ -37,14 +37,14 @@ def detection_match(dets, ref_dets, top=100, iou_thr=0.5):
     """Mean over images of the fraction of the reference's `top` best detections matched by a detection of the same
     label with IoU >= iou_thr.  dets / ref_dets: lists of dicts with boxes [n,4], labels [n] (tensors or arrays)."""
     from torchvision.ops import box_iou
+    def host(v):
+        return torch.as_tensor(np.asarray(v.detach().cpu() if hasattr(v, "detach") else v))
     fr = []
     for d, r in zip(dets, ref_dets):
-        rb = torch.as_tensor(np.asarray(r["boxes"]))[:top].float()
-        rl = torch.as_tensor(np.asarray(r["labels"]))[:top]
+        rb, rl = host(r["boxes"])[:top].float(), host(r["labels"])[:top]
         if rb.shape[0] == 0:
             continue
-        db = torch.as_tensor(np.asarray(d["boxes"].cpu() if hasattr(d["boxes"], "cpu") else d["boxes"])).float()
-        dl = torch.as_tensor(np.asarray(d["labels"].cpu() if hasattr(d["labels"], "cpu") else d["labels"]))
+        db, dl = host(d["boxes"]).float(), host(d["labels"])
         if db.shape[0] == 0:
             fr.append(0.0)
             continue

@@ -210,7 +210,7 @@ def test_benchmarked_configuration_against_oracle():
     st = eng.stats()
     assert st["pipeline_slots"] == 2 and st["graph_replays"] >= 2, st
     assert st["fused_pwdw"] == 1 and st["fused_dwpw"] == 1, st
-    assert st["se_layers"] == 8 and st["se_pooled"] == 8, st
+    assert st["se_layers"] == 8 and st["se_pooled"] == 8 and st["se_folded"] == 8, st
     assert st["act_dtype"] == model.act_dtype
     dets = outs[-1]                                       # a replayed graph on the second slot
     for o in outs[:-1]:

@@ -250,3 +250,32 @@ def test_dwpw_fused_matches_two_kernels(B, H, W, act, res, dt):
     if res:
         ref = ref + x.float().permute(0, 3, 1, 2)
     _close_h16(dt, y, ref.permute(0, 2, 3, 1), extra_abs=2e-2)
+
+
+@pytest.mark.parametrize("B,HW,C,Cs,N,res", [(3, 1600, 120, 32, 40, True), (3, 1600, 72, 24, 40, False), (5, 400, 480, 120, 112, False),
+                                             (4, 400, 672, 168, 112, True), (7, 100, 672, 168, 80, False), (6, 100, 480, 120, 80, True),
+                                             (2, 9, 16, 8, 24, False), (33, 130, 40, 16, 264, True)])
+def test_se_folded_into_the_project_gemm(B, HW, C, Cs, N, res, dt):
+    """dn_se_project: the squeeze-excitation scaling applied to the GEMM's A operand in shared memory (pwconv_tc.cu,
+    SCALE_A) must equal the in-place scaling pass followed by the plain GEMM BIT FOR BIT (same products, same single
+    rounding of x * scale to the storage type), leave x untouched, and match fp32 PyTorch within one ulp."""
+    g = torch.Generator().manual_seed(B * 100 + C + N)
+    x = torch.randn(B, HW, C, generator=g).to(dt).cuda()
+    w1 = (torch.randn(Cs, C, generator=g) / C ** 0.5).cuda()
+    b1 = torch.randn(Cs, generator=g).cuda() * 0.5
+    w2 = (torch.randn(C, Cs, generator=g) / Cs ** 0.5).cuda()
+    b2 = torch.randn(C, generator=g).cuda() * 0.5
+    w_pw = (torch.randn(N, C, generator=g) / C ** 0.5).to(dt).cuda()
+    b_pw = torch.randn(N, generator=g).cuda()
+    r = torch.randn(B * HW, N, generator=g).to(dt).cuda() if res else None
+    w2t = w2.t().contiguous()
+    x0 = x.clone()
+    y = ops.se_project(x, w1, b1, w2t, b2, w_pw, b_pw, r)
+    assert torch.equal(x, x0)                                           # the scaled tensor never exists in HBM
+    xs = ops.se_inplace(x.clone(), w1, b1, w2t, b2)
+    two = ops.pwconv(xs.view(B * HW, C), w_pw, b_pw, "none", r)
+    assert torch.equal(y, two)
+    xf = x.float()
+    scale = F.hardsigmoid(F.relu(xf.mean(1) @ w1.t() + b1) @ w2.t() + b2)
+    ref = (xf * scale[:, None, :]).to(dt).float().view(B * HW, C) @ w_pw.float().t() + b_pw + (r.float() if res else 0)
+    _close_h16(dt, y, ref, extra_abs=4e-3)
