@@ -65,6 +65,31 @@ def parse():
     return ap.parse_args()
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs NVML reports as local to its GPU (nvmlDeviceGetCpuAffinity), so that the pinned staging
+    buffers it allocates afterwards are first-touched on the NUMA node the GPU's PCIe root hangs off: with 8 ranks the
+    host-buffer path otherwise funnels every H2D copy through whichever node the allocations happened to land on.
+    Returns (original affinity, description); the original set is restored for the CPU baseline."""
+    try:
+        import pynvml
+        orig = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & orig
+        if not cpus or cpus == orig:
+            return orig, "all %d cpus (NVML reports no narrower GPU-local set)" % len(orig)
+        os.sched_setaffinity(0, cpus)
+        return orig, "%d of %d cpus local to GPU %d (nvmlDeviceGetCpuAffinity)" % (len(cpus), len(orig), phys)
+    except Exception as e:          # no NVML / not permitted: run unbound
+        try:
+            return os.sched_getaffinity(0), "unbound (%s)" % type(e).__name__
+        except Exception:
+            return None, "unbound"
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -395,6 +420,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU path)")
+    orig_affinity, affinity_note = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -571,7 +597,7 @@ def main():
                             "weights": "seeded re-init 1234 (demonet_b200/seeded.py)", "images": "torch.rand seed 1+rank",
                             "l2": "inputs larger than L2 (%.0f MB fp32 images per step; device memory %.1f GB)"
                                   % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
-                            "cuda_graph": True, "batches_in_flight": nslot, "engine": st},
+                            "cuda_graph": True, "batches_in_flight": nslot, "host_affinity": affinity_note, "engine": st},
                     gpu_launches=n_launch * args.steps, gpu_launches_per_step=n_launch)
         if not args.no_extras:
             e2e_ms, _ = timed(step_host, args.steps, warm)
@@ -658,6 +684,11 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_extras:
         # bounded sample of the same workload on the host cores (BASELINE.md section 3 protocol, fewer timed steps)
+        if orig_affinity:
+            try:
+                os.sched_setaffinity(0, orig_affinity)          # the CPU baseline gets every core again
+            except Exception:
+                pass
         n = args.cpu_sample or (4 if cfg["model"] == "post" else (4 if cfg["model"] == "v2" else 32))
         line["cpu_baseline"] = cpu_baseline_block(args.config, n, 3, 1)
     if rank == 0:

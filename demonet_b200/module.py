@@ -368,47 +368,54 @@ class SSDLiteB200(nn.Module):
             images = list(images.unbind(0))
         if len(images) == 0:
             return []
+        # one pass over the list: the reference's input checks (transform.py:110-112, 130-134), the original sizes, and
+        # whether the list is the unbind() of one contiguous fp32 batch (then it needs no copy at all)
+        B, S = len(images), self.plan.size
         original_sizes: List[Tuple[int, int]] = []
-        for img in images:
-            if img.dim() != 3:
+        first = images[0]
+        step, base = 3 * S * S * 4, first.data_ptr() if first.dim() == 3 else 0
+        in_place = first.dtype == torch.float32 and first.dim() == 3
+        resized = False
+        for i, img in enumerate(images):
+            shp = img.shape
+            if len(shp) != 3:
                 raise ValueError("images is expected to be a list of 3d tensors "
-                                 "of shape [C, H, W], got {}".format(img.shape))       # transform.py:110-112
+                                 "of shape [C, H, W], got {}".format(shp))                 # transform.py:110-112
             if not img.is_floating_point():
                 raise TypeError("Expected input images to be of floating type (in range [0, 1]), "
                                 f"but found type {img.dtype} instead")                # transform.py:130-134
-            original_sizes.append((int(img.shape[-2]), int(img.shape[-1])))
+            h, w = shp[1], shp[2]
+            original_sizes.append((h, w))
+            if h != S or w != S:
+                resized = True
+            if in_place and (img.data_ptr() != base + i * step or img.dtype != torch.float32 or not img.is_contiguous()):
+                in_place = False
         if not torch.cuda.is_available():
             raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        B, S = len(images), self.plan.size
-        in_dev = images[0].device
+        in_dev = first.device
         host = in_dev.type != "cuda"
         device = torch.device("cuda", torch.cuda.current_device()) if host else in_dev
         eng = self._engine_for(device, B)
-        resized = any(sz != (S, S) for sz in original_sizes)
         # images that need the fixed-size resize (transform.py:27-53) go through the device kernel, so a host batch
         # with such images is assembled on the device; an all-S x S host batch takes the pinned-staging path
         io = self._io_buffers(device, B, host and not resized)
         batch = io["images"]
         if not resized:
-            # one launch (or none) for the whole list instead of one copy per image: a list that is the unbind() of one
-            # contiguous fp32 batch is used in place; anything else is packed by a single torch.stack into the staging batch
-            first = images[0]
-            step = 3 * S * S * 4
-            if (not host and first.dtype == torch.float32
-                    and first.untyped_storage().nbytes() - first.storage_offset() * 4 >= B * step and all(
-                    im.dtype == torch.float32 and im.is_contiguous() and im.shape[0] == 3 and im.device == in_dev
-                    and im.data_ptr() == first.data_ptr() + i * step for i, im in enumerate(images))):
-                # in place only for a buffer the caller keeps reusing (same address as in the previous call): the engine
-                # keys its CUDA graphs by address, so a fresh address every call would mean an eager run every call
-                if self._last_input_ptr == first.data_ptr():
-                    batch = torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1))
+            if any(im.shape[0] != 3 for im in images):
+                raise ValueError("images must have 3 channels")
+            in_place = (in_place and not host and first.untyped_storage().nbytes() - first.storage_offset() * 4 >= B * step)
+            if in_place:
+                # used in place only when the caller keeps reusing the buffer (same address as in the previous call): the
+                # engine keys its CUDA graphs by address, so a fresh address every call would mean an eager run every call
+                whole = torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1))
+                if self._last_input_ptr == base:
+                    batch = whole
                 else:
-                    batch.copy_(torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1)))
-                self._last_input_ptr = first.data_ptr()
+                    batch.copy_(whole)
+                self._last_input_ptr = base
             else:
-                if any(im.shape[0] != 3 for im in images):
-                    raise ValueError("images must have 3 channels")
-                torch.stack([im if im.dtype == torch.float32 else im.float() for im in images], 0, out=batch)
+                # one launch for the whole list instead of one copy per image
+                torch.stack(images if first.dtype == torch.float32 else [im.float() for im in images], 0, out=batch)
         else:
             for i, img in enumerate(images):
                 if tuple(img.shape[-2:]) != (S, S):
