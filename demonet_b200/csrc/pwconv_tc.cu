@@ -18,6 +18,7 @@
 // Reference ops replaced: see dn_pwconv in include/demonet_b200.h.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -35,7 +36,7 @@ constexpr int TC_SCALE_WARPS = TC_EPI_WARPS;    // SCALE_A variant: the epilogue
 constexpr int TC_A_STAGE_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;      // 16 KiB
 constexpr int TC_STAGE_PITCH = 36;                                 // floats; 144-B rows keep 16-B smem accesses conflict-free
 constexpr int TC_STAGE_BYTES = 5120;                               // >= 32*36*4 and a multiple of 1024
-constexpr int TC_STATIC_SMEM = TC_EPI_WARPS * 32 * 4 + TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // bias + epilogue staging (+ alignment)
+constexpr int TC_STATIC_SMEM = TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // epilogue staging (+ alignment)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -155,6 +156,7 @@ struct __align__(8) TcBarriers {
     uint64_t tmem_full[2];               // MMA -> epilogue: accumulator buffer complete
     uint64_t tmem_empty[2];              // epilogue -> MMA: accumulator buffer drained
     uint64_t scaled[TC_MAX_STAGES];      // SCALE_A: scaler warps -> MMA: the A tile of the stage has been rescaled
+    uint64_t w_full;                     // W-stationary mode: the CTA's weight tile (all k-blocks) has landed
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -181,12 +183,11 @@ __device__ __forceinline__ float act_fn(float v) {
 // one read and one write of every SE tensor disappear.  (The K loop of tile i + 1 then starts behind the epilogue of
 // tile i; these GEMMs have long K and narrow N, and the other CTAs of the SM fill the gap.)
 template <int ACT, bool TMA_STORE, bool SCALE_A>
-__global__ void __launch_bounds__(TC_THREADS, SCALE_A ? 2 : 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
-                 int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols) {
+                 int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols, int w_stat) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ float s_bias[TC_EPI_WARPS][32];                         // warp-private bias slice of the current 32 columns
     // per epilogue warp: 32 rows x 32 fp32 (+pad) for the staged stores, or a 32 x 64 bf16 SWIZZLE_128B tile
     // for the TMA store
     __shared__ __align__(1024) uint8_t s_stage_raw[TC_EPI_WARPS][TC_STAGE_BYTES];
@@ -194,11 +195,19 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
     const int w_stage_bytes = block_n * TC_BLOCK_K * 2;
     uint8_t* smem_a = smem;
+    // W-stationary mode (w_stat): the grid is a multiple of n_tiles, so a CTA meets ONE weight tile for its whole life; all
+    // its k-blocks are loaded once into their own buffers and the ring only carries A.  Otherwise the (L2-resident)
+    // weight tile is fetched again with every output tile -- for the expand layers (K <= 128, N up to 256 per tile) that
+    // is more bytes into the SM than the activations themselves.
+    const int num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
     uint8_t* smem_w = smem + num_stages * TC_A_STAGE_BYTES;
-    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_w + num_stages * w_stage_bytes);
+    TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_w + (w_stat ? num_k_blocks : num_stages) * w_stage_bytes);
+    // the whole (zero-padded) bias vector, staged once per CTA: weights are not produced by the previous kernel, so this
+    // happens before the programmatic-dependency wait, and no epilogue chunk waits for a global load any more
+    float* s_bias_all = reinterpret_cast<float*>(bars + 1);            // [n_tiles * block_n + 32]
+    for (int i = threadIdx.x; i < n_tiles * block_n + 32; i += blockDim.x) s_bias_all[i] = (i < N) ? __ldg(ep.bias + i) : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_k_blocks = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -213,6 +222,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_init(&bars->tmem_full[b], 1);
             mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS);          // one arrival per epilogue warp
         }
+        mbar_init(&bars->w_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
@@ -226,7 +236,13 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (elect_one()) {
-            const uint32_t stage_bytes = (uint32_t)(TC_A_STAGE_BYTES + w_stage_bytes);
+            const uint32_t stage_bytes = (uint32_t)(TC_A_STAGE_BYTES + (w_stat ? 0 : w_stage_bytes));
+            if (w_stat) {
+                const int n0 = ((int)blockIdx.x % n_tiles) * block_n;
+                mbar_expect_tx(&bars->w_full, (uint32_t)(num_k_blocks * w_stage_bytes));
+                for (int kb = 0; kb < num_k_blocks; ++kb)
+                    tma_load_2d(smem_w + kb * w_stage_bytes, &tmap_w, &bars->w_full, kb * TC_BLOCK_K, n0);
+            }
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
@@ -235,7 +251,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
                     mbar_expect_tx(&bars->full[s], stage_bytes);
                     tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
-                    tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
+                    if (!w_stat) tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
                 }
             }
         }
@@ -243,6 +259,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ===== MMA issuer =====
         const uint32_t idesc = make_idesc(TC_BLOCK_M, block_n);
         uint32_t it = 0, lt = 0;
+        if (w_stat) mbar_wait(&bars->w_full, 0u);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const uint32_t buf = lt & 1u;
             mbar_wait(&bars->tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
@@ -254,7 +271,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tcgen05_fence_after();
                 if (elect_one()) {
                     const uint64_t da = make_smem_desc(smem_u32(smem_a + s * TC_A_STAGE_BYTES));
-                    const uint64_t dw = make_smem_desc(smem_u32(smem_w + s * w_stage_bytes));
+                    const uint64_t dw = make_smem_desc(smem_u32(smem_w + (w_stat ? kb : s) * w_stage_bytes));
                     const int k_left = K - kb * TC_BLOCK_K;              // zero-filled K tail needs no MMA
                     const int ksteps = k_left >= TC_BLOCK_K ? TC_BLOCK_K / TC_UMMA_K : (k_left + TC_UMMA_K - 1) / TC_UMMA_K;
                     for (int k = 0; k < ksteps; ++k) {
@@ -344,7 +361,6 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
             const int n_valid = min(block_n, N - n0);
-            float* sbw = s_bias[warp - 2];
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16);
@@ -355,15 +371,12 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint8_t* obase = s_stage_raw[warp - 2];
                 for (int c0 = half * 32; c0 < n_valid; c0 += 64, ++stores) {
                     uint8_t* obuf = obase + (stores & 1u) * 2048;
-                    const int nb = n0 + c0 + lane;
-                    const float bv = (nb < N) ? __ldg(ep.bias + nb) : 0.f;
+                    const float* sbw = s_bias_all + n0 + c0;
                     uint32_t v[32];
                     const bool second = (c0 + 16 < block_n);              // warp-uniform
                     tmem_ld16(tmem_d + (uint32_t)c0, v);
                     if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this tile's previous store
-                    __syncwarp();
-                    sbw[lane] = bv;
                     __syncwarp();
                     tmem_ld_wait();
 #pragma unroll
@@ -407,11 +420,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool second = (c0 + 16 < block_n);                  // warp-uniform
                 tmem_ld16(tmem_d + (uint32_t)c0, v);
                 if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
-                {
-                    const int nb = n0 + c0 + lane;
-                    sbw[lane] = (nb < N) ? __ldg(ep.bias + nb) : 0.f;
-                }
-                __syncwarp();
+                const float* sbw = s_bias_all + n0 + c0;
                 tmem_ld_wait();
                 // residual tile of this chunk: issue all loads now, they complete behind the TMEM read / staging
                 const int cg = (lane & 7) * 4;
@@ -546,7 +555,8 @@ static size_t smem_cap(int n) {
     return n == 1 ? (size_t)(227 * 1024 - TC_STATIC_SMEM - 256) : (size_t)(228 * 1024) / n - TC_STATIC_SMEM - 1024 - 256;
 }
 
-void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes) {
+void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes,
+                    int* w_stationary) {
     static const int bn_max = [] {                     // measurement aid: DN_PW_BN_MAX=64|128 caps the tile width
         const char* v = getenv("DN_PW_BN_MAX");
         const int x = v ? atoi(v) : 256;
@@ -565,7 +575,23 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     *n_tiles = nt;
     const int kb = (K + TC_BLOCK_K - 1) / TC_BLOCK_K;
     int st = kb >= 3 ? TC_MAX_STAGES : kb + 1;            // short-K layers: fewer stages -> more CTAs per SM
-    auto need = [&](int stg) { return 1024 + (size_t)stg * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2) + sizeof(TcBarriers); };
+    int st_max = kb + 1;
+    // W-stationary: the weight tile of a CTA (all k-blocks) stays in shared memory and the ring carries A only
+    // (DN_PW_WSTAT=0 turns it off, measurement aid)
+    static const int wstat_on = [] {
+        const char* v = getenv("DN_PW_WSTAT");
+        return v ? atoi(v) : 1;
+    }();
+    // (only for K <= 128, i.e. at most two k-blocks: the resident tile then never takes more shared memory than the
+    // weight share of the two-stage ring it replaces, so the CTA count per SM cannot drop)
+    const size_t w_total = (size_t)kb * bn * TC_BLOCK_K * 2;
+    const bool ws = wstat_on && kb <= 2;
+    if (w_stationary) *w_stationary = ws ? 1 : 0;
+    if (ws) st = st_max = TC_MAX_STAGES;                   // A-only stages: the ring can run several tiles ahead
+    auto need = [&](int stg) {
+        const size_t ring = ws ? (size_t)stg * TC_A_STAGE_BYTES + w_total : (size_t)stg * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2);
+        return 1024 + ring + sizeof(TcBarriers) + ((size_t)nt * bn + 32) * 4;
+    };
     while (st > 2 && need(st) > smem_cap(1)) --st;
     // Resident CTAs beat ring depth: these GEMMs are bound by the latency chains of the epilogue warps and of the
     // load -> MMA -> commit loop, not by bytes in flight (same total either way), so take the largest CTA count whose
@@ -579,7 +605,7 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
         for (int n = 4; n >= 2; --n)
             if (n * cols <= 512 && need(2) <= smem_cap(n)) {
                 int s2 = 2;
-                while (s2 < TC_MAX_STAGES && s2 < kb + 1 && need(s2 + 1) <= smem_cap(n)) ++s2;
+                while (s2 < TC_MAX_STAGES && s2 < st_max && need(s2 + 1) <= smem_cap(n)) ++s2;
                 st = s2;
                 break;
             }
@@ -592,11 +618,11 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
 template <int ACT, bool TMA_STORE, bool SCALE_A = false>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
                           int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int w_stat = 0) {
     static SmemOptIn optin;
     DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, smem_cap(1)));
     launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles,
-               st, cols);
+               st, cols, w_stat);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
@@ -605,9 +631,9 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CU
 // ty is given and the layer has neither a residual nor fp32 / strided output.
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
                      int N, cudaStream_t stream) {
-    int bn, nt, st, cols;
+    int bn, nt, st, cols, ws;
     size_t smem;
-    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem);
+    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws);
     // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
     // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
     // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).
@@ -623,21 +649,25 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
     DN_REQUIRE(tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "GEMM too large");
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
+    if (ws) {                    // a CTA must keep meeting the same weight tile: tile % nt == blockIdx.x % nt
+        grid = grid / nt * nt;
+        if (grid < nt) ws = 0, grid = std::min<long long>((long long)sm_count() * per_sm, tiles);
+    }
     const bool tma_store = ty != nullptr && ep.residual == nullptr && !ep.out_fp32;
     const CUtensorMap& tyr = tma_store ? *ty : ta;
     if (ep.a_scale) {           // squeeze-excitation folded into its project GEMM (no activation there: mobilenetv3.py:88-89)
         DN_REQUIRE(ep.act == DN_ACT_NONE && ep.a_scale_c > 0 && ep.a_scale_c % 8 == 0 && K % ep.a_scale_c == 0, DN_ERR_UNSUPPORTED,
                    "A-operand scaling needs a linear GEMM whose K is a multiple of the scale width");
         return tma_store ? launch_variant<DN_ACT_NONE, true, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
-                                                                   (unsigned)grid, smem_req, stream)
+                                                                   (unsigned)grid, smem_req, stream, ws)
                          : launch_variant<DN_ACT_NONE, false, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
-                                                                    (unsigned)grid, smem_req, stream);
+                                                                    (unsigned)grid, smem_req, stream, ws);
     }
 #define DN_PW_CASE(ACT)                                                                                                   \
     return tma_store ? launch_variant<ACT, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid,  \
-                                                 smem_req, stream)                                                        \
+                                                 smem_req, stream, ws)                                                    \
                      : launch_variant<ACT, false>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid, \
-                                                  smem_req, stream)
+                                                  smem_req, stream, ws)
     switch (ep.act) {
         case DN_ACT_RELU: DN_PW_CASE(DN_ACT_RELU);
         case DN_ACT_RELU6: DN_PW_CASE(DN_ACT_RELU6);
@@ -650,7 +680,7 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream) {
     int bn, nt, st, cols;
     size_t smem;
-    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem);
+    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem, nullptr);
     CUtensorMap ta, tw, ty;
     int rc = make_tmap_h16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
     if (rc) return rc;
