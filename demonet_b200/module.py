@@ -368,28 +368,50 @@ class SSDLiteB200(nn.Module):
             images = list(images.unbind(0))
         if len(images) == 0:
             return []
-        # one pass over the list: the reference's input checks (transform.py:110-112, 130-134), the original sizes, and
-        # whether the list is the unbind() of one contiguous fp32 batch (then it needs no copy at all)
         B, S = len(images), self.plan.size
-        original_sizes: List[Tuple[int, int]] = []
         first = images[0]
-        step, base = 3 * S * S * 4, first.data_ptr() if first.dim() == 3 else 0
-        in_place = first.dtype == torch.float32 and first.dim() == 3
+        step = 3 * S * S * 4
+        # Fast path for the common case -- B float32 [3,S,S] CUDA tensors: torch.stack validates shapes, dtypes and devices
+        # in C++ (one launch for the whole list), so the per-image Python checks below only run when something is off, to
+        # raise the reference's own exceptions (transform.py:110-112, 130-134) or to take the resize / host paths.
+        stacked = None
+        if (isinstance(first, Tensor) and first.is_cuda and first.dim() == 3 and first.dtype == torch.float32
+                and tuple(first.shape) == (3, S, S)):
+            self._engine_for(first.device, B)         # (a larger batch re-creates the engine and its staging buffers first)
+            base = first._base
+            if (base is not None and base.dim() == 4 and tuple(base.shape) == (B, 3, S, S) and base.is_contiguous()
+                    and base.dtype == torch.float32 and images[-1]._base is base
+                    and all(im.data_ptr() == base.data_ptr() + i * step for i, im in enumerate(images))):
+                stacked = base                                        # the list is the unbind() of one batch: no copy at all
+            else:
+                try:
+                    stacked = torch.stack(images, 0, out=self._io_buffers(first.device, B, False)["images"])
+                except (RuntimeError, TypeError):
+                    stacked = None                                    # mixed shapes / dtypes / devices: the general path decides
+        original_sizes: List[Tuple[int, int]] = []
+        in_place = False
         resized = False
-        for i, img in enumerate(images):
-            shp = img.shape
-            if len(shp) != 3:
-                raise ValueError("images is expected to be a list of 3d tensors "
-                                 "of shape [C, H, W], got {}".format(shp))                 # transform.py:110-112
-            if not img.is_floating_point():
-                raise TypeError("Expected input images to be of floating type (in range [0, 1]), "
-                                f"but found type {img.dtype} instead")                # transform.py:130-134
-            h, w = shp[1], shp[2]
-            original_sizes.append((h, w))
-            if h != S or w != S:
-                resized = True
-            if in_place and (img.data_ptr() != base + i * step or img.dtype != torch.float32 or not img.is_contiguous()):
-                in_place = False
+        if stacked is not None:
+            original_sizes = [(S, S)] * B
+            base = stacked.data_ptr()
+            in_place = stacked is not self._io.get((str(first.device), B), {}).get("images")
+        else:
+            base = first.data_ptr() if first.dim() == 3 else 0
+            in_place = first.dtype == torch.float32 and first.dim() == 3
+            for i, img in enumerate(images):
+                shp = img.shape
+                if len(shp) != 3:
+                    raise ValueError("images is expected to be a list of 3d tensors "
+                                     "of shape [C, H, W], got {}".format(shp))                 # transform.py:110-112
+                if not img.is_floating_point():
+                    raise TypeError("Expected input images to be of floating type (in range [0, 1]), "
+                                    f"but found type {img.dtype} instead")                # transform.py:130-134
+                h, w = shp[1], shp[2]
+                original_sizes.append((h, w))
+                if h != S or w != S:
+                    resized = True
+                if in_place and (img.data_ptr() != base + i * step or img.dtype != torch.float32 or not img.is_contiguous()):
+                    in_place = False
         if not torch.cuda.is_available():
             raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         in_dev = first.device
@@ -400,13 +422,22 @@ class SSDLiteB200(nn.Module):
         # with such images is assembled on the device; an all-S x S host batch takes the pinned-staging path
         io = self._io_buffers(device, B, host and not resized)
         batch = io["images"]
-        if not resized:
+        if stacked is not None:
+            if in_place:
+                # a caller-owned batch is used in place only when the caller keeps reusing it (same address as in the
+                # previous call): the engine keys its CUDA graphs by address, so a fresh address every call would mean an
+                # eager run every call
+                if self._last_input_ptr == base:
+                    batch = stacked
+                else:
+                    batch.copy_(stacked)
+                self._last_input_ptr = base
+            # else: torch.stack has already filled the staging batch
+        elif not resized:
             if any(im.shape[0] != 3 for im in images):
                 raise ValueError("images must have 3 channels")
             in_place = (in_place and not host and first.untyped_storage().nbytes() - first.storage_offset() * 4 >= B * step)
             if in_place:
-                # used in place only when the caller keeps reusing the buffer (same address as in the previous call): the
-                # engine keys its CUDA graphs by address, so a fresh address every call would mean an eager run every call
                 whole = torch.as_strided(first, (B, 3, S, S), (3 * S * S, S * S, S, 1))
                 if self._last_input_ptr == base:
                     batch = whole
