@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--layers", action="store_true", help="also print the per-layer time table to stderr")
     ap.add_argument("--act-dtype", default=None, choices=["fp16", "bf16"],
                     help="activation storage type (default: the library default, fp16)")
+    ap.add_argument("--gather-every", type=int, default=1,
+                    help="N > 1: all-gather the detections of this many consecutive batches in ONE collective (1 = a collective "
+                         "per step; every detection is gathered inside the timed region either way)")
     ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
                     help="batches in flight per GPU (2 = the engine's pipeline mode, 1 = one forward at a time)")
     return ap.parse_args()
@@ -546,35 +549,57 @@ def main():
         # one packed output buffer per rank and slot so that the gather of a batch is ONE collective
         packed_det = [ddist.PackedDetections(B, D, dev) for _ in range(nslot)]
         io = [p.as_io() for p in packed_det]
-        gathered = torch.empty(world * packed_det[0].buffer.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+        # N > 1: the detections of G consecutive batches are gathered by ONE all_gather_into_tensor.  A collective per step makes
+        # every step a cross-rank barrier (the slowest rank of each step paces all of them: 0.968 efficiency at 8 GPUs in r01);
+        # with G = 4 the ranks only meet every fourth step.  Batch j is copied (2 MB, device to device) into position j % 2G of a
+        # ring, so the G batches of a group are contiguous and the next group fills the other half while this one is in flight.
+        G = max(1, args.gather_every) if world > 1 else 1
+        nb = packed_det[0].buffer.numel()
+        ring = torch.zeros(2 * G * nb, dtype=torch.uint8, device=dev) if world > 1 else None
+        gathered = torch.empty(world * G * nb, dtype=torch.uint8, device=dev) if world > 1 else None
         host_outs = [{"boxes": torch.empty(B, D, 4, dtype=torch.float32).pin_memory(),
                       "scores": torch.empty(B, D, dtype=torch.float32).pin_memory(),
                       "labels": torch.empty(B, D, dtype=torch.int64).pin_memory(),
                       "counts": torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(nslot)]
-        tick = {"dev": 0, "host": 0, "u8": 0, "gather_owed": False}
+        tick = {"dev": 0, "calls": 0, "host": 0, "u8": 0, "gathers": 0, "base": 0}
+
+        def collect(j, k):
+            """batch j (computed on slot k, already joined) -> ring; close the group when it is complete"""
+            pos = j % (2 * G)
+            ring[pos * nb:(pos + 1) * nb].copy_(packed_det[k].buffer, non_blocking=True)
+            if (j + 1) % G == 0:
+                g0 = (j + 1 - G) % (2 * G)
+                dist.all_gather_into_tensor(gathered, ring[g0 * nb:(g0 + G) * nb])
+                tick["gathers"] += 1
 
         def step_device():
-            # forward of batch i on slot i % nslot; with N > 1 every step closes with ONE all-gather of detections: those
-            # of this batch, or in pipeline mode those of the previous batch (its forward is joined, this one keeps running)
-            k = tick["dev"] % nslot
+            # forward of batch i on slot i % nslot; the previous batch (its forward is joined, this one keeps running) goes
+            # into the gather ring
+            i = tick["dev"]                 # logical batch index (position in the gather ring)
+            k = tick["calls"] % nslot       # the engine alternates its two instances per call: keep output buffers paired with them
             tick["dev"] += 1
+            tick["calls"] += 1
             eng.forward(imgs, io[k])
             if world > 1:
                 if nslot == 1:
-                    ddist.gather_detections(packed_det[0], gathered)
-                else:
-                    if tick["gather_owed"]:
-                        eng.join_previous()
-                        ddist.gather_detections(packed_det[k ^ 1], gathered)
-                    tick["gather_owed"] = True
+                    collect(i, 0)
+                elif i > tick["base"]:
+                    eng.join_previous()
+                    collect(i - 1, k ^ 1)
 
         def finish_device():
-            # drain the pipeline inside the timed region: join the last forward(s) and gather the batch still owed
+            # drain inside the timed region: join the last forward, hand its batch over and gather the (partial) last group
             if nslot == 2:
                 eng.join()
-                if world > 1 and tick["gather_owed"]:
-                    ddist.gather_detections(packed_det[(tick["dev"] - 1) % nslot], gathered)
-                    tick["gather_owed"] = False
+            if world > 1:
+                i = tick["dev"]
+                if nslot == 2 and i > tick["base"]:
+                    collect(i - 1, (tick["calls"] - 1) % nslot)
+                if i % G != 0:
+                    g0 = (i - i % G) % (2 * G)
+                    dist.all_gather_into_tensor(gathered, ring[g0 * nb:(g0 + G) * nb])
+                    tick["gathers"] += 1
+                tick["base"] = tick["dev"] = (i + G - 1) // G * G      # the next timed region starts on a group boundary
 
         def step_host():
             k = tick["host"] % nslot
@@ -593,7 +618,9 @@ def main():
         st = eng.stats()
         line.update(value=to_metric(total_ms, args.steps), ms_per_step=total_ms / args.steps, dtype=model.act_dtype, clocks=clocks,
                     config={"workload": cfg["name"] % (B, model.act_dtype), "baseline_config": args.config, "batch_per_gpu": B,
-                            "global_batch": B * world, "parallelism": "dp%d (image shards, final NCCL all-gather of detections)" % world,
+                            "global_batch": B * world,
+                            "parallelism": "dp%d (image shards, no hot-path traffic; NCCL all-gather of the detections of every %d "
+                                           "batches in one collective)" % (world, G),
                             "weights": "seeded re-init 1234 (demonet_b200/seeded.py)", "images": "torch.rand seed 1+rank",
                             "l2": "inputs larger than L2 (%.0f MB fp32 images per step; device memory %.1f GB)"
                                   % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
