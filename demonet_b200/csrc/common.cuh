@@ -82,6 +82,10 @@ inline int sm_count() {
     if (n[dev] == 0) {
         cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
         if (n[dev] <= 0) n[dev] = 148;
+        // DN_SM_COUNT=<n>: size the persistent grids for n SMs (measurement aid: with two batches in flight, kernels sized
+        // for half the GPU leave room for the other batch's kernel to run beside them)
+        const char* v = getenv("DN_SM_COUNT");
+        if (v && atoi(v) > 0 && atoi(v) < n[dev]) n[dev] = atoi(v);
     }
     return n[dev];
 }
