@@ -73,6 +73,12 @@ _SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_void_p]),
     "dn_dwpw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_conv3x3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_int, c_int64, c_int64, c_void_p]),
+    "dn_conv3x3_first": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
+                                 c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_maxpool2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_l2norm_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dn_se_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

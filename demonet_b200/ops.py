@@ -346,6 +346,65 @@ def dwconv_se(x: Tensor, w: Tensor, bias: Tensor, k: int, stride: int, act: str,
     return y, bool(pooled.value)
 
 
+# ---- dense convolutions and the small operators of ssd300_vgg16 ------------------------------------
+def conv3x3(x: Tensor, w: Tensor, bias: Tensor, stride: int = 1, padding: int = 1, dilation: int = 1, act: str = "relu",
+            out: Tensor = None, out_batch_stride: int = 0, out_row_stride: int = 0) -> Tensor:
+    """Dense 3x3 convolution on the tensor cores.  x 16-bit [B,H,W,C] NHWC (C % 64 == 0); w 16-bit [9,N,C] (tap-major:
+    w[kh*3+kw, n, c] = conv.weight[n, c, kh, kw]); bias fp32 [N] -> act(conv) as 16-bit [B,Ho,Wo,N].  With `out` (an fp32
+    tensor) the result is written with the SSD head addressing (see pwconv / dn_pwconv) and `out` is returned."""
+    _require_cuda(x, w, bias, out)
+    B, H, W, C = x.shape
+    N = w.shape[1]
+    Ho = (H + 2 * padding - 2 * dilation - 1) // stride + 1
+    Wo = (W + 2 * padding - 2 * dilation - 1) // stride + 1
+    y = out if out is not None else torch.empty(B, Ho, Wo, N, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _CL(x).dn_conv3x3(x.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(), y.data_ptr(), B, H, W, C,
+                          N, stride, padding, dilation, _C.ACT[act], int(out is not None), out_batch_stride, out_row_stride,
+                          _stream(x))
+    return y
+
+
+def conv3x3_first(images: Tensor, w: Tensor, bias: Tensor, mean, std, act_dtype: str = None) -> Tensor:
+    """normalise + conv 3 -> 64 (3x3, stride 1, padding 1) + ReLU.  images fp32 [B,3,H,W]; w fp32 [27,64]."""
+    _require_cuda(images, w, bias)
+    B, _, H, W = images.shape
+    y = torch.empty(B, H, W, w.shape[1], dtype=_C.torch_dtype(act_dtype), device=images.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    with torch.cuda.device(images.device):
+        _CL(y).dn_conv3x3_first(images.contiguous().data_ptr(), w.contiguous().data_ptr(), bias.contiguous().data_ptr(), m, s,
+                                y.data_ptr(), B, H, W, w.shape[1], _stream(images))
+    return y
+
+
+def maxpool2d(x: Tensor, k: int, stride: int, padding: int = 0, ceil_mode: bool = False) -> Tensor:
+    """nn.MaxPool2d on 16-bit NHWC activations."""
+    _require_cuda(x)
+    B, H, W, C = x.shape
+
+    def out(n):
+        o = (n + 2 * padding - k + (stride - 1 if ceil_mode else 0)) // stride + 1
+        if ceil_mode and (o - 1) * stride >= n + padding:
+            o -= 1
+        return o
+    y = torch.empty(B, out(H), out(W), C, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _CL(x).dn_maxpool2d(x.contiguous().data_ptr(), y.data_ptr(), B, H, W, C, k, stride, padding, int(ceil_mode), _stream(x))
+    return y
+
+
+def l2norm_scale(x: Tensor, scale: Tensor) -> Tensor:
+    """scale * F.normalize(x) over the last (channel) dimension of 16-bit NHWC activations."""
+    _require_cuda(x, scale)
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _CL(x).dn_l2norm_scale(x.contiguous().data_ptr(), scale.float().contiguous().data_ptr(), y.data_ptr(), x.numel() // C, C,
+                               _stream(x))
+    return y
+
+
 # ---- detection sink (SURVEY 8(f2)) ---------------------------------------------------------------
 def detections_to_coco(boxes: Tensor, scores: Tensor, labels: Tensor, counts: Tensor, image_ids) -> Dict[str, Tensor]:
     """Padded detections (boxes [B,D,4] xyxy, scores [B,D], labels [B,D], counts [B], as written by the engine) ->

@@ -118,6 +118,32 @@ int dn_dwconv_se(const void* x, const float* w, const float* bias, void* y, int 
                  int Cs, void* workspace, size_t workspace_bytes, int* pooled_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * the operators ssd300_vgg16 (demonet/models/ssd_vgg16.py:139-213) needs beyond the SSDLite path
+ * ---------------------------------------------------------------------------------------- */
+
+/* Dense 3x3 convolution + bias + activation as an implicit GEMM on the tcgen05 tensor cores (no im2col buffer: one 4-D TMA
+ * box per tap, out-of-bounds zero fill = the convolution's padding).  Replaces nn.Conv2d(C, N, 3, stride, padding,
+ * dilation) + ReLU of the VGG16 features and the SSD extra blocks (ssd_vgg16.py:30-109, conv6: dilation 6) and the dense
+ * SSD heads (SSDScoringHead / SSDClassificationHead / SSDRegressionHead, generalized_ssd.py:38-92).
+ * x: [B,H,W,C] 16-bit NHWC, C % 64 == 0; w: 16-bit [9][N][C] (tap = kh * 3 + kw major); bias fp32 [N];
+ * y: [B,Ho,Wo,N] 16-bit, or fp32 with the head addressing of dn_pwconv when out_fp32 != 0 (out_*_stride = 0: dense).
+ * stride 1 or 2; pad 0 or = dilation; act: none / relu / relu6. */
+int dn_conv3x3(const void* x, const void* w, const float* bias, void* y, int B, int H, int W, int C, int N, int stride, int pad,
+               int dilation, int act, int out_fp32, int64_t out_batch_stride, int64_t out_row_stride, void* stream);
+
+/* Input normalisation (transform.py:129-138) + the first VGG convolution (3 -> 64, 3x3, stride 1, padding 1) + ReLU.
+ * images: fp32 NCHW [B,3,H,W] in [0,1]; w: fp32 [27][64] ((ci*3+kh)*3+kw major); y: 16-bit NHWC [B,H,W,64]. */
+int dn_conv3x3_first(const float* images, const float* w, const float* bias, const float* mean3_host, const float* std3_host,
+                     void* y, int B, int H, int W, int Cout, void* stream);
+
+/* nn.MaxPool2d(k, stride, pad, ceil_mode) on 16-bit NHWC activations (vgg features; ceil_mode patched in at
+ * ssd_vgg16.py:36-37; the 3x3 stride-1 "pool5" of ssd_vgg16.py:84). */
+int dn_maxpool2d(const void* x, void* y, int B, int H, int W, int C, int k, int stride, int pad, int ceil_mode, void* stream);
+
+/* scale_weight * F.normalize(x) over the channels of every pixel (ssd_vgg16.py:98-100, eps 1e-12).  x, y: [npix, C]. */
+int dn_l2norm_scale(const void* x, const float* scale, void* y, int64_t npix, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Transforms either side of the path (GeneralizedRCNNTransform, demonet/models/transform.py)
  * ---------------------------------------------------------------------------------------- */
 
