@@ -566,18 +566,24 @@ def build_ops(plan: Plan, offsets, t2b, logits_buf, bbox_buf, fuse: bool = True)
     return ops
 
 
-def default_boxes(plan: Plan, aspect_ratios=None, min_ratio=0.2, max_ratio=0.95, clip=True) -> np.ndarray:
+def default_boxes(plan: Plan, aspect_ratios=None, min_ratio=0.2, max_ratio=0.95, clip=True, scales=None, steps=None) -> np.ndarray:
     """The SSD default-box table, f32 [P,4] xyxy pixels -- DefaultBoxGenerator
     (demonet/models/anchor_utils.py:39-126) evaluated once per (model, size) instead of per forward.
     Same fp32 operation order as the reference so the table is bit-identical."""
-    grids = plan.grid_sizes
+    return default_boxes_for(plan.grid_sizes, plan.size, aspect_ratios, min_ratio, max_ratio, clip, scales, steps)
+
+
+def default_boxes_for(grids, size, aspect_ratios=None, min_ratio=0.2, max_ratio=0.95, clip=True, scales=None, steps=None) -> np.ndarray:
+    """default_boxes for explicit grid sizes [(H_k, W_k)] and a square image of `size` pixels.  `scales` / `steps`: the explicit
+    form ssd300_vgg16 uses (ssd_vgg16.py:193-195; anchor_utils.py:29-50, 79-83)."""
     n = len(grids)
     if aspect_ratios is None:
         aspect_ratios = [[2, 3]] * n
-    if n > 1:
-        scales = [min_ratio + (max_ratio - min_ratio) * k / (n - 1.0) for k in range(n)] + [1.0]
-    else:
-        scales = [min_ratio, max_ratio]
+    if scales is None:
+        if n > 1:
+            scales = [min_ratio + (max_ratio - min_ratio) * k / (n - 1.0) for k in range(n)] + [1.0]
+        else:
+            scales = [min_ratio, max_ratio]
     f32 = np.float32
     rows = []
     for k, (fh, fw) in enumerate(grids):
@@ -589,13 +595,14 @@ def default_boxes(plan: Plan, aspect_ratios=None, min_ratio=0.2, max_ratio=0.95,
         wh = np.asarray(wh, dtype=f32)
         if clip:
             wh = np.clip(wh, f32(0), f32(1))
-        cx = (np.arange(fw).astype(f32) + f32(0.5)) / f32(fw)
-        cy = (np.arange(fh).astype(f32) + f32(0.5)) / f32(fh)
+        x_f, y_f = (size / steps[k], size / steps[k]) if steps is not None else (fw, fh)
+        cx = (np.arange(fw).astype(f32) + f32(0.5)) / f32(x_f)
+        cy = (np.arange(fh).astype(f32) + f32(0.5)) / f32(y_f)
         gy, gx = np.meshgrid(cy, cx, indexing="ij")
         ctr = np.repeat(np.stack([gx.reshape(-1), gy.reshape(-1)], -1), wh.shape[0], axis=0)
         rows.append(np.concatenate([ctr, np.tile(wh, (fh * fw, 1))], axis=1).astype(f32))
     t = np.concatenate(rows, 0)
     out = np.concatenate([t[:, :2] - f32(0.5) * t[:, 2:], t[:, :2] + f32(0.5) * t[:, 2:]], -1).astype(f32)
-    out[:, 0::2] *= f32(plan.size)
-    out[:, 1::2] *= f32(plan.size)
+    out[:, 0::2] *= f32(size)
+    out[:, 1::2] *= f32(size)
     return np.ascontiguousarray(out)

@@ -43,6 +43,8 @@ def seeded_state_dict(template, seed=DEFAULT_SEED):
             v = torch.randn(shape, generator=g) * 0.1
         elif leaf == "running_var":
             v = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif leaf == "scale_weight":            # ssd300_vgg16's L2-norm scale (ssd_vgg16.py:40: 20), spread a little
+            v = 20.0 * (torch.rand(shape, generator=g) * 0.5 + 0.75)
         elif leaf == "weight" and len(shape) == 4:
             fan_in = shape[1] * shape[2] * shape[3]
             v = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
@@ -59,3 +61,20 @@ def synthetic_images(batch, size, seed=1):
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     return torch.rand(batch, 3, size, size, generator=g)
+
+
+def seeded_vgg_state_dict(template, seed=DEFAULT_SEED):
+    """The recipe above for ssd300_vgg16, with the SSD heads scaled down: the VGG input is normalised to +-128
+    (image_std = 1/255, ssd_vgg16.py:199) and He-initialised ReLU layers keep that magnitude, so unscaled heads would give
+    logits with a standard deviation in the hundreds and one-hot softmax scores -- a degenerate parity input.  With these
+    factors the logits have std ~ 1.6 (no score saturates to exactly 1.0, which would make top-k / sort order a matter of
+    tie-breaking) and the box regression std ~ 1.5."""
+    sd = seeded_state_dict(template, seed)
+    for k in sd:
+        if k.startswith("head.classification_head") and k.endswith(".weight"):
+            sd[k] = sd[k] * 0.008
+        elif k.startswith("head.regression_head") and k.endswith(".weight"):
+            sd[k] = sd[k] * 0.008
+        elif k.startswith("head.") and k.endswith(".bias"):
+            sd[k] = sd[k] * (1.0 if "classification" in k else 0.2)
+    return sd

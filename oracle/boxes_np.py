@@ -55,7 +55,7 @@ def default_box_wh_pairs(aspect_ratios, scales):
 
 
 def default_boxes(grid_sizes, image_size, aspect_ratios=None, min_ratio=0.2, max_ratio=0.95,
-                  scales=None, clip=True):
+                  scales=None, clip=True, steps=None):
     """anchor_utils.py:75-100 + :111-126.  Returns f32[P,4] xyxy in pixels.
 
     grid_sizes: [(H_k, W_k)], image_size: (H, W).  Order: level, then cell
@@ -69,8 +69,10 @@ def default_boxes(grid_sizes, image_size, aspect_ratios=None, min_ratio=0.2, max
     rows = []
     for k, (fh, fw) in enumerate(grid_sizes):
         # ((arange + 0.5) / f_k).to(float32): torch promotes int64 + 0.5 to fp32 (:85-86)
-        sx = (np.arange(fw).astype(F32) + F32(0.5)) / F32(fw)
-        sy = (np.arange(fh).astype(F32) + F32(0.5)) / F32(fh)
+        # (:79-83) with `steps` the centres are tiled by image_size / step instead of the grid size (ssd300_vgg16)
+        x_f, y_f = (image_size[1] / steps[k], image_size[0] / steps[k]) if steps is not None else (fw, fh)
+        sx = (np.arange(fw).astype(F32) + F32(0.5)) / F32(x_f)
+        sy = (np.arange(fh).astype(F32) + F32(0.5)) / F32(y_f)
         yy, xx = np.meshgrid(sy, sx, indexing="ij")
         xx = xx.reshape(-1)
         yy = yy.reshape(-1)

@@ -290,6 +290,64 @@ def v2_forward_raw(sd, images, mode="fp32", num_classes=21, image_mean=(0.485, 0
 
 
 # ---------------------------------------------------------------------------------------
+# ssd300_vgg16: SSDFeatureExtractorVGG (ssd_vgg16.py:30-109) + SSDHead with dense 3x3 convolutions
+# (generalized_ssd.py:25-92).  state_dict keys: backbone.scale_weight, backbone.features.N, backbone.extra.*, head.*
+# ---------------------------------------------------------------------------------------
+VGG_FEATURES = [("c", 0), ("c", 2), ("p", False), ("c", 5), ("c", 7), ("p", False), ("c", 10), ("c", 12), ("c", 14), ("p", True),
+                ("c", 17), ("c", 19), ("c", 21)]          # torchvision vgg16 cfg "D" up to conv4_3; third pool with ceil_mode
+VGG_ANCHORS_PER_LOC = [4, 6, 6, 6, 4, 4]
+
+
+def vgg_forward_raw(sd, images, mode="fp32", num_classes=91, image_mean=(0.48235, 0.45882, 0.40784),
+                    image_std=(1.0 / 255.0, 1.0 / 255.0, 1.0 / 255.0), return_features=False, times=None):
+    """ssd300_vgg16 up to the head outputs: (cls_logits f32[B,8732,K], bbox_regression f32[B,8732,4], grid sizes).
+    mode fp32 = the reference's op sequence; fp16 / bf16 = the engine's contract (16-bit weights for the tensor-core
+    convolutions, every stored activation rounded, fp32 accumulate, fp32 head outputs; the first convolution keeps fp32
+    weights like the SSDLite stem)."""
+    import time
+    t0 = time.perf_counter()
+    rnd = {"bf16": _bf16, "fp16": _fp16}.get(mode, _ident)
+    wr = rnd
+
+    def conv(x, prefix, stride=1, padding=1, dilation=1, relu=True, round_w=True, out_round=True):
+        w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+        y = F.conv2d(x, wr(w) if round_w else w, b, stride, padding, dilation)
+        if relu:
+            y = F.relu(y)
+        return rnd(y) if out_round else y
+    mean = torch.as_tensor(image_mean, dtype=torch.float32)[None, :, None, None]
+    std = torch.as_tensor(image_std, dtype=torch.float32)[None, :, None, None]
+    x = (images - mean) / std                                  # transform.py:129-138
+    t0 = _tick(times, "transform", t0)
+    for kind, arg in VGG_FEATURES:
+        if kind == "c":
+            x = conv(x, "backbone.features.%d" % arg, round_w=(arg != 0))
+        else:
+            x = F.max_pool2d(x, 2, 2, 0, ceil_mode=arg)
+    feats = [rnd(sd["backbone.scale_weight"].view(1, -1, 1, 1) * F.normalize(x))]          # ssd_vgg16.py:98-100
+    x = F.max_pool2d(x, 2, 2)                                   # backbone[maxpool4_pos:-1]: pool4, conv5_1..5_3
+    for i in (1, 3, 5):
+        x = conv(x, "backbone.extra.0.%d" % i)
+    x = F.max_pool2d(x, 3, 1, 1)                                # modified pool5, ssd_vgg16.py:84
+    x = conv(x, "backbone.extra.0.7.1", padding=6, dilation=6)  # fc6, atrous
+    x = conv(x, "backbone.extra.0.7.3", padding=0)              # fc7
+    feats.append(x)
+    for e, (s, p) in zip((1, 2, 3, 4), ((2, 1), (2, 1), (1, 0), (1, 0))):                  # ssd_vgg16.py:48-73
+        x = conv(x, "backbone.extra.%d.0" % e, padding=0)
+        x = conv(x, "backbone.extra.%d.2" % e, stride=s, padding=p)
+        feats.append(x)
+    t0 = _tick(times, "backbone", t0)
+    cls, reg = [], []
+    for l, f in enumerate(feats):                               # SSDScoringHead.forward, generalized_ssd.py:60-74
+        for name, cols, dst in (("classification_head", num_classes, cls), ("regression_head", 4, reg)):
+            o = conv(f, "head.%s.module_list.%d" % (name, l), relu=False, out_round=False)
+            dst.append(_score_layout(o, cols))
+    out = (torch.cat(cls, 1), torch.cat(reg, 1), [tuple(f.shape[-2:]) for f in feats])
+    _tick(times, "head", t0)
+    return out + (feats,) if return_features else out
+
+
+# ---------------------------------------------------------------------------------------
 # Post-processing: torch port of the reference's CPU path (the CPU baseline "port")
 # ---------------------------------------------------------------------------------------
 def decode_boxes_torch(rel, anchors, weights=(10.0, 10.0, 5.0, 5.0), clip=4.135166556742356):

@@ -14,7 +14,7 @@ restatements agree with the reference:
   * oracle.boxes_np.postprocess_detections                       == SSD.postprocess_detections
     (given the reference's softmax scores)
 Outputs (small, committed): tests/golden/{v3_ssdlite.npz, v2_ssdlite.npz, nms_cases.npz,
-postprocess_stress.npz}.  Inputs are regenerated from seeds (oracle/weights.py), never stored.
+postprocess_stress.npz, ssd300_vgg16.npz}.  Inputs are regenerated from seeds (oracle/weights.py), never stored.
 """
 import hashlib
 import os
@@ -155,6 +155,45 @@ def gen_v2():
     np.savez_compressed(os.path.join(OUT, "v2_ssdlite.npz"), **store)
 
 
+def gen_vgg():
+    """ssd300_vgg16 (demonet/models/ssd_vgg16.py:139-213), seeded weights with scaled-down heads."""
+    from torchvision.models.detection.image_list import ImageList
+    m = refshim.ref_module("ssd_vgg16")
+    model = m.ssd300_vgg16(pretrained=False, pretrained_backbone=False).eval()
+    sd = weights.seeded_vgg_state_dict(model.state_dict())
+    model.load_state_dict(sd)
+    x = weights.synthetic_images(2, 300)
+    with torch.no_grad():
+        dets = model([x[0], x[1]])
+        mean = torch.tensor(model.transform.image_mean)[None, :, None, None]
+        std = torch.tensor(model.transform.image_std)[None, :, None, None]
+        feats = list(model.backbone((x - mean) / std).values())
+        ho = model.head(feats)
+        anchors = model.anchor_generator(ImageList(x, [(300, 300)] * 2), feats)[0]
+        cls, reg, grids = net_ref.vgg_forward_raw(sd, x, "fp32")
+        cls16, reg16, _ = net_ref.vgg_forward_raw(sd, x, "fp16")
+    assert torch.equal(cls, ho["cls_logits"]) and torch.equal(reg, ho["bbox_regression"])
+    ar, sc, st = [[2], [2, 3], [2, 3], [2, 3], [2], [2]], [0.07, 0.15, 0.33, 0.51, 0.69, 0.87, 1.05], [8, 16, 32, 64, 100, 300]
+    a_np = boxes_np.default_boxes(grids, (300, 300), ar, scales=sc, steps=st)
+    assert np.array_equal(a_np, anchors.numpy())
+    scores = torch.softmax(cls, -1).numpy()
+    for i in range(2):
+        o = boxes_np.postprocess_detections(None, reg[i].numpy(), a_np, (300, 300), score_thresh=0.01, nms_thresh=0.45,
+                                            detections_per_img=200, topk_candidates=400, scores=scores[i])
+        assert np.array_equal(o["labels"], dets[i]["labels"].numpy())
+        assert np.array_equal(o["scores"], dets[i]["scores"].numpy())
+        assert np.allclose(o["boxes"], dets[i]["boxes"].numpy(), atol=1e-3)
+    stride = 29
+    np.savez_compressed(
+        os.path.join(OUT, "ssd300_vgg16.npz"), seed=np.int64(weights.DEFAULT_SEED), image_seed=np.int64(1),
+        anchors_sha256=np.array(sha(a_np)), logits_rows=cls[:, ::stride].numpy(), row_stride=np.int64(stride),
+        logits_fp16emu_rows=cls16[:, ::stride].numpy(), bbox_rows=reg[:, ::stride].numpy(), logits_sha256=np.array(sha(cls.numpy())),
+        det_boxes=np.stack([d["boxes"].numpy() for d in dets]), det_scores=np.stack([d["scores"].numpy() for d in dets]),
+        det_labels=np.stack([d["labels"].numpy() for d in dets]),
+        state_dict_keys=np.array(list(sd.keys())), state_dict_shapes=np.array([str(tuple(v.shape)) for v in sd.values()]))
+    print("vgg: ok; dets/img", [len(d["scores"]) for d in dets])
+
+
 def random_boxes(g, n, size=320.0, clustered=True):
     if clustered:      # many overlapping boxes around a few centres -> non-trivial suppression
         nc = max(1, n // 12)
@@ -265,6 +304,7 @@ if __name__ == "__main__":
     gen_v3()
     gen_v2()
     gen_stress()
+    gen_vgg()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
