@@ -43,6 +43,10 @@ CONFIGS = {
             metric="ssd_lite_mobilenet_v2 512x512 images/sec (forward + postprocess)",
             name="ssd_lite_mobilenet_v2, VOC 21 classes, 512x512, batch %d per GPU, %s activations, forward + legacy PostProcess "
                  "(thr 0.5, NMS 0.45, top-100) (BASELINE.json configs[4])"),
+    6: dict(model="vgg", S=300, K=91, batch=64, scaling="weak", D=200, unit="img/s", hib=True,
+            metric="ssd300_vgg16 images/sec (forward + postprocess)",
+            name="ssd300_vgg16, 91 classes, 300x300, batch %d per GPU, %s activations, forward + postprocess (SURVEY.md 8(f4); not a "
+                 "BASELINE.json configuration)"),
 }
 
 
@@ -117,7 +121,21 @@ def cpu_reference(cfg_id, n_images, steps, warmup, threads=None):
     torch.set_num_threads(cores)
     S, K = cfg["S"], cfg["K"]
     stages = {}
-    if cfg["model"] == "post":
+    if cfg["model"] == "vgg":
+        model = demonet_b200.ssd300_vgg16(num_classes=K)              # state_dict template only
+        sd = weights.seeded_vgg_state_dict(model.state_dict())
+        x = weights.synthetic_images(n_images, S)
+        anchors = torch.from_numpy(dplan.default_boxes_for([(38, 38), (19, 19), (10, 10), (5, 5), (3, 3), (1, 1)], 300,
+                                                           [[2], [2, 3], [2, 3], [2, 3], [2], [2]],
+                                                           scales=[0.07, 0.15, 0.33, 0.51, 0.69, 0.87, 1.05], steps=[8, 16, 32, 64, 100, 300]))
+
+        def step():
+            with torch.no_grad():
+                cls, reg, _ = net_ref.vgg_forward_raw(sd, x, "fp32", K, times=stages)
+                t0 = time.perf_counter()
+                net_ref.postprocess_detections_torch(cls, reg, anchors, (S, S), 0.01, 0.45, 200, 400)
+                stages["postprocess"] = stages.get("postprocess", 0.0) + time.perf_counter() - t0
+    elif cfg["model"] == "post":
         g = torch.Generator().manual_seed(7)
         logits = torch.randn(n_images, 3234, K, generator=g) * 4.0
         bbox = torch.randn(n_images, 3234, 4, generator=g) * 1.5
@@ -190,13 +208,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    n = args.cpu_sample or (8 if cfg["model"] == "post" else (8 if cfg["model"] == "v2" else 32))
+    n = args.cpu_sample or (8 if cfg["model"] in ("post", "v2", "vgg") else 32)
     steps = max(1, min(args.steps, 10 if cfg["model"] == "v3" else 4))     # bounded: the whole run ends within minutes
     warm = max(1, min(args.warmup, 3))
     blk = cpu_baseline_block(args.config, n, steps, warm)
     workload = {"v3": "ssdlite320_mobilenet_v3_large 91 classes 320x320 forward+postprocess on the host CPU",
                 "v2": "ssd_lite_mobilenet_v2 21 classes 512x512 forward+legacy PostProcess on the host CPU",
-                "post": "postprocess stress (3234 anchors x 91 classes, thr .001, top-k 400, NMS .55) on the host CPU"}[cfg["model"]]
+                "post": "postprocess stress (3234 anchors x 91 classes, thr .001, top-k 400, NMS .55) on the host CPU",
+                "vgg": "ssd300_vgg16 91 classes 300x300 forward+postprocess on the host CPU"}[cfg["model"]]
     line = {"impl": "reference", "metric": cfg["metric"], "value": blk["value"], "unit": cfg["unit"], "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": None, "higher_is_better": cfg["hib"], "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -476,7 +495,79 @@ def main():
     line = {"metric": cfg["metric"], "unit": cfg["unit"], "n_gpus": world, "steps": args.steps, "warmup": warm,
             "higher_is_better": cfg["hib"], "scaling": cfg["scaling"], "vs_baseline": None, "data": "synthetic"}
 
-    if cfg["model"] == "post":
+    if cfg["model"] == "vgg":
+        # ---------------- ssd300_vgg16, layer by layer from Python (tensor-bound) -----------------------
+        from demonet_b200 import ops, vgg as dvgg
+        model = demonet_b200.ssd300_vgg16(num_classes=K, act_dtype=args.act_dtype)
+        model.load_state_dict(weights.seeded_vgg_state_dict(model.state_dict()))
+        model = model.to(dev)
+        imgs_host = weights.synthetic_images(B, S, seed=1 + rank).pin_memory()
+        imgs = imgs_host.to(dev)
+        anchors = model.anchors(dev)
+        keep = {}
+
+        def step_device():
+            cls, reg = model.head_outputs(imgs)
+            keep["out"] = ops.postprocess_padded(cls, reg, anchors, (S, S), model.score_thresh, model.nms_thresh,
+                                                 model.detections_per_img, model.topk_candidates)
+
+        stage = torch.empty_like(imgs)
+
+        def step_host():
+            stage.copy_(imgs_host, non_blocking=True)
+            cls, reg = model.head_outputs(stage)
+            out = ops.postprocess_padded(cls, reg, anchors, (S, S), model.score_thresh, model.nms_thresh,
+                                         model.detections_per_img, model.topk_candidates)
+            keep["host"] = [t.to("cpu", non_blocking=True) for t in out]
+        total_ms, clocks = timed(step_device, args.steps, warm, sampler)
+        # algorithmic flops of the convolutions (2 * MAC, unpadded channels)
+        flops, hw, launches = 0, S, 0
+        for op in dvgg._VGG:
+            if op[0] == "first":
+                flops += 2 * hw * hw * 27 * 64
+                launches += 1
+            elif op[0] == "conv":
+                ho = (hw + 2 * op[5] - 2 * op[6] - 1) // op[4] + 1
+                flops += 2 * ho * ho * op[2] * op[3] * 9
+                hw = ho
+                launches += 1
+            elif op[0] == "pw":
+                flops += 2 * hw * hw * op[2] * op[3]
+                launches += 1
+            elif op[0] == "pool":
+                k, st_, p, ceil = op[1:]
+                hw = -(-(hw + 2 * p - k) // st_) + 1 if ceil else (hw + 2 * p - k) // st_ + 1
+                launches += 1
+            elif op[0] == "tap_l2norm":
+                launches += 1
+        for (gh, gw), c, a in zip(dvgg._GRIDS, dvgg._FEATURE_CHANNELS, model.num_anchors):
+            flops += 2 * gh * gw * c * a * (K + 4) * 9
+            launches += 2
+        launches += 14
+        step_ms = total_ms / args.steps
+        tf = flops * B / (step_ms * 1e-3) / 1e12
+        peak_tf = None
+        try:
+            peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            peak_tf = 1392.3
+        line.update(value=to_metric(total_ms, args.steps), ms_per_step=step_ms, dtype=model.act_dtype, clocks=clocks,
+                    config={"workload": cfg["name"] % (B, model.act_dtype), "baseline_config": None, "batch_per_gpu": B,
+                            "weights": "seeded re-init 1234 with scaled heads (demonet_b200/seeded.py)", "images": "torch.rand seed 1+rank",
+                            "l2": "activations larger than L2 (%.0f MB after conv1_2)" % (B * S * S * 64 * 2 / 1e6),
+                            "cuda_graph": False, "gflop_per_image": flops / 1e9},
+                    gpu_launches=launches * args.steps, gpu_launches_per_step=launches)
+        if not args.no_extras:
+            e2e_ms, _ = timed(step_host, args.steps, warm)
+            line["e2e"] = {"value": to_metric(e2e_ms, args.steps), "unit": cfg["unit"], "ms_per_step": e2e_ms / args.steps,
+                           "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
+                           "api": "pinned fp32 images in (H2D inside the timed region), layer-by-layer C-ABI calls, detections out"}
+            line["roofline"] = {"kernel": "conv3x3_tc_kernel + pwconv_tc_kernel (whole forward)", "bound": "tensor", "achieved": tf,
+                                "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                                "note": "algorithmic conv flops of the whole step over the whole step time (pools, L2-norm, "
+                                        "post-processing included in the time)"}
+    elif cfg["model"] == "post":
         # ---------------- config 4: the post-processing entry point alone --------------------------------------
         P = 3234
         g = torch.Generator().manual_seed(7 + rank)
@@ -716,7 +807,7 @@ def main():
                 os.sched_setaffinity(0, orig_affinity)          # the CPU baseline gets every core again
             except Exception:
                 pass
-        n = args.cpu_sample or (4 if cfg["model"] == "post" else (4 if cfg["model"] == "v2" else 32))
+        n = args.cpu_sample or (4 if cfg["model"] in ("post", "v2", "vgg") else 32)
         line["cpu_baseline"] = cpu_baseline_block(args.config, n, 3, 1)
     if rank == 0:
         print(json.dumps(line), file=_claim_stdout(), flush=True)

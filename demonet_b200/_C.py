@@ -77,6 +77,8 @@ _SIGNATURES = {
                            c_int, c_int64, c_int64, c_void_p]),
     "dn_conv3x3_first": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,
                                  c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_im2col3x3_first": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int,
+                                   c_void_p]),
     "dn_maxpool2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dn_l2norm_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "dn_stem_conv": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p,

@@ -1,6 +1,7 @@
 // The small memory-bound operators ssd300_vgg16 needs next to the tensor-core convolutions, sm_100a:
-//   dn_conv3x3_first   normalise + dense 3x3 stride-1 conv on the 3-channel image + ReLU  (vgg features[0:2];
+//   dn_conv3x3_first   normalise + dense 3x3 stride-1 conv on the 3-channel image + ReLU  (vgg features[0:2], fp32 SIMT;
 //                      GeneralizedRCNNTransform.normalize, transform.py:129-138, folded in like the SSDLite stem)
+//   dn_im2col3x3_first the same layer's tensor-core form: normalised 27-tap rows (padded to 32) for dn_pwconv
 //   dn_maxpool2d       nn.MaxPool2d(k, s, p, ceil_mode) on NHWC 16-bit activations (vgg features; ceil_mode patched in at
 //                      ssd_vgg16.py:36-37; the 3x3 s1 p1 "pool5" of ssd_vgg16.py:84)
 //   dn_l2norm_scale    scale_weight * F.normalize(x) over the channels (ssd_vgg16.py:98-100)
@@ -10,29 +11,86 @@
 
 namespace dn {
 
-// thread = one output pixel x 16 output channels; taps of the 27 x Cout filter in shared memory
+// thread = two horizontally adjacent output pixels x 32 output channels (blockIdx.y selects the channel half, so every lane
+// of a block reads the same filter taps: broadcast LDS.128, one load per 8 FMAs); the 27 x Cout filter lives in shared memory
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                      uint4* __restrict__ y, int B, int H, int W, float3 mean, float3 rstd) {
-    __shared__ float ws[27 * COUT];
+    __shared__ __align__(16) float ws[27 * COUT];
     __shared__ float bs[COUT];
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) ws[i] = __ldg(w + i);
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = __ldg(bias + i);
     pdl_trigger();
     __syncthreads();
     pdl_wait();
-    constexpr int G = COUT / 16;
+    const int half = blockIdx.y;
+    const int Wp = (W + 1) >> 1;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)B * H * W;
-    if (t >= npix * G) return;
-    const int grp = (int)(t % G);
-    const long long pix = t / G;
-    const int x = (int)(pix % W), yy = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    float acc[16];
+    if (t >= (long long)B * H * Wp) return;
+    const int xp = (int)(t % Wp), yy = (int)((t / Wp) % H), b = (int)(t / ((long long)Wp * H));
+    const int x0 = 2 * xp;
+    float acc[2][32];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = bs[grp * 16 + i];
+    for (int i = 0; i < 32; ++i) acc[0][i] = acc[1][i] = bs[half * 32 + i];
     const float mu[3] = {mean.x, mean.y, mean.z}, rs[3] = {rstd.x, rstd.y, rstd.z};
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const float* plane = img + ((long long)b * 3 + ci) * H * W;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int iy = yy + kh - 1;
+            float in[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ix = x0 + j - 1;
+                in[j] = 0.f;                                          // zero padding of the NORMALISED image
+                if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+                    in[j] = __fmul_rn(__fsub_rn(__ldg(plane + (long long)iy * W + ix), mu[ci]), rs[ci]);
+            }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4* wt = reinterpret_cast<const float4*>(ws + ((ci * 3 + kh) * 3 + kw) * COUT + half * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 wv = wt[q];
+                    acc[0][q * 4 + 0] = fmaf(in[kw], wv.x, acc[0][q * 4 + 0]);
+                    acc[0][q * 4 + 1] = fmaf(in[kw], wv.y, acc[0][q * 4 + 1]);
+                    acc[0][q * 4 + 2] = fmaf(in[kw], wv.z, acc[0][q * 4 + 2]);
+                    acc[0][q * 4 + 3] = fmaf(in[kw], wv.w, acc[0][q * 4 + 3]);
+                    acc[1][q * 4 + 0] = fmaf(in[kw + 1], wv.x, acc[1][q * 4 + 0]);
+                    acc[1][q * 4 + 1] = fmaf(in[kw + 1], wv.y, acc[1][q * 4 + 1]);
+                    acc[1][q * 4 + 2] = fmaf(in[kw + 1], wv.z, acc[1][q * 4 + 2]);
+                    acc[1][q * 4 + 3] = fmaf(in[kw + 1], wv.w, acc[1][q * 4 + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        if (x0 + p >= W) break;
+        const long long pix = ((long long)b * H + yy) * W + x0 + p;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(acc[p][h * 8 + i], 0.f);
+            y[(pix * COUT + half * 32) / 8 + h] = pack8(f);
+        }
+    }
+}
+
+// im2col of the normalised 3-channel image for the tensor-core form of the first convolution: thread = one pixel, writes
+// the 27 taps ((ci*3+kh)*3+kw major, zero padding) + 5 zeros as one 64-byte row of 16-bit values
+__global__ void __launch_bounds__(256)
+im2col3x3_first_kernel(const float* __restrict__ img, uint4* __restrict__ cols, int B, int H, int W, float3 mean, float3 rstd) {
+    pdl_trigger();
+    pdl_wait();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * H * W) return;
+    const int x = (int)(t % W), yy = (int)((t / W) % H), b = (int)(t / ((long long)W * H));
+    const float mu[3] = {mean.x, mean.y, mean.z}, rs[3] = {rstd.x, rstd.y, rstd.z};
+    float v[32];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
         const float* plane = img + ((long long)b * 3 + ci) * H * W;
@@ -42,22 +100,17 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ w,
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const int ix = x + kw - 1;
-                float v = 0.f;                                        // zero padding of the NORMALISED image
+                float f = 0.f;
                 if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
-                    v = __fmul_rn(__fsub_rn(__ldg(plane + (long long)iy * W + ix), mu[ci]), rs[ci]);
-                const float* wt = ws + ((ci * 3 + kh) * 3 + kw) * COUT + grp * 16;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wt[i], acc[i]);
+                    f = __fmul_rn(__fsub_rn(__ldg(plane + (long long)iy * W + ix), mu[ci]), rs[ci]);
+                v[(ci * 3 + kh) * 3 + kw] = f;
             }
         }
     }
-    float f[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaxf(acc[h * 8 + i], 0.f);
-        y[(pix * COUT + grp * 16) / 8 + h] = pack8(f);
-    }
+    for (int h = 0; h < 4; ++h) cols[t * 4 + h] = pack8(v + h * 8);
 }
 
 // thread = one output pixel x 8 channels
@@ -131,9 +184,22 @@ extern "C" int dn_conv3x3_first(const float* images, const float* w, const float
     // (x - mean) / std with the division replaced by the reciprocal only where it is exact enough: the reference's
     // std = 1 / 255 (ssd_vgg16.py:199) -> rstd = 255 up to the rounding of 1 / 255 itself
     const float3 rstd = make_float3(1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2]);
-    const long long threads = (long long)B * H * W * (Cout / 16);
-    launch_pdl(conv3x3_first_kernel<64>, (unsigned)ceil_div<long long>(threads, 256), 256, 0, (cudaStream_t)stream_, images, w, bias,
-               (uint4*)y, B, H, W, mean, rstd);
+    const long long threads = (long long)B * H * ((W + 1) / 2);
+    launch_pdl(conv3x3_first_kernel<64>, dim3((unsigned)ceil_div<long long>(threads, 256), Cout / 32), 256, 0, (cudaStream_t)stream_,
+               images, w, bias, (uint4*)y, B, H, W, mean, rstd);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+extern "C" int dn_im2col3x3_first(const float* images, const float* mean3_host, const float* std3_host, void* cols, int B, int H,
+                                  int W, void* stream_) {
+    DN_REQUIRE(images && mean3_host && std3_host && cols, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(B > 0 && H > 0 && W > 0, DN_ERR_INVALID, "bad shape");
+    const float3 mean = make_float3(mean3_host[0], mean3_host[1], mean3_host[2]);
+    const float3 rstd = make_float3(1.f / std3_host[0], 1.f / std3_host[1], 1.f / std3_host[2]);
+    const long long threads = (long long)B * H * W;
+    launch_pdl(im2col3x3_first_kernel, (unsigned)ceil_div<long long>(threads, 256), 256, 0, (cudaStream_t)stream_, images,
+               (uint4*)cols, B, H, W, mean, rstd);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }

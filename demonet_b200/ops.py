@@ -378,6 +378,18 @@ def conv3x3_first(images: Tensor, w: Tensor, bias: Tensor, mean, std, act_dtype:
     return y
 
 
+def im2col3x3_first(images: Tensor, mean, std, act_dtype: str = None) -> Tensor:
+    """Normalised 3x3 neighbourhoods of a fp32 [B,3,H,W] batch as 16-bit rows [B*H*W, 32] (27 taps + 5 zeros)."""
+    _require_cuda(images)
+    B, _, H, W = images.shape
+    cols = torch.empty(B * H * W, 32, dtype=_C.torch_dtype(act_dtype), device=images.device)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    with torch.cuda.device(images.device):
+        _CL(cols).dn_im2col3x3_first(images.contiguous().data_ptr(), m, s, cols.data_ptr(), B, H, W, _stream(images))
+    return cols
+
+
 def maxpool2d(x: Tensor, k: int, stride: int, padding: int = 0, ceil_mode: bool = False) -> Tensor:
     """nn.MaxPool2d on 16-bit NHWC activations."""
     _require_cuda(x)

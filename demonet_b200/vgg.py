@@ -5,12 +5,14 @@ demonet/models/generalized_ssd.py:25-92).
 Same constructor arguments, `state_dict` keys (71) and `forward(images) -> List[Dict[boxes, scores, labels]]` contract as the
 reference, inference only.  Every convolution runs on the tcgen05 tensor cores -- the dense 3x3 ones as an implicit GEMM
 (`dn_conv3x3`), the 1x1 ones on the pointwise GEMM of the SSDLite path (`dn_pwconv`) -- with 16-bit NHWC activations and
-fp32 accumulation; the first convolution folds the input normalisation in (`dn_conv3x3_first`); max-pooling and the
+fp32 accumulation; the first convolution (3 -> 64) is `dn_im2col3x3_first` (normalisation folded in, 27 taps padded to one
+32-wide k-block) + the pointwise GEMM, or the exact-fp32 SIMT kernel `dn_conv3x3_first` with `first_conv="direct"`; max-pooling and the
 L2-normalisation of conv4_3 are small memory-bound kernels; the SSD heads write fp32 logits / box regression straight
 into the [B, 8732, K] layout, and the post-processing is `dn_postprocess`, the kernels of the SSDLite path.
 Unlike the SSDLite engine this model is driven layer by layer from Python (25 launches per batch, no CUDA graph): it is
 tensor-bound (31 GMAC per image), not launch-bound.
 """
+import os
 import warnings
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -50,8 +52,11 @@ class SSD300VGG16B200(nn.Module):
     size = (300, 300)
 
     def __init__(self, num_classes: int = 91, score_thresh: float = 0.01, nms_thresh: float = 0.45, detections_per_img: int = 200,
-                 topk_candidates: int = 400, image_mean=None, image_std=None, act_dtype: Optional[str] = None):
+                 topk_candidates: int = 400, image_mean=None, image_std=None, act_dtype: Optional[str] = None, first_conv: Optional[str] = None):
         super().__init__()
+        self.first_conv = first_conv or os.environ.get("DN_VGG_FIRST", "gemm")
+        if self.first_conv not in ("gemm", "direct"):
+            raise ValueError("first_conv must be 'gemm' or 'direct'")
         self.num_classes = num_classes
         self.score_thresh, self.nms_thresh = score_thresh, nms_thresh
         self.detections_per_img, self.topk_candidates = detections_per_img, topk_candidates
@@ -119,8 +124,11 @@ class SSD300VGG16B200(nn.Module):
         def conv(prefix):
             w = sd[prefix + ".weight"].detach().float()
             n, c, k, _ = w.shape
-            if c == 3:                                   # first layer: fp32 [27][64], (ci*3+kh)*3+kw major
+            if c == 3:                                   # first layer: fp32 [27][64], (ci*3+kh)*3+kw major ...
                 wk = w.permute(1, 2, 3, 0).reshape(27, n)
+                w32 = torch.zeros(n, 32)                 # ... and its GEMM form, 16-bit [64][32] K-major (27 taps + 5 zeros)
+                w32[:, :27] = w.reshape(n, 27)
+                out[prefix + "/gemm"] = w32.to(h16).contiguous().to(device)
             elif k == 3:                                 # [9][N][C], tap = kh*3+kw major
                 wk = w.permute(2, 3, 0, 1).reshape(9, n, c).to(h16)
             else:
@@ -152,8 +160,11 @@ class SSD300VGG16B200(nn.Module):
         x, feats = None, []
         for op in _VGG:
             kind = op[0]
-            if kind == "first":
+            if kind == "first" and self.first_conv == "direct":
                 x = ops.conv3x3_first(images, *W[op[1]], self.image_mean, self.image_std, act_dtype=self.act_dtype)
+            elif kind == "first":
+                cols = ops.im2col3x3_first(images, self.image_mean, self.image_std, act_dtype=self.act_dtype)
+                x = ops.pwconv(cols, W[op[1] + "/gemm"], W[op[1]][1], act="relu").view(B, images.shape[2], images.shape[3], op[3])
             elif kind == "conv":
                 x = ops.conv3x3(x, *W[op[1]], stride=op[4], padding=op[5], dilation=op[6], act="relu")
             elif kind == "pw":
@@ -235,7 +246,7 @@ def ssd300_vgg16(pretrained: bool = False, progress: bool = True, num_classes: i
         raise NotImplementedError("pretrained_backbone=True needs a download; load the reference's state_dict instead")
     for k in ("iou_thresh", "positive_fraction"):          # training-only arguments of SSD.__init__
         kwargs.pop(k, None)
-    allowed = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std", "act_dtype"}
+    allowed = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std", "act_dtype", "first_conv"}
     unknown = sorted(set(kwargs) - allowed)
     if unknown:
         raise TypeError("SSD.__init__() got an unexpected keyword argument '%s'" % unknown[0])

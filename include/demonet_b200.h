@@ -136,6 +136,13 @@ int dn_conv3x3(const void* x, const void* w, const float* bias, void* y, int B, 
 int dn_conv3x3_first(const float* images, const float* w, const float* bias, const float* mean3_host, const float* std3_host,
                      void* y, int B, int H, int W, int Cout, void* stream);
 
+/* The tensor-core form of the same layer: writes the normalised 3x3 neighbourhood of every pixel as one row of 32 16-bit
+ * values (27 taps, (ci*3+kh)*3+kw major, zero padding at the border, 5 trailing zeros) -- cols: [B*H*W, 32] -- so that
+ * dn_pwconv(cols, w16 [64][32], bias, relu) is the convolution (K = 32, one tcgen05 k-block).  The image values are rounded
+ * to the 16-bit activation type once, like the input of every later layer. */
+int dn_im2col3x3_first(const float* images, const float* mean3_host, const float* std3_host, void* cols, int B, int H, int W,
+                       void* stream);
+
 /* nn.MaxPool2d(k, stride, pad, ceil_mode) on 16-bit NHWC activations (vgg features; ceil_mode patched in at
  * ssd_vgg16.py:36-37; the 3x3 stride-1 "pool5" of ssd_vgg16.py:84). */
 int dn_maxpool2d(const void* x, void* y, int B, int H, int W, int C, int k, int stride, int pad, int ceil_mode, void* stream);

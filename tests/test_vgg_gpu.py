@@ -27,10 +27,10 @@ def _rel(a, b):
     return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
 
 
-@pytest.mark.parametrize("act_dtype", ["fp16", "bf16"])
-def test_head_outputs_features_and_detections(golden_dir, act_dtype):
+@pytest.mark.parametrize("act_dtype,first_conv", [("fp16", "gemm"), ("fp16", "direct"), ("bf16", "gemm")])
+def test_head_outputs_features_and_detections(golden_dir, act_dtype, first_conv):
     g = np.load(os.path.join(golden_dir, "ssd300_vgg16.npz"))
-    model, sd = _model(act_dtype=act_dtype)
+    model, sd = _model(act_dtype=act_dtype, first_conv=first_conv)
     x = weights.synthetic_images(2, 300)
     cls, reg, feats = model.head_outputs(x.cuda(), return_features=True)
     with torch.no_grad():
@@ -46,12 +46,12 @@ def test_head_outputs_features_and_detections(golden_dir, act_dtype):
     m = parity.head_metrics(cls.cpu(), reg.cpu(), ocls, oreg, anchors, (300, 300))
     gold = [{"boxes": g["det_boxes"][i], "labels": g["det_labels"][i]} for i in range(2)]
     m["top100_match"] = parity.detection_match(dets, gold)                                      # the reference's own detections
-    print("[parity] ssd300_vgg16 B=2 vs fp32 reference [%s]: %s" % (act_dtype, parity.format_metrics(m)))
+    print("[parity] ssd300_vgg16 B=2 vs fp32 reference [%s, first conv %s]: %s" % (act_dtype, first_conv, parity.format_metrics(m)))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         import json
         with open(os.path.join(out, "parity_report.jsonl"), "a") as f:
-            f.write(json.dumps({"case": "ssd300_vgg16 B=2 vs fp32 reference [%s]" % act_dtype, **m}) + "\n")
+            f.write(json.dumps({"case": "ssd300_vgg16 B=2 vs fp32 reference [%s, first conv %s]" % (act_dtype, first_conv), **m}) + "\n")
     assert m["logits_rel_rms"] < tol["rel"] and m["bbox_rel_rms"] < tol["rel"], m
     assert m["score_mean_abs"] < tol["score_mean"] and m["box_mean_abs_px"] < tol["box_mean"], m
     assert m["top100_match"] >= tol["top100"], m

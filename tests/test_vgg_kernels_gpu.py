@@ -73,6 +73,31 @@ def test_first_conv_with_normalisation(S, dt):
     _close(dt, y, ref, 2e-2)                                              # inputs are ~ +-128: fp32 summation noise ~ 1e-3 relative
 
 
+@pytest.mark.parametrize("S", [300, 37])
+def test_first_conv_as_im2col_plus_gemm(S, dt):
+    """The tensor-core form of the first layer: the im2col rows are the normalised taps of F.unfold bit for bit (after the
+    one rounding to the activation type), and rows x the 32-wide K-major filter through dn_pwconv is the convolution."""
+    g = torch.Generator().manual_seed(S + 1)
+    img = torch.rand(2, 3, S, S, generator=g).cuda()
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.05).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    mean, std = [0.48235, 0.45882, 0.40784], [1.0 / 255.0] * 3
+    name = {torch.float16: "fp16", torch.bfloat16: "bf16"}[dt]
+    cols = ops.im2col3x3_first(img, mean, std, act_dtype=name)
+    assert cols.shape == (2 * S * S, 32) and cols.dtype == dt
+    m = torch.tensor(mean, device="cuda")[None, :, None, None]
+    rs = (1.0 / torch.tensor(std, dtype=torch.float32, device="cuda"))[None, :, None, None]          # fp32 division, like the entry
+    norm = (img - m) * rs                                                  # the kernel's own two fp32 roundings
+    want = F.unfold(norm, 3, padding=1).view(2, 27, S * S).permute(0, 2, 1).reshape(-1, 27).to(dt)
+    assert torch.equal(cols[:, :27], want) and float(cols[:, 27:].abs().sum()) == 0
+    w32 = torch.zeros(64, 32, device="cuda")
+    w32[:, :27] = w.reshape(64, 27)
+    y = ops.pwconv(cols, w32.to(dt), b, act="relu").view(2, S, S, 64)
+    sd = torch.tensor(std, device="cuda")[None, :, None, None]
+    ref = F.relu(F.conv2d((img - m) / sd, w, b, 1, 1)).permute(0, 2, 3, 1)
+    _close(dt, y, ref, 6e-2 if dt == torch.float16 else 0.5)               # inputs ~ +-128 rounded to the activation type
+
+
 @pytest.mark.parametrize("H,W,C,k,s,p,ceil", [(300, 300, 64, 2, 2, 0, False), (75, 75, 256, 2, 2, 0, True), (19, 19, 512, 3, 1, 1, False),
                                               (38, 38, 512, 2, 2, 0, False), (7, 9, 8, 2, 2, 0, True)])
 def test_maxpool(H, W, C, k, s, p, ceil, dt):
