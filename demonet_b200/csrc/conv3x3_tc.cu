@@ -68,6 +68,46 @@ __device__ __forceinline__ float c3_act(float v) {
     return v;
 }
 
+
+// the storing half of the epilogue: a warp's 32 rows x 32 staged columns, lanes = 8 column groups x 4 rows per pass, so that a
+// row's 32 columns leave as one contiguous run; `out_row` is each lane's own row offset (-1: not stored), shared by shuffle
+__device__ __forceinline__ void c3_store_rows(const PwEpilogue& ep, const float* stg, long long out_row, int lane, int col0, int col_end) {
+    const int cg = (lane & 7) * 4;
+    const int n = col0 + cg;
+    const int cnt = col_end - n;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const long long orow = __shfl_sync(0xffffffffu, out_row, r);
+        if (orow >= 0 && cnt > 0) {
+            const float4 o = *reinterpret_cast<const float4*>(stg + r * C3_STAGE_PITCH + cg);
+            const float f[4] = {o.x, o.y, o.z, o.w};
+            if (ep.out_fp32) {
+                float* dst = reinterpret_cast<float*>(ep.y) + orow + n;
+                if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(dst) = o;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < cnt) dst[i] = f[i];
+                }
+            } else {
+                dn_half_t* dst = reinterpret_cast<dn_half_t*>(ep.y) + orow + n;
+                if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+                    uint2 pk;
+                    pk.x = float2_to_h2(f[0], f[1]);
+                    pk.y = float2_to_h2(f[2], f[3]);
+                    *reinterpret_cast<uint2*>(dst) = pk;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < cnt) dst[i] = float_to_half(f[i]);
+                }
+            }
+        }
+    }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, PwEpilogue ep, ConvGeom g,
@@ -197,40 +237,214 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     *reinterpret_cast<float4*>(stg + lane * C3_STAGE_PITCH + j) = o;
                 }
                 __syncwarp();
-                const int cg = (lane & 7) * 4;
-                const int n = n0 + c0 + cg;
-                const int cnt = n0 + n_valid - n;
+                c3_store_rows(ep, stg, out_row, lane, n0 + c0, n0 + n_valid);
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars->tmem_empty[buf])) : "memory");
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+}
+
+
+// ---- halo variant (stride 1, dilation 1, padding 1) ---------------------------------------------------------------
+// The 9 taps of a patch read the SAME (TH + 2) x (TW + 2) input window, shifted.  The kernel above fetches that window nine
+// times (nine boxes of 128 rows from L2 per k-block: at 64 / 128 channels the layer is bound by L2 -> shared-memory traffic,
+// not by the tensor pipe).  Here the window is fetched ONCE per k-block as a [TH + 2][PW = TW + 2][64] box, and the M tile
+// is laid out with the window's own row pitch: GEMM row i <-> patch pixel (i / PW, i % PW); the PW - TW = 2 rightmost
+// columns of every patch row are dummies that are computed and never stored.  With that pitch the A operand of tap
+// (dy, dx) is the SAME shared-memory tile started (dy * PW + dx) rows later -- a descriptor start-address offset of
+// (dy * PW + dx) * 128 bytes -- so one 24 KB box feeds 36 UMMAs instead of 4.  (Measured on B200: the 128-byte swizzle is
+// a function of the ABSOLUTE shared-memory address bits [7,10), so a start address that is not a multiple of 8 rows needs
+// nothing else; setting the descriptor's base-offset field to (address >> 7) & 7 on top of that gives wrong products.)  The filter is either resident for the whole kernel (9 * C * N * 2 bytes fit next to the window
+// ring: conv1_2) or streamed through its own ring by a second producer warp.
+constexpr int CH_THREADS = C3_THREADS + 32;          // + warp 10: filter producer
+constexpr int CH_MAX_A = 4, CH_MAX_W = 8;
+
+struct HaloGeom {
+    int B, H, W, C, N;
+    int TH, TW, PW;              // patch, row pitch PW = TW + 2
+    int tiles_x, tiles_y;
+    int a_stage_bytes;           // (128 + 2 * PW + 2) rows of 128 B, rounded up to 1024
+    int w_resident;              // 1: all 9 * C / 64 filter tiles stay in shared memory (n_tiles == 1)
+};
+
+struct __align__(8) HaloBarriers {
+    uint64_t a_full[CH_MAX_A], a_empty[CH_MAX_A];
+    uint64_t w_full[CH_MAX_W], w_empty[CH_MAX_W];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base, pad;
+};
+
+template <int ACT>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, PwEpilogue ep, HaloGeom g,
+                    int block_n, int n_tiles, int num_tiles, int na, int nw, int tmem_cols) {
+    extern __shared__ __align__(1024) uint8_t c3_smem_raw[];
+    __shared__ __align__(1024) uint8_t s_stage_raw[C3_EPI_WARPS][C3_STAGE_BYTES];
+    uint8_t* smem = c3_smem_raw + ((1024u - (smem_u32(c3_smem_raw) & 1023u)) & 1023u);
+    const int kblocks = g.C / C3_BLOCK_K;
+    const int w_tile_bytes = block_n * C3_BLOCK_K * 2;
+    const int w_slots = g.w_resident ? 9 * kblocks : nw;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_w = smem + na * g.a_stage_bytes;
+    HaloBarriers* bars = reinterpret_cast<HaloBarriers*>(smem_w + (size_t)w_slots * w_tile_bytes);
+    float* s_bias = reinterpret_cast<float*>(bars + 1);
+    for (int i = threadIdx.x; i < n_tiles * block_n + 32; i += blockDim.x) s_bias[i] = (i < g.N) ? __ldg(ep.bias + i) : 0.f;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < CH_MAX_A; ++s) {
+            mbar_init(&bars->a_full[s], 1);
+            mbar_init(&bars->a_empty[s], 1);
+        }
+        for (int s = 0; s < CH_MAX_W; ++s) {
+            mbar_init(&bars->w_full[s], 1);
+            mbar_init(&bars->w_empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->tmem_full[b], 1);
+            mbar_init(&bars->tmem_empty[b], C3_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
+    pdl_trigger();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
+
+    const int tiles_xy = g.tiles_x * g.tiles_y;
+    if (warp == 0) {
+        // ===== window producer: one box per (tile, k-block) =====
+        if (elect_one()) {
+            const uint32_t box_bytes = (uint32_t)((g.TH + 2) * g.PW * C3_BLOCK_K * 2);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = tile / n_tiles;
+                const int b = mt / tiles_xy, rem = mt - b * tiles_xy;
+                const int y0 = (rem / g.tiles_x) * g.TH, x0 = (rem % g.tiles_x) * g.TW;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % na;
+                    mbar_wait(&bars->a_empty[s], ((it / na) & 1u) ^ 1u);
+                    mbar_expect_tx(&bars->a_full[s], box_bytes);
+                    tma_load_4d(smem_a + (size_t)s * g.a_stage_bytes, &tmap_a, &bars->a_full[s], kb * C3_BLOCK_K, x0 - 1, y0 - 1, b);
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===== filter producer: resident (loaded once) or one tile per (tile, k-block, tap) =====
+        if (elect_one()) {
+            if (g.w_resident) {
+                mbar_expect_tx(&bars->w_full[0], (uint32_t)(9 * kblocks * w_tile_bytes));
+                for (int kb = 0; kb < kblocks; ++kb)
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d(smem_w + (size_t)(kb * 9 + tap) * w_tile_bytes, &tmap_w, &bars->w_full[0], kb * C3_BLOCK_K, tap * g.N);
+            } else {
+                uint32_t it = 0;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                    const int n0 = (tile % n_tiles) * block_n;
+                    for (int kb = 0; kb < kblocks; ++kb)
+                        for (int tap = 0; tap < 9; ++tap, ++it) {
+                            const int s = it % nw;
+                            mbar_wait(&bars->w_empty[s], ((it / nw) & 1u) ^ 1u);
+                            mbar_expect_tx(&bars->w_full[s], (uint32_t)w_tile_bytes);
+                            tma_load_2d(smem_w + (size_t)s * w_tile_bytes, &tmap_w, &bars->w_full[s], kb * C3_BLOCK_K, tap * g.N + n0);
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: per window, 9 taps x 4 UMMAs =====
+        const uint32_t idesc = make_idesc(C3_BLOCK_M, block_n);
+        uint32_t ita = 0, itw = 0, lt = 0;
+        if (g.w_resident) mbar_wait(&bars->w_full[0], 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            mbar_wait(&bars->tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n;
+            for (int kb = 0; kb < kblocks; ++kb, ++ita) {
+                const int sa = ita % na;
+                mbar_wait(&bars->a_full[sa], (ita / na) & 1u);
+                const uint32_t a_base = smem_u32(smem_a + (size_t)sa * g.a_stage_bytes);
+                for (int tap = 0; tap < 9; ++tap) {
+                    int sw = kb * 9 + tap;
+                    if (!g.w_resident) {
+                        sw = itw % nw;
+                        mbar_wait(&bars->w_full[sw], (itw / nw) & 1u);
+                        ++itw;
+                    }
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = make_smem_desc(a_base + (uint32_t)(((tap / 3) * g.PW + tap % 3) * 128));
+                        const uint64_t dw = make_smem_desc(smem_u32(smem_w + (size_t)sw * w_tile_bytes));
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + (lane >> 3);
-                    const long long orow = __shfl_sync(0xffffffffu, out_row, r);
-                    if (orow >= 0 && cnt > 0) {
-                        const float4 o = *reinterpret_cast<const float4*>(stg + r * C3_STAGE_PITCH + cg);
-                        const float f[4] = {o.x, o.y, o.z, o.w};
-                        if (ep.out_fp32) {
-                            float* dst = reinterpret_cast<float*>(ep.y) + orow + n;
-                            if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                                *reinterpret_cast<float4*>(dst) = o;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    if (i < cnt) dst[i] = f[i];
-                            }
-                        } else {
-                            dn_half_t* dst = reinterpret_cast<dn_half_t*>(ep.y) + orow + n;
-                            if (cnt >= 4 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-                                uint2 pk;
-                                pk.x = float2_to_h2(f[0], f[1]);
-                                pk.y = float2_to_h2(f[2], f[3]);
-                                *reinterpret_cast<uint2*>(dst) = pk;
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    if (i < cnt) dst[i] = float_to_half(f[i]);
-                            }
+                        for (int k = 0; k < C3_BLOCK_K / 16; ++k)
+                            umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | tap | k) != 0 ? 1u : 0u);
+                        if (!g.w_resident) umma_commit(&bars->w_empty[sw]);
+                        if (tap == 8) {
+                            umma_commit(&bars->a_empty[sa]);
+                            if (kb == kblocks - 1) umma_commit(&bars->tmem_full[buf]);
                         }
                     }
+                    __syncwarp();
                 }
+            }
+        }
+    } else {
+        // ===== epilogue: thread = GEMM row = patch pixel (row / PW, row % PW); dummy columns and rows are not stored =====
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            const int mt = tile / n_tiles, n0 = (tile % n_tiles) * block_n;
+            const int b = mt / tiles_xy, rem = mt - b * tiles_xy;
+            const int y0 = (rem / g.tiles_x) * g.TH, x0 = (rem % g.tiles_x) * g.TW;
+            long long out_row = -1;
+            {
+                const int ty = row / g.PW, tx = row - ty * g.PW;
+                const int y = y0 + ty, x = x0 + tx;
+                if (ty < g.TH && tx < g.TW && y < g.H && x < g.W) out_row = ep.row_offset((b * g.H + y) * g.W + x);
+            }
+            const int n_valid = min(block_n, g.N - n0);
+            mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16);
+            float* stg = reinterpret_cast<float*>(s_stage_raw[warp - 2]);
+            for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
+                uint32_t v[32];
+                const bool second = (c0 + 16 < block_n);
+                tmem_ld16(tmem_d + (uint32_t)c0, v);
+                if (second) tmem_ld16(tmem_d + (uint32_t)(c0 + 16), v + 16);
+                const float* sbw = s_bias + n0 + c0;
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = c3_act<ACT>(__uint_as_float(v[j + 0]) + sbw[j + 0]);
+                    o.y = c3_act<ACT>(__uint_as_float(v[j + 1]) + sbw[j + 1]);
+                    o.z = c3_act<ACT>(__uint_as_float(v[j + 2]) + sbw[j + 2]);
+                    o.w = c3_act<ACT>(__uint_as_float(v[j + 3]) + sbw[j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * C3_STAGE_PITCH + j) = o;
+                }
+                __syncwarp();
+                c3_store_rows(ep, stg, out_row, lane, n0 + c0, n0 + n_valid);
                 __syncwarp();
             }
             tcgen05_fence_before();
@@ -290,6 +504,90 @@ static int c3_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilo
     return DN_OK;
 }
 
+// ---- halo variant, host side ----
+static int c3_halo_mode() {                      // DN_C3_HALO: 0 off, 1 on (default)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DN_C3_HALO");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+template <int ACT>
+static int ch_launch(const CUtensorMap& ta, const CUtensorMap& tw, const PwEpilogue& ep, const HaloGeom& g, int bn, int nt, int tiles,
+                     int na, int nw, int cols, unsigned grid, size_t smem, cudaStream_t stream) {
+    static SmemOptIn optin;
+    DN_CHECK_CUDA(optin.ensure(conv3x3_halo_kernel<ACT>, smem));
+    launch_pdl(conv3x3_halo_kernel<ACT>, grid, CH_THREADS, smem, stream, ta, tw, ep, g, bn, nt, tiles, na, nw, cols);
+    DN_CHECK_LAUNCH();
+    return DN_OK;
+}
+
+// returns DN_OK after launching, or 1 when the shape is left to the general kernel
+static int conv3x3_halo(const void* x, const void* w, const PwEpilogue& ep, int B, int H, int W, int C, int N, cudaStream_t stream) {
+    if (W < 8 || H < 2) return 1;
+    HaloGeom g{};
+    g.B = B, g.H = H, g.W = W, g.C = C, g.N = N;
+    // patch: TH * (TW + 2) <= 128 rows; best useful fraction of the 128 GEMM rows, ties -> the smaller window
+    double best = -1.0;
+    for (int tw = std::min(W, 126); tw >= 6; --tw) {
+        const int pw = tw + 2, th = std::min(H, 128 / pw);
+        if (th < 1) continue;
+        const long long tiles = (long long)ceil_div(W, tw) * ceil_div(H, th);
+        const double util = (double)H * W / ((double)tiles * 128.0) - 1e-3 * (double)((th + 2) * pw) / 128.0;
+        if (util > best) best = util, g.TH = th, g.TW = tw, g.PW = pw;
+    }
+    if (best < 0.5) return 1;
+    g.tiles_x = ceil_div(W, g.TW), g.tiles_y = ceil_div(H, g.TH);
+    g.a_stage_bytes = ((128 + 2 * g.PW + 2) * 128 + 1023) & ~1023;
+    const int kblocks = C / C3_BLOCK_K;
+    const int nt = ceil_div(N, 256);
+    int bn = ceil_div(N, nt);
+    bn = nt > 1 ? (bn + 63) & ~63 : (bn + 15) & ~15;
+    int cols = 32;
+    while (cols < 2 * bn) cols <<= 1;
+    const size_t w_tile = (size_t)bn * C3_BLOCK_K * 2;
+    const size_t fixed = 1024 + sizeof(HaloBarriers) + ((size_t)nt * bn + 32) * 4;
+    const size_t cap = (size_t)(227 * 1024 - C3_STATIC_SMEM - 256);
+    int na = 0, nw = 0;
+    if (nt == 1 && fixed + 9 * kblocks * w_tile + 2 * (size_t)g.a_stage_bytes <= cap) {
+        g.w_resident = 1;
+        na = (int)std::min<size_t>(CH_MAX_A, (cap - fixed - 9 * kblocks * w_tile) / g.a_stage_bytes);
+    } else {
+        na = 2;
+        if (fixed + 2 * (size_t)g.a_stage_bytes + 3 * w_tile > cap) return 1;
+        nw = (int)std::min<size_t>(CH_MAX_W, (cap - fixed - 2 * (size_t)g.a_stage_bytes) / w_tile);
+        while (na < 3 && fixed + (size_t)(na + 1) * g.a_stage_bytes + (size_t)nw * w_tile <= cap) ++na;
+    }
+    const size_t smem = fixed + (size_t)na * g.a_stage_bytes + (g.w_resident ? 9 * kblocks : nw) * w_tile;
+    PFN_encodeTiled3 fn = c3_encode_fn();
+    DN_REQUIRE(fn != nullptr, DN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    DN_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0, DN_ERR_INVALID,
+               "dense 3x3: operands must be 16-byte aligned");
+    CUtensorMap ta, tw;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)C3_BLOCK_K, (cuuint32_t)g.PW, (cuuint32_t)(g.TH + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = fn(&ta, DN_TMAP_HALF, 4, const_cast<void*>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DN_REQUIRE(r == CUDA_SUCCESS, DN_ERR_CUDA, "cuTensorMapEncodeTiled (dense 3x3 window) failed (%d)", (int)r);
+    }
+    int rc = make_tmap_h16_2d(&tw, w, 9ll * N, C, bn, C3_BLOCK_K);
+    if (rc) return rc;
+    const long long tiles = (long long)g.tiles_x * g.tiles_y * B * nt;
+    DN_REQUIRE(tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "dense 3x3 problem too large");
+    const unsigned grid = (unsigned)std::min<long long>(sm_count(), tiles);
+    switch (ep.act) {
+        case DN_ACT_RELU: return ch_launch<DN_ACT_RELU>(ta, tw, ep, g, bn, nt, (int)tiles, na, nw, cols, grid, smem, stream);
+        case DN_ACT_RELU6: return ch_launch<DN_ACT_RELU6>(ta, tw, ep, g, bn, nt, (int)tiles, na, nw, cols, grid, smem, stream);
+        case DN_ACT_NONE: return ch_launch<DN_ACT_NONE>(ta, tw, ep, g, bn, nt, (int)tiles, na, nw, cols, grid, smem, stream);
+    }
+    DN_REQUIRE(false, DN_ERR_UNSUPPORTED, "dense 3x3: activation %d not built (none / relu / relu6)", ep.act);
+}
+
 int conv3x3_tc(const void* x, const void* w, const PwEpilogue& ep, int B, int H, int W, int C, int N, int stride, int pad, int dil,
                cudaStream_t stream) {
     DN_REQUIRE(C % C3_BLOCK_K == 0, DN_ERR_UNSUPPORTED, "dense 3x3: input channels must be a multiple of 64 (got %d)", C);
@@ -300,6 +598,10 @@ int conv3x3_tc(const void* x, const void* w, const PwEpilogue& ep, int B, int H,
     g.Ho = (H + 2 * pad - 2 * dil - 1) / stride + 1;
     g.Wo = (W + 2 * pad - 2 * dil - 1) / stride + 1;
     DN_REQUIRE(g.Ho > 0 && g.Wo > 0, DN_ERR_INVALID, "dense 3x3: empty output");
+    if (stride == 1 && dil == 1 && pad == 1 && c3_halo_mode() != 0) {
+        const int rc = conv3x3_halo(x, w, ep, B, H, W, C, N, stream);
+        if (rc <= 0) return rc;
+    }
     c3_pick_patch(B, g.Ho, g.Wo, &g.TB, &g.TH, &g.TW);
     g.tiles_x = ceil_div(g.Wo, g.TW), g.tiles_y = ceil_div(g.Ho, g.TH), g.tiles_b = ceil_div(B, g.TB);
     // N tiling: up to 256 columns per tile (two TMEM buffers of BLOCK_N columns)

@@ -23,7 +23,8 @@ CONV_CASES = [(2, 150, 150, 64, 128, 1, 1, 1), (2, 75, 75, 128, 256, 1, 1, 1), (
               (3, 19, 19, 512, 1024, 1, 6, 6), (3, 19, 19, 256, 512, 2, 1, 1), (5, 10, 10, 128, 256, 2, 1, 1),
               (7, 5, 5, 128, 256, 1, 0, 1), (9, 3, 3, 128, 256, 1, 0, 1), (2, 38, 38, 512, 364, 1, 1, 1),
               (2, 19, 19, 1024, 546, 1, 1, 1), (40, 1, 1, 256, 16, 1, 1, 1), (3, 13, 29, 64, 24, 1, 1, 1),
-              (2, 300, 300, 64, 64, 1, 1, 1), (130, 3, 3, 256, 364, 1, 1, 1)]
+              (2, 300, 300, 64, 64, 1, 1, 1), (130, 3, 3, 256, 364, 1, 1, 1),
+              (2, 20, 9, 64, 40, 1, 1, 1), (1, 8, 8, 128, 16, 1, 1, 1), (3, 77, 51, 64, 96, 1, 1, 1), (2, 10, 10, 512, 546, 1, 1, 1)]
 
 
 @pytest.mark.parametrize("B,H,W,C,N,s,p,d", CONV_CASES)
