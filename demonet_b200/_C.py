@@ -14,7 +14,7 @@ DEFAULT_ACT_DTYPE = os.environ.get("DN_ACT_DTYPE", "fp16")
 LIB_PATHS = {dt: os.path.join(_HERE, "lib", "libdemonet_b200_%s.so" % dt) for dt in ACT_DTYPES}
 LIB_PATH = LIB_PATHS["fp16"]
 
-ABI_VERSION = 3          # include/demonet_b200.h DN_ABI_VERSION
+ABI_VERSION = 4          # include/demonet_b200.h DN_ABI_VERSION
 DN_OK = 0
 DN_ERR_INVALID = -1
 DN_ERR_CUDA = -2
@@ -101,6 +101,11 @@ _SIGNATURES = {
     "dn_batched_nms_workspace_bytes": (c_size_t, [c_int64]),
     "dn_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
                                c_void_p]),
+    "dn_ssd_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dn_ssd_match": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dn_match_quality": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dn_ssd_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_float, ctypes.POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "dn_engine_create": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(ModelDesc), c_int]),
     "dn_engine_destroy": (c_int, [c_void_p]),
     "dn_engine_load_weights": (c_int, [c_void_p, c_void_p, c_size_t]),

@@ -22,8 +22,8 @@ model_urls = {
     "ssd_lite_mobilenet_v2": "./checkpoints/mobilenet_v2/ssd_lite_mobilenet_v2_199.pth",
 }
 
-# kwargs the reference forwards to SSD.__init__ (generalized_ssd.py:154-163); the training-only ones
-# are accepted and ignored because this build is inference only
+# kwargs the reference forwards to SSD.__init__ (generalized_ssd.py:154-163); the training-only ones configure the loss
+# branch (SSDMatcher threshold, hard-negative ratio)
 _SSD_KWARGS = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std"}
 _SSD_TRAIN_KWARGS = {"iou_thresh", "positive_fraction"}
 _ENGINE_KWARGS = {"gemm_impl", "use_cuda_graph", "keep_activations", "pipeline_slots", "act_dtype"}
@@ -65,7 +65,7 @@ def ssdlite320_mobilenet_v3_large(pretrained: bool = False, progress: bool = Tru
     _reject_unknown(kwargs)
     defaults = {"score_thresh": 0.001, "nms_thresh": 0.55, "detections_per_img": 300, "topk_candidates": 300,
                 "image_mean": [0.5, 0.5, 0.5], "image_std": [0.5, 0.5, 0.5]}
-    cfg = {**defaults, **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _ENGINE_KWARGS}}
+    cfg = {**defaults, **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _SSD_TRAIN_KWARGS | _ENGINE_KWARGS}}
     model = SSDLiteB200(_plan.plan_ssdlite320_mobilenet_v3_large(num_classes, 320), postprocess="ssd", **cfg)
     if pretrained:
         state_dict = torch.hub.load_state_dict_from_url(model_urls["ssdlite320_mobilenet_v3_large_coco"],
@@ -88,7 +88,7 @@ def ssd_lite_mobilenet_v2(pretrained: bool = False, image_size: int = 320, score
     flavour = kwargs.pop("postprocess", "legacy")
     _reject_unknown(kwargs)
     cfg = {"nms_thresh": 0.45, "detections_per_img": 100, "topk_candidates": 400,
-           **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _ENGINE_KWARGS}}
+           **{k: v for k, v in kwargs.items() if k in _SSD_KWARGS | _SSD_TRAIN_KWARGS | _ENGINE_KWARGS}}
     cfg["score_thresh"] = score_thresh
     model = SSDLiteB200(_plan.plan_ssd_lite_mobilenet_v2(num_classes, image_size), postprocess=flavour, **cfg)
     if pretrained:

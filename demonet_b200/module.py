@@ -230,7 +230,8 @@ def rescale_boxes_(boxes: Tensor, original_sizes: List[Tuple[int, int]], new_siz
 
 
 class SSDLiteB200(nn.Module):
-    """Inference-only SSDLite detector on the B200 engine.
+    """SSDLite detector on the B200 engine: the eval branch of SSD.forward (detections) and, in training mode, its loss
+    branch evaluated on the engine's head outputs (generalized_ssd.py:321-337; `demonet_b200.loss`).
 
     Args mirror `SSD.__init__` (generalized_ssd.py:154-163): score_thresh, nms_thresh,
     detections_per_img, topk_candidates, image_mean, image_std.  `postprocess` selects the
@@ -240,8 +241,11 @@ class SSDLiteB200(nn.Module):
 
     def __init__(self, plan: _plan.Plan, score_thresh=0.01, nms_thresh=0.45, detections_per_img=200,
                  topk_candidates=400, image_mean=None, image_std=None, postprocess="ssd", init="normal",
-                 gemm_impl=0, use_cuda_graph=True, keep_activations=False, pipeline_slots=0, act_dtype=None):
+                 gemm_impl=0, use_cuda_graph=True, keep_activations=False, pipeline_slots=0, act_dtype=None,
+                 iou_thresh=0.5, positive_fraction=0.25):
         super().__init__()
+        self.iou_thresh = iou_thresh                                          # SSDMatcher(iou_thresh), generalized_ssd.py:184
+        self.neg_to_pos_ratio = (1.0 - positive_fraction) / positive_fraction  # generalized_ssd.py:197
         if postprocess not in ("ssd", "legacy"):
             raise ValueError("postprocess must be 'ssd' or 'legacy'")
         self.plan = plan
@@ -294,12 +298,41 @@ class SSDLiteB200(nn.Module):
             else:
                 mod.register_buffer(parts[-1], torch.tensor(0, dtype=torch.long))
 
-    def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError(
-                "demonet_b200 implements the inference hot path only (SSD.forward eval branch, "
-                "generalized_ssd.py:335-342); training / losses are out of scope")
-        return super().train(False)
+    # train(True) selects the LOSS branch of SSD.forward (generalized_ssd.py:321-337): forward(images, targets) then returns
+    # {'bbox_regression', 'classification'} computed by dn_ssd_match / dn_ssd_loss on the engine's head outputs.  The engine
+    # always runs with the folded running statistics of BatchNorm and produces no gradients for the parameters (they are
+    # registered with requires_grad=False): this is loss EVALUATION; `demonet_b200.loss.compute_loss` is differentiable with
+    # respect to head outputs for callers that train a torch head / backbone.
+
+    def anchors(self, device) -> Tensor:
+        """Default boxes [P,4] on `device` (DefaultBoxGenerator, anchor_utils.py:110-126)."""
+        key = str(device)
+        cache = self.__dict__.setdefault("_anchor_cache", {})
+        if key not in cache:
+            cache[key] = torch.from_numpy(_plan.default_boxes(self.plan)).to(device)
+        return cache[key]
+
+    def _losses(self, images, targets):
+        from . import loss as _loss
+        if targets is None:
+            raise ValueError("In training mode, targets should be passed")                     # generalized_ssd.py:273-274
+        if isinstance(images, Tensor):
+            images = list(images.unbind(0))
+        _loss.check_targets(targets)
+        if not torch.cuda.is_available():
+            raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        S = self.plan.size
+        first = images[0]
+        device = first.device if first.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+        batch = torch.empty(len(images), 3, S, S, dtype=torch.float32, device=device)
+        for i, img in enumerate(images):
+            if sizes[i] != (S, S):
+                resize_bilinear(img.to(device), (S, S), out=batch[i])                           # transform.py:27-53
+            else:
+                batch[i].copy_(img)
+        targets = [{k: v.to(device) for k, v in t.items()} for t in targets]
+        return _loss.detector_losses(self, batch, targets, sizes, self.iou_thresh, self.neg_to_pos_ratio)
 
     # ---- engine management -----------------------------------------------------------------
     # The engine holds BN-folded, re-laid-out copies of the parameters.  They are refreshed when the weights change
@@ -360,7 +393,7 @@ class SSDLiteB200(nn.Module):
     # ---- forward ---------------------------------------------------------------------------
     def forward(self, images: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
         if self.training:
-            raise NotImplementedError("training mode is out of scope")
+            return self._losses(images, targets)
         if isinstance(images, Tensor):
             if images.dim() != 4:
                 raise ValueError("images is expected to be a list of 3d tensors of shape [C, H, W] "

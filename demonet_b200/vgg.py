@@ -47,13 +47,17 @@ _GRIDS = [(38, 38), (19, 19), (10, 10), (5, 5), (3, 3), (1, 1)]
 
 
 class SSD300VGG16B200(nn.Module):
-    """Inference-only SSD300 / VGG16 on the B200 kernels; arguments mirror `SSD.__init__` (generalized_ssd.py:154-163)."""
+    """SSD300 / VGG16 on the B200 kernels; arguments mirror `SSD.__init__` (generalized_ssd.py:154-163).  Eval mode returns
+    detections; training mode evaluates the loss branch (generalized_ssd.py:321-337) on the head outputs (`demonet_b200.loss`)."""
 
     size = (300, 300)
 
     def __init__(self, num_classes: int = 91, score_thresh: float = 0.01, nms_thresh: float = 0.45, detections_per_img: int = 200,
-                 topk_candidates: int = 400, image_mean=None, image_std=None, act_dtype: Optional[str] = None, first_conv: Optional[str] = None):
+                 topk_candidates: int = 400, image_mean=None, image_std=None, act_dtype: Optional[str] = None, first_conv: Optional[str] = None,
+                 iou_thresh: float = 0.5, positive_fraction: float = 0.25):
         super().__init__()
+        self.iou_thresh = iou_thresh                                                                        # generalized_ssd.py:184
+        self.neg_to_pos_ratio = (1.0 - positive_fraction) / positive_fraction                                # generalized_ssd.py:197
         self.first_conv = first_conv or os.environ.get("DN_VGG_FIRST", "gemm")
         if self.first_conv not in ("gemm", "direct"):
             raise ValueError("first_conv must be 'gemm' or 'direct'")
@@ -91,12 +95,6 @@ class SSD300VGG16B200(nn.Module):
                 mod.add_module(name, nn.Module())
             mod = mod._modules[name]
         mod.register_parameter(parts[-1], nn.Parameter(value, requires_grad=False))
-
-    def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError("demonet_b200 implements the inference path only (SSD.forward eval branch); "
-                                      "training / losses are out of scope")
-        return super().train(False)
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -206,6 +204,11 @@ class SSD300VGG16B200(nn.Module):
                 raise TypeError("Expected input images to be of floating type (in range [0, 1]), "
                                 f"but found type {img.dtype} instead")                # transform.py:130-134
             original_sizes.append((int(img.shape[-2]), int(img.shape[-1])))
+        if self.training and targets is None:
+            raise ValueError("In training mode, targets should be passed")                 # generalized_ssd.py:273-274
+        if self.training:
+            from . import loss as _loss
+            _loss.check_targets(targets)
         if not torch.cuda.is_available():
             raise RuntimeError("demonet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         in_dev = images[0].device
@@ -221,6 +224,10 @@ class SSD300VGG16B200(nn.Module):
                     batch[i].copy_(img)
         else:
             batch = torch.stack([im.to(device, torch.float32) for im in images], 0)
+        if self.training:
+            # loss branch (generalized_ssd.py:321-337); parameters carry no gradients: loss evaluation (see demonet_b200.loss)
+            targets = [{k: v.to(device) for k, v in t.items()} for t in targets]
+            return _loss.detector_losses(self, batch, targets, original_sizes, self.iou_thresh, self.neg_to_pos_ratio)
         cls, reg = self.head_outputs(batch)
         boxes, scores, labels, counts = ops.postprocess_padded(cls, reg, self.anchors(device), self.size, self.score_thresh,
                                                                self.nms_thresh, self.detections_per_img, self.topk_candidates)
@@ -244,9 +251,7 @@ def ssd300_vgg16(pretrained: bool = False, progress: bool = True, num_classes: i
         kwargs.pop("size")
     if pretrained_backbone and not pretrained:
         raise NotImplementedError("pretrained_backbone=True needs a download; load the reference's state_dict instead")
-    for k in ("iou_thresh", "positive_fraction"):          # training-only arguments of SSD.__init__
-        kwargs.pop(k, None)
-    allowed = {"score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std", "act_dtype", "first_conv"}
+    allowed = {"iou_thresh", "positive_fraction", "score_thresh", "nms_thresh", "detections_per_img", "topk_candidates", "image_mean", "image_std", "act_dtype", "first_conv"}
     unknown = sorted(set(kwargs) - allowed)
     if unknown:
         raise TypeError("SSD.__init__() got an unexpected keyword argument '%s'" % unknown[0])

@@ -23,7 +23,8 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 3          /* 3: dn_postprocess_scored, dn_engine_get_stats, activation dtype builds */
+#define DN_ABI_VERSION 4          /* 3: dn_postprocess_scored, dn_engine_get_stats, activation dtype builds
+                                     4: dn_ssd_match, dn_match_quality, dn_ssd_loss (training-side operators) */
 
 typedef enum {
     DN_OK = 0,
@@ -232,6 +233,40 @@ int dn_postprocess_profile(const float* cls_logits, const float* bbox_regression
 size_t dn_batched_nms_workspace_bytes(int64_t n);
 int dn_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, double iou_threshold,
                    void* workspace, size_t workspace_bytes, int64_t* keep_out, int64_t* nkeep_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training-side operators: default-box matching and the multibox loss
+ * ---------------------------------------------------------------------------------------- */
+
+/* Workspace of the three entry points below for B images, P default boxes per image and G ground-truth boxes in total. */
+size_t dn_ssd_loss_workspace_bytes(int B, int P, int G);
+
+/* box_ops.box_iou(targets['boxes'], anchors) followed by SSDMatcher(iou_thresh) for every image of a batch
+ * (generalized_ssd.py:326-335; _utils.py:283-323 Matcher.__call__ with low == high threshold, :350-362 the forced match
+ * of each ground-truth box to its best default box).  gt_boxes: fp32 [G,4] xyxy, the images' boxes back to back;
+ * gt_offsets: int32 [B+1] (device), image b owns rows gt_offsets[b] .. gt_offsets[b+1]; anchors: fp32 [P,4] (shared by the
+ * images, anchor_utils.py:110-126); matched_idxs: int64 [B,P] = index of the matched ground-truth box within its image,
+ * or -1.  An image without boxes gets -1 everywhere (generalized_ssd.py:329-332).  Bit-exact against the reference's CPU
+ * result: first maximum on arg-max ties, the larger ground-truth index when two boxes claim one default box. */
+int dn_ssd_match(const float* gt_boxes, const int32_t* gt_offsets, const float* anchors, int B, int P, int G,
+                 float iou_thresh, int64_t* matched_idxs, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SSDMatcher.__call__(match_quality_matrix) (_utils.py:350-362) on a caller-supplied fp32 [M,P] matrix (one image);
+ * matches: int64 [P].  DN_ERR_INVALID with the reference's message for an empty matrix (_utils.py:298-307). */
+int dn_match_quality(const float* quality, int M, int P, float thresh, int64_t* matches, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* SSD.compute_loss (generalized_ssd.py:210-269): smooth-L1 on BoxCoder.encode_single targets (_utils.py:83-127) of the
+ * matched boxes, softmax cross entropy against the matched labels (0 = background), hard-negative mining (the
+ * ceil(neg_to_pos_ratio * #foreground) largest background losses per image), both sums divided by N = max(1, #matched).
+ * cls_logits: fp32 [B,P,K]; bbox_regression: fp32 [B,P,4]; gt_labels: int64 [G]; matched_idxs: int64 [B,P] (dn_ssd_match).
+ * losses (device fp32 [3]) receives {bbox_regression, classification, N}.  grad_cls (fp32 [B,P,K]) / grad_reg (fp32 [B,P,4]),
+ * when not NULL, receive d(classification)/d(cls_logits) and d(bbox_regression loss)/d(bbox_regression).  Sums are
+ * accumulated in double in a fixed order (deterministic).  Equal losses at the mining cut go to the lower index. */
+int dn_ssd_loss(const float* cls_logits, const float* bbox_regression, const float* anchors, const float* gt_boxes,
+                const int64_t* gt_labels, const int32_t* gt_offsets, const int64_t* matched_idxs, int B, int P, int K,
+                int G, float neg_to_pos_ratio, const float* box_weights4_host, float* losses, float* grad_cls,
+                float* grad_reg, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: the whole forward (SSD.forward eval branch, generalized_ssd.py:271-349) as one

@@ -13,8 +13,10 @@ restatements agree with the reference:
   * oracle.boxes_np.batched_nms_vanilla                          == _batched_nms_vanilla indices
   * oracle.boxes_np.postprocess_detections                       == SSD.postprocess_detections
     (given the reference's softmax scores)
+  * oracle.loss_np.box_iou / match_image / compute_loss         == box_iou + SSDMatcher indices (bit for bit),
+    SSD.compute_loss (to fp32 summation order)
 Outputs (small, committed): tests/golden/{v3_ssdlite.npz, v2_ssdlite.npz, nms_cases.npz,
-postprocess_stress.npz, ssd300_vgg16.npz}.  Inputs are regenerated from seeds (oracle/weights.py), never stored.
+postprocess_stress.npz, ssd300_vgg16.npz, ssd_loss.npz}.  Inputs are regenerated from seeds (oracle/weights.py), never stored.
 """
 import hashlib
 import os
@@ -26,7 +28,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import boxes_np, net_ref, nms_c, refshim, weights  # noqa: E402
+from oracle import boxes_np, loss_np, net_ref, nms_c, refshim, weights  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 LOGIT_ROW_STRIDE = 13        # store every 13th anchor row of the logits to keep fixtures small
@@ -297,6 +299,50 @@ def gen_stress():
     print("stress: ok")
 
 
+def gen_loss():
+    """SURVEY 8(f4), training side: box_iou + SSDMatcher (generalized_ssd.py:326-335) and SSD.compute_loss (:210-269) of the
+    UNMODIFIED reference on seeded targets / head outputs, with its autograd gradients; the NumPy restatement must agree."""
+    from torchvision.ops import boxes as box_ops
+    m = refshim.ref_module("ssd_mobilenetv3")
+    model = m.ssdlite320_mobilenet_v3_large(pretrained=False, pretrained_backbone=False)      # only compute_loss / matcher
+    out = {}
+    for name in loss_np.LOSS_CASES:
+        anchors, targets, cls, reg = loss_np.seeded_case(name)
+        B = len(targets)
+        ta = torch.from_numpy(anchors)
+        tt = [{"boxes": torch.from_numpy(b), "labels": torch.from_numpy(l)} for b, l in targets]
+        matched = []
+        for t in tt:
+            if t["boxes"].numel() == 0:
+                matched.append(torch.full((ta.size(0),), -1, dtype=torch.int64))
+                continue
+            q = box_ops.box_iou(t["boxes"], ta)
+            assert np.array_equal(loss_np.box_iou(t["boxes"].numpy(), anchors), q.numpy())
+            matched.append(model.proposal_matcher(q))
+        mnp = np.stack([loss_np.match_image(b, anchors, 0.5) for b, _ in targets])
+        assert np.array_equal(mnp, torch.stack(matched).numpy()), name
+        tc = torch.from_numpy(cls).requires_grad_(True)
+        tr = torch.from_numpy(reg).requires_grad_(True)
+        losses = model.compute_loss(tt, {"cls_logits": tc, "bbox_regression": tr}, [ta] * B, matched)
+        (losses["bbox_regression"] + losses["classification"]).backward()
+        o = loss_np.compute_loss(targets, cls, reg, anchors, mnp, model.neg_to_pos_ratio)
+        for k in o:
+            assert abs(o[k] - float(losses[k])) <= 2e-6 * abs(float(losses[k])), (name, k, o[k], float(losses[k]))
+        nfg = int(sum((mm >= 0).sum() for mm in matched))
+        forced = int(sum(((mm >= 0) & (box_ops.box_iou(t["boxes"], ta).max(0)[0] < 0.5)).sum() for mm, t in zip(matched, tt)
+                         if t["boxes"].numel()))
+        print("loss[%s]: ok; matched %d (%d by the forced match only), bbox %.6f cls %.6f" % (
+            name, nfg, forced, float(losses["bbox_regression"]), float(losses["classification"])))
+        out[name + "_matched"] = torch.stack(matched).numpy()
+        out[name + "_losses"] = np.array([float(losses["bbox_regression"]), float(losses["classification"])], np.float64)
+        out[name + "_grad_reg"] = tr.grad.numpy()[:, ::7].copy()
+        out[name + "_grad_cls"] = tc.grad.numpy()[:, ::53].copy()
+        out[name + "_grad_cls_abs_sum"] = np.float64(tc.grad.double().abs().sum())
+        out[name + "_inputs_sha256"] = np.array(sha(cls) + sha(reg) + sha(anchors))
+    out["neg_to_pos_ratio"] = np.float64(model.neg_to_pos_ratio)
+    np.savez_compressed(os.path.join(OUT, "ssd_loss.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -305,6 +351,7 @@ if __name__ == "__main__":
     gen_v2()
     gen_stress()
     gen_vgg()
+    gen_loss()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -47,8 +47,14 @@ def test_builder_argument_errors():
         demonet_b200.ssdlite320_mobilenet_v3_large(bogus=1)
     m = demonet_b200.ssdlite320_mobilenet_v3_large(topk_candidates=400, score_thresh=0.01)      # kwargs quirk, SURVEY 8(b)
     assert m.topk_candidates == 400 and m.score_thresh == 0.01
-    with pytest.raises(NotImplementedError):
-        m.train()
+    m.train()                                     # loss branch of SSD.forward (generalized_ssd.py:273-274)
+    with pytest.raises(ValueError, match="In training mode, targets should be passed"):
+        m([torch.rand(3, 320, 320)])
+    with pytest.raises(ValueError, match="Expected target boxes to be a tensor"):
+        m([torch.rand(3, 320, 320)], [{"boxes": torch.zeros(4), "labels": torch.zeros(1, dtype=torch.int64)}])
+    with pytest.raises(ValueError, match="All bounding boxes should have positive height and width"):
+        m([torch.rand(3, 320, 320)], [{"boxes": torch.tensor([[5.0, 5.0, 5.0, 9.0]]), "labels": torch.ones(1, dtype=torch.int64)}])
+    m.eval()
     with pytest.raises(ValueError):
         m([torch.rand(320, 320)])                 # transform.py:110-112
     with pytest.raises(TypeError):
@@ -115,7 +121,7 @@ def test_c_abi_exports_every_declared_symbol():
         handle = ctypes.CDLL(_C.LIB_PATHS[dt])
         for name in declared:
             assert hasattr(handle, name), "missing export in the %s build: %s" % (dt, name)
-        assert _C.lib(dt).dn_abi_version() == _C.ABI_VERSION == 3
+        assert _C.lib(dt).dn_abi_version() == _C.ABI_VERSION == 4
     assert declared == set(_C.EXPORTED_SYMBOLS)
 
 

@@ -31,9 +31,12 @@ def test_state_dict_contract_matches_the_reference(golden_dir):
     assert (m.score_thresh, m.nms_thresh, m.detections_per_img, m.topk_candidates) == (0.01, 0.45, 200, 400)
     with pytest.raises(TypeError):
         demonet_b200.ssd300_vgg16(bogus=1)
-    with pytest.raises(NotImplementedError):
-        m.train()
-    assert demonet_b200.ssd300_vgg16(score_thresh=0.3, iou_thresh=0.4).score_thresh == 0.3      # training-only kwargs are accepted
+    m.train()
+    with pytest.raises(ValueError, match="In training mode, targets should be passed"):
+        m([torch.rand(3, 300, 300)])
+    m.eval()
+    m2 = demonet_b200.ssd300_vgg16(score_thresh=0.3, iou_thresh=0.4, positive_fraction=0.5)      # training-side kwargs of SSD.__init__
+    assert (m2.score_thresh, m2.iou_thresh, m2.neg_to_pos_ratio) == (0.3, 0.4, 1.0)
     import hubconf
     assert hubconf.ssd300_vgg16 is demonet_b200.ssd300_vgg16
 
