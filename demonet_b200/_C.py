@@ -11,7 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # argument of the model builders selects the bfloat16 build.
 ACT_DTYPES = ("fp16", "bf16")
 DEFAULT_ACT_DTYPE = os.environ.get("DN_ACT_DTYPE", "fp16")
-LIB_PATHS = {dt: os.path.join(_HERE, "lib", "libdemonet_b200_%s.so" % dt) for dt in ACT_DTYPES}
+# DN_LIB_DIR: a variant build of the library (csrc/build.sh with DN_LIB_OUT / DN_EXTRA_FLAGS), for A/B measurements
+_LIB_DIR = os.environ.get("DN_LIB_DIR") or os.path.join(_HERE, "lib")
+LIB_PATHS = {dt: os.path.join(_LIB_DIR, "libdemonet_b200_%s.so" % dt) for dt in ACT_DTYPES}
 LIB_PATH = LIB_PATHS["fp16"]
 
 ABI_VERSION = 4          # include/demonet_b200.h DN_ABI_VERSION

@@ -5,10 +5,10 @@
 # DN_BUILD_DTYPES="fp16" builds only one of them (faster edit-compile loop).
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../lib"
+OUT="${DN_LIB_OUT:-$HERE/../lib}"      # DN_LIB_OUT / DN_EXTRA_FLAGS: variant builds for A/B measurements (DN_LIB_DIR selects one at run time)
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
-SRCS="error.cu postprocess.cu dwconv.cu dwconv_tma.cu dwconv_stream.cu dwconv_stream2.cu se.cu transform.cu stem_tma.cu pwconv_simt.cu pwconv_tc.cu pwdw_fused.cu dwpw_fused.cu conv3x3_tc.cu vgg_ops.cu ssd_loss.cu engine.cu"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC ${DN_EXTRA_FLAGS:-}"
+SRCS="error.cu postprocess.cu dwconv.cu dwconv_tma.cu dwconv_stream.cu dwconv_stream2.cu se.cu transform.cu stem_tma.cu stem_tc.cu pwconv_simt.cu pwconv_tc.cu pwdw_fused.cu dwpw_fused.cu conv3x3_tc.cu vgg_ops.cu ssd_loss.cu engine.cu"
 DTYPES=${DN_BUILD_DTYPES:-"fp16 bf16"}
 for dt in $DTYPES; do
   if [ "$dt" = "fp16" ]; then DEF="-DDN_ACT_FP16=1"; else DEF="-DDN_ACT_FP16=0"; fi

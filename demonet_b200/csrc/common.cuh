@@ -25,7 +25,23 @@ int dn_postprocess_marked(const float* cls_logits, const float* bbox_regression,
                           float* out_scores, int64_t* out_labels, int32_t* out_counts, cudaStream_t stream,
                           cudaEvent_t after_front);
 
+// Back-off of mbarrier spin loops (nanoseconds, 0 = plain spin).  A warp that spins on mbarrier.try_wait stays eligible and
+// competes for its scheduler's issue slots with the warps doing the arithmetic: the producer warps run several stages
+// ahead, so a late wake-up costs them nothing (DN_SLEEP_PRODUCER); DN_SLEEP_CONSUMER is the back-off of the waits that sit
+// on the critical path (consumers waiting for data, epilogue warps waiting for an accumulator).
+#ifndef DN_SLEEP_PRODUCER
+#define DN_SLEEP_PRODUCER 0
+#endif
+#ifndef DN_SLEEP_CONSUMER
+#define DN_SLEEP_CONSUMER 0
+#endif
+
 namespace dn {
+
+template <int NS>
+__device__ __forceinline__ void spin_backoff() {
+    if (NS > 0) asm volatile("nanosleep.u32 %0;" ::"n"(NS));
+}
 
 void set_error(const char* fmt, ...);
 // uint8 -> fp32 / 255 (transform.cu), used by the engine's uint8 ingest
@@ -117,6 +133,33 @@ struct SmemOptIn {
             cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
             if (e != cudaSuccess) return e;
             occupancy[dev] = n > 0 ? n : 1;
+        }
+        *out = occupancy[dev];
+        return cudaSuccess;
+    }
+    // The same for kernels that allocate TMEM: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that
+    // contains tcgen05.alloc (measured on B200 / CUDA 12.9: ncu showed one CTA per SM for dwpw_fused and the tensor-core
+    // stem at 31 KB / 68 KB of shared memory), so residency is computed from the kernel's own resources: shared memory
+    // (+ 1 KB the driver reserves per CTA), registers, threads and the `tmem_cols` columns every resident CTA holds.
+    template <typename Kernel>
+    cudaError_t blocks_per_sm_tmem(Kernel kern, int threads, size_t smem, int tmem_cols, int* out) {
+        const int dev = current_device();
+        std::lock_guard<std::mutex> lock(mu);
+        if (occupancy[dev] == 0) {
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+            if (e != cudaSuccess) return e;
+            int smem_sm = 0, regs_sm = 0, thr_sm = 0;
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+            cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+            cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+            const size_t per_cta = smem + fa.sharedSizeBytes + 1024;
+            const int regs_cta = ((fa.numRegs + 7) & ~7) * ((threads + 31) & ~31);
+            int n = (int)((size_t)smem_sm / per_cta);
+            if (regs_cta > 0 && regs_sm / regs_cta < n) n = regs_sm / regs_cta;
+            if (thr_sm / threads < n) n = thr_sm / threads;
+            if (tmem_cols > 0 && 512 / tmem_cols < n) n = 512 / tmem_cols;
+            occupancy[dev] = n > 0 ? (n > 32 ? 32 : n) : 1;
         }
         *out = occupancy[dev];
         return cudaSuccess;

@@ -163,7 +163,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     const int ix = x0 * g.stride + (tap % 3) * g.dil - g.pad;
                     for (int kb = 0; kb < kblocks; ++kb, ++it) {
                         const int s = it % num_stages;
-                        mbar_wait(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
+                        mbar_wait_producer(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
                         mbar_expect_tx(&bars->full[s], stage_bytes);
                         tma_load_4d(smem_a + s * C3_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * C3_BLOCK_K, ix, iy, b0);
                         tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * C3_BLOCK_K, tap * g.N + n0);
@@ -339,7 +339,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int y0 = (rem / g.tiles_x) * g.TH, x0 = (rem % g.tiles_x) * g.TW;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % na;
-                    mbar_wait(&bars->a_empty[s], ((it / na) & 1u) ^ 1u);
+                    mbar_wait_producer(&bars->a_empty[s], ((it / na) & 1u) ^ 1u);
                     mbar_expect_tx(&bars->a_full[s], box_bytes);
                     tma_load_4d(smem_a + (size_t)s * g.a_stage_bytes, &tmap_a, &bars->a_full[s], kb * C3_BLOCK_K, x0 - 1, y0 - 1, b);
                 }
@@ -360,7 +360,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int kb = 0; kb < kblocks; ++kb)
                         for (int tap = 0; tap < 9; ++tap, ++it) {
                             const int s = it % nw;
-                            mbar_wait(&bars->w_empty[s], ((it / nw) & 1u) ^ 1u);
+                            mbar_wait_producer(&bars->w_empty[s], ((it / nw) & 1u) ^ 1u);
                             mbar_expect_tx(&bars->w_full[s], (uint32_t)w_tile_bytes);
                             tma_load_2d(smem_w + (size_t)s * w_tile_bytes, &tmap_w, &bars->w_full[s], kb * C3_BLOCK_K, tap * g.N + n0);
                         }

@@ -314,7 +314,9 @@ extern "C" int dn_stem_conv(const float* images, const float* w, const float* bi
     DN_REQUIRE(images && w && bias && y && mean3_host && std3_host, DN_ERR_INVALID, "NULL pointer");
     DN_REQUIRE(B > 0 && H > 0 && W > 0, DN_ERR_INVALID, "bad shape");
     DN_REQUIRE(Cout == 16 || Cout == 32, DN_ERR_UNSUPPORTED, "stem supports 16 or 32 output channels (got %d)", Cout);
-    if (stem_can_tma(images, W) && stem_norm_ok(std3_host)) {          // TMA-tiled kernel; the direct kernel below covers unaligned rows
+    if (stem_can_tma(images, W) && stem_norm_ok(std3_host)) {          // TMA-tiled kernels; the direct kernel below covers unaligned rows
+        if (stem_tc_enabled())                                          // tensor-core form (default); DN_STEM=simt: fp32 SIMT tiles
+            return stem_tc_launch(images, w, bias, mean3_host, std3_host, y, B, H, W, Cout, act, (cudaStream_t)stream_);
         CUtensorMap tm;
         int rc = stem_make_tmap(&tm, images, B, H, W);
         if (rc) return rc;

@@ -59,6 +59,10 @@ DwImpl dw_choose(int H, int W, int C, int k, int stride);
 bool stem_can_tma(const void* images, int W);
 bool stem_norm_ok(const float* std3);
 int stem_make_tmap(CUtensorMap* map, const float* images, int B, int H, int W);
+// tensor-core stem (stem_tc.cu): im2col rows built by the threads, hi / lo fp16 split, tcgen05 GEMM; same preconditions
+bool stem_tc_enabled();
+int stem_tc_launch(const float* images, const float* w, const float* bias, const float* mean3, const float* std3, void* y, int B,
+                   int H, int W, int Cout, int act, cudaStream_t stream);
 int stem_tma_launch(const CUtensorMap& tm, const float* w, const float* bias, const float* mean3, const float* std3, void* y,
                     int B, int H, int W, int Cout, int act, cudaStream_t stream);
 

@@ -28,14 +28,17 @@ __device__ __forceinline__ float dws_act(float v) {
     return v;
 }
 
+template <int NS = DN_SLEEP_CONSUMER>
 __device__ __forceinline__ void dws_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    do {
+    for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
                      : "r"(bar), "r"(parity)
                      : "memory");
-    } while (!ok);
+        if (ok) break;
+        spin_backoff<NS>();
+    }
 }
 
 // taps are re-read from shared memory at every use: `volatile` keeps ptxas from hoisting all k*k of them into
@@ -122,7 +125,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                 const int groups = (o1 - o0 + 2 * P + KS - 1) / KS;
                 for (int gi = 0; gi < groups; ++gi, ++seq) {
                     const uint32_t slot = seq % sp.nst, round = seq / sp.nst;
-                    if (round > 0) dws_wait(dws_u32(&empty[slot]), (round - 1) & 1u);
+                    if (round > 0) dws_wait<DN_SLEEP_PRODUCER>(dws_u32(&empty[slot]), (round - 1) & 1u);
                     const uint32_t bar = dws_u32(&full[slot]);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sp.stage_bytes)
                                  : "memory");

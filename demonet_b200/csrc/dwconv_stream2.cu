@@ -25,14 +25,17 @@ __device__ __forceinline__ float dw2_act(float v) {
     return v;
 }
 
+template <int NS = DN_SLEEP_CONSUMER>
 __device__ __forceinline__ void dw2_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    do {
+    for (;;) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
                      : "r"(bar), "r"(parity)
                      : "memory");
-    } while (!ok);
+        if (ok) break;
+        spin_backoff<NS>();
+    }
 }
 // volatile: the taps are re-read at every use instead of being hoisted into k*k*2 registers
 __device__ __forceinline__ float2 dw2_lds_tap(uint32_t addr) {
@@ -92,7 +95,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
                 const int groups = (n_steps + G - 1) / G;
                 for (int gi = 0; gi < groups; ++gi, ++seq) {
                     const uint32_t slot = seq % sp.nst, round = seq / sp.nst;
-                    if (round > 0) dw2_wait(dw2_u32(&empty[slot]), (round - 1) & 1u);
+                    if (round > 0) dw2_wait<DN_SLEEP_PRODUCER>(dw2_u32(&empty[slot]), (round - 1) & 1u);
                     const uint32_t bar = dw2_u32(&full[slot]);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sp.stage_bytes)
                                  : "memory");

@@ -271,7 +271,7 @@ static int fd_launch_t(const CUtensorMap& tx, const CUtensorMap& tw, const float
     static SmemOptIn optin;
     int per_sm = 1;
     DN_CHECK_CUDA(optin.ensure(kern, smem));
-    DN_CHECK_CUDA(optin.blocks_per_sm(kern, FD_THREADS, smem, &per_sm));
+    DN_CHECK_CUDA(optin.blocks_per_sm_tmem(kern, FD_THREADS, smem, FD_TMEM_COLS, &per_sm));
     const int tiles_x = ceil_div(W, FD_TW), tiles_y = ceil_div(H, FD_TH);
     const long long n_tiles = (long long)B * tiles_x * tiles_y;
     DN_REQUIRE(n_tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "fused depthwise + project problem too large");

@@ -137,7 +137,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                     const int s = it % num_stages;
-                    mbar_wait(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
+                    mbar_wait_producer(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
                     mbar_expect_tx(&bars->full[s], stage_bytes);
                     tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
                     if (!w_stat) tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);

@@ -29,8 +29,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    while (!mbar_try_wait(bar, parity)) spin_backoff<DN_SLEEP_CONSUMER>();
+}
+// waits of a producer that runs stages ahead of its consumers (empty slots): a late wake-up is free
+__device__ __forceinline__ void mbar_wait_producer(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) spin_backoff<DN_SLEEP_PRODUCER>();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

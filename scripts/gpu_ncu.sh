@@ -3,7 +3,7 @@
 # usage: gpu_ncu.sh "<kernel-regex>:<skip>:<tag>" ...
 mkdir -p gpurun_out/ncu
 CMD=${NCU_CMD:-"python bench.py --steps 1 --warmup 3 --no-cpu-baseline"}
-KEEP='dram__bytes_read.sum|dram__bytes_write.sum|gpu__time_duration.sum|dram__throughput.avg.pct_of_peak_sustained_elapsed|sm__throughput.avg.pct|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|launch__occupancy_limit|sm__pipe_tensor|l1tex__t_sector_hit_rate|lts__t_sector_hit_rate|smsp__warp_issue_stalled.*_per_warp_active.pct|smsp__inst_executed.sum|launch__grid_size|launch__block_size|launch__shared_mem|l1tex__data_bank_conflicts|smsp__cycles_active.avg|sm__inst_executed_pipe|lts__t_bytes.sum|l1tex__t_bytes.sum|smsp__issue_active.avg.pct|achieved_occupancy|sm__maximum_warps'
+KEEP='issue_stalled|pcsamp|dram__bytes_read.sum|dram__bytes_write.sum|gpu__time_duration.sum|dram__throughput.avg.pct_of_peak_sustained_elapsed|sm__throughput.avg.pct|sm__warps_active.avg.pct_of_peak_sustained_active|launch__registers_per_thread|launch__occupancy_limit|sm__pipe_tensor|l1tex__t_sector_hit_rate|lts__t_sector_hit_rate|smsp__warp_issue_stalled.*_per_warp_active.pct|smsp__inst_executed.sum|launch__grid_size|launch__block_size|launch__shared_mem|l1tex__data_bank_conflicts|smsp__cycles_active.avg|sm__inst_executed_pipe|lts__t_bytes.sum|l1tex__t_bytes.sum|smsp__issue_active.avg.pct|achieved_occupancy|sm__maximum_warps'
 for spec in "$@"; do
   IFS=: read pat skip tag <<< "$spec"
   rm -f /tmp/p.ncu-rep

@@ -128,10 +128,13 @@ def test_pwconv_head_addressing(dt):
     assert float(out[:, :off].abs().sum()) == 0 and float(out[:, off + HW * A:].abs().sum()) == 0
 
 
-@pytest.mark.parametrize("Cout,S,act", [(16, 320, "hardswish"), (32, 300, "relu6"), (32, 512, "relu6"), (16, 33, "hardswish")])
-def test_stem(Cout, S, act, dt):
+@pytest.mark.parametrize("impl", ["tc", "simt"])          # tensor-core im2col GEMM (default) / fp32 SIMT tiles (DN_STEM=simt)
+@pytest.mark.parametrize("Cout,S,act,B", [(16, 320, "hardswish", 3), (32, 300, "relu6", 3), (32, 512, "relu6", 3), (16, 33, "hardswish", 3),
+                                          (16, 324, "relu", 3), (32, 36, "hardswish", 3),
+                                          (16, 320, "hardswish", 40), (32, 300, "relu6", 37)])      # many tiles per CTA: the window ring wraps
+def test_stem(Cout, S, act, B, dt, impl, monkeypatch):
+    monkeypatch.setenv("DN_STEM", impl)
     g = torch.Generator().manual_seed(S)
-    B = 2
     img = torch.rand(B, 3, S, S, generator=g).cuda()
     w = (torch.randn(Cout, 3, 3, 3, generator=g) * 0.3).cuda()
     b = torch.randn(Cout, generator=g).cuda()
