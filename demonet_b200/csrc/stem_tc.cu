@@ -92,8 +92,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __rest
     constexpr uint32_t TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
     extern __shared__ __align__(1024) unsigned char sc_smem_raw[];
     unsigned char* base = sc_smem_raw + ((1024u - (sc_u32(sc_smem_raw) & 1023u)) & 1023u);
-    unsigned char* a_t = base;                                       // [2][4][128 x 16] fp16, SWIZZLE_32B
-    unsigned char* w_t = a_t + 2 * SC_A_BYTES;                       // [4][COUT x 16] fp16: hi k0, hi k1, lo k0, lo k1
+    unsigned char* a_t = base;                                       // [4][128 x 16] fp16, SWIZZLE_32B (single buffer: the six
+                                                                     // UMMAs of a tile retire long before the next tile's rows are ready)
+    unsigned char* w_t = a_t + SC_A_BYTES;                       // [4][COUT x 16] fp16: hi k0, hi k1, lo k0, lo k1
     float* raw = reinterpret_cast<float*>(w_t + 4 * B_TILE);         // [SC_RING][3][9][72] fp32 input windows
     float* sb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(raw) + SC_RING * SC_RAW_BYTES);      // [COUT]
     ScBars* bars = reinterpret_cast<ScBars*>(sb + COUT);
@@ -234,7 +235,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_img, const float* __rest
         else gather(win, ih0, iw0, std::true_type{}, a);
 #pragma unroll
         for (int k = 27; k < 32; ++k) a[k] = 0.f;
-        unsigned char* at = a_t + buf * SC_A_BYTES;
+        unsigned char* at = a_t;
+        // the previous tile's UMMAs read the A operands: they must have retired (they were issued a whole drain + gather ago)
+        if (it > 0) sc_wait(&bars->mma_done[(it - 1) & 1u], ((it - 1) >> 1) & 1u);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {             // K step (16 taps) -> one hi and one lo operand
 #pragma unroll
@@ -322,7 +325,7 @@ template <int COUT, int ACT>
 static int stem_tc_launch_t(const CUtensorMap& tm, const float* w, const float* bias, const ScNorm& nm, void* y, int B, int H, int W,
                             cudaStream_t stream) {
     auto kern = stem_tc_kernel<COUT, ACT>;
-    const size_t smem = 2 * SC_A_BYTES + 4 * COUT * 32 + SC_RING * SC_RAW_BYTES + COUT * 4 + sizeof(ScBars) + 1024;
+    const size_t smem = SC_A_BYTES + 4 * COUT * 32 + SC_RING * SC_RAW_BYTES + COUT * 4 + sizeof(ScBars) + 1024;
     static SmemOptIn optin;
     int per_sm = 1;
     DN_CHECK_CUDA(optin.ensure(kern, smem));
