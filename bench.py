@@ -347,7 +347,7 @@ def layer_costs(plan, B, D):
                         2 * B * hi * wi * (L.cin * L.k * L.k + L.cin * Pj.cout)))
             continue
         if L.kind == "stem":
-            out.append(("stem_tma_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
+            out.append(("stem_tc_kernel", B * (3 * hi * wi * 4 + ho * wo * L.cout * 2), 2 * B * ho * wo * L.cout * 27))
         elif L.kind == "dw":
             out.append(("dwconv kernels (stream / stream2 / tma / direct)", B * (hi * wi + ho * wo) * L.cin * 2 + L.k * L.k * L.cin * 4,
                         2 * B * ho * wo * L.cin * L.k * L.k))
@@ -367,7 +367,7 @@ def layer_costs(plan, B, D):
 
 NCU_FAMILIES = {"dwconv kernels (stream / stream2 / tma / direct)": ["dwconv_kernel", "dwconv_tma_kernel", "dwconv_stream_kernel", "dwconv_stream2_kernel"],
                 "pwconv_tc_kernel": ["pwconv_tc_kernel"], "pwdw_fused_kernel": ["pwdw_fused_kernel"],
-                "dwpw_fused_kernel": ["dwpw_fused_kernel"], "stem_tma_kernel": ["stem_tma_kernel", "stem_conv_kernel"],
+                "dwpw_fused_kernel": ["dwpw_fused_kernel"], "stem_tc_kernel": ["stem_tc_kernel", "stem_tma_kernel", "stem_conv_kernel"],
                 "se kernels (fc1 + fc2 + scale)": ["se_pool_kernel", "se_fc1_kernel", "se_fc2_kernel", "se_scale_kernel", "se_fc_kernel"],
                 "softmax_decode_kernel (+ histogram, thresholds)": ["softmax_decode_kernel", "pick_thresholds_kernel"],
                 "class_sort + nms + merge kernels (lazy rounds)": ["class_sort_kernel", "class_nms_warp_kernel", "class_nms_cta_kernel", "merge_topd_kernel"]}
