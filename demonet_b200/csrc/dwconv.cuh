@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dn {
@@ -25,14 +27,21 @@ int dwconv_tma_launch(const CUtensorMap& tm, const DwTiling& tl, const float* w,
 constexpr int DWS_MAX_THREADS = 288;        // producer warp + up to 8 consumer warps
 struct DwStream {
     int CB;                 // channels per block (multiple of 8, divides C)
-    int ncb;                // column blocks (TW output columns each) across the width
+    int ncb;                // column blocks (TW output columns each) of one column strip
     int IW;                 // staged row width in pixels (ncb * TW + k - 1)
+    int nstrip;             // column strips across the width (1 = a CTA stages whole rows); a strip is ncb * TW output
+                            // columns wide, so that wide maps still get >= 64-byte channel blocks per staged pixel
     int ncblk;              // channel blocks
     int nst;                // ring stages (k input rows each)
     int stage_bytes, stage_stride;
     int threads;
     size_t smem;
 };
+// measurement aid: DN_DW_STRIPS=0 restores whole-row CTAs on wide maps (read per call: the tests flip it inside one process)
+inline bool dn_dw_strips() {
+    const char* e = getenv("DN_DW_STRIPS");
+    return !(e && e[0] == '0');
+}
 bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp);
 int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp);
 // Pooling side output of a row-stream launch for the squeeze-excitation that follows (dwconv_stream.cu, se.cu).

@@ -111,9 +111,12 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     pdl_wait();                 // the barriers are set up; nothing above touches activation memory
 
     // this CTA's channel block and its share of that block's output-row stream (B * H rows)
+    // (wide maps: the width is cut into sp.nstrip column strips and a CTA also keeps its strip for its whole life)
+    const int ncs = sp.ncblk * sp.nstrip;
     const int cblk = blockIdx.x % sp.ncblk;
+    const int col0 = ((blockIdx.x / sp.ncblk) % sp.nstrip) * sp.ncb * TW;       // first output column of the strip
     const long long T = (long long)B * H;
-    const int part = blockIdx.x / sp.ncblk, parts = gridDim.x / sp.ncblk;
+    const int part = blockIdx.x / ncs, parts = gridDim.x / ncs;
     const long long g_begin = T * part / parts, g_end = T * (part + 1) / parts;
 
     if (warp == 0) {
@@ -132,7 +135,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
                     asm volatile(
                         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
                         "[%2];" ::"r"(dws_u32(stages + (size_t)slot * sp.stage_stride)),
-                        "l"(&tmap_x), "r"(bar), "r"(cblk * sp.CB), "r"(-P), "r"(o0 - P + gi * KS), "r"(b)
+                        "l"(&tmap_x), "r"(bar), "r"(cblk * sp.CB), "r"(col0 - P), "r"(o0 - P + gi * KS), "r"(b)
                         : "memory");
                 }
                 g += o1 - o0;
@@ -146,7 +149,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     const int nqb = sp.CB / CH;                      // channel groups (CH channels) per block
     const int q = ct % nqb, cb = ct / nqb;
     const bool active = cb < sp.ncb;
-    const int ow0 = cb * TW;
+    const int ow0 = col0 + cb * TW;
     const int cw = C >> 1;                           // 32-bit words per pixel of the output
     const int row_bytes = sp.IW * sp.CB * 2;
     const int n_cons = n_cons_warps * 32;
@@ -164,7 +167,7 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     float2 bv[NP];
 #pragma unroll
     for (int h = 0; h < NP; ++h) bv[h] = __ldg(reinterpret_cast<const float2*>(bias + cblk * sp.CB + (active ? q : 0) * CH) + h);
-    const uint32_t stage0 = dws_u32(stages) + (uint32_t)((ow0 * sp.CB + q * CH) * 2);
+    const uint32_t stage0 = dws_u32(stages) + (uint32_t)((cb * TW * sp.CB + q * CH) * 2);
     const uint32_t cstep = (uint32_t)sp.CB * 2;     // bytes between staged pixels
     float2 acc[KS][TW][NP];                         // ring of k output rows (slot = row mod k)
 #pragma unroll
@@ -288,20 +291,21 @@ static constexpr int dws_tw() { return 4; }
 template <int KS>
 static constexpr int dws_ch() { return KS == 3 ? 4 : 2; }      // channels per consumer thread
 
-bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
-    if (stride != 1 || (k != 3 && k != 5) || C % 8 != 0 || H < 4) return false;
+// One candidate plan: the width cut into nstrip column strips.  small_only: the consumers must fit the 160-thread variant
+// (three CTAs per SM); the channel block with the most consumer threads wins, the wider one on ties.
+static bool dws_plan_strips(int W, int C, int k, int nstrip, bool small_only, DwStream* sp) {
     const int TW = (k == 3) ? dws_tw<3>() : dws_tw<5>();
     const int CH = (k == 3) ? dws_ch<3>() : dws_ch<5>();
     const int P = k / 2;
-    const int ncb = (W + TW - 1) / TW;
+    const int ncb = ((W + nstrip - 1) / nstrip + TW - 1) / TW;     // column blocks per strip
     const int IW = ncb * TW + 2 * P;
-    if (IW > 256) return false;
+    if (IW > 256 || (nstrip - 1) * ncb * TW >= W) return false;
     // channel block: consumers (CB/4 x ncb threads) should fill about four warps -- small CTAs, several per SM
     int best = 0, best_thr = 0;
     for (int cb = 8; cb <= C; cb += 8) {
         if (C % cb) continue;
         const int thr = (cb / CH) * ncb;
-        if (thr > DWS_MAX_THREADS - 32) break;
+        if (thr > (small_only ? 128 : DWS_MAX_THREADS - 32)) break;
         const bool good = thr >= 96 && thr <= 128, best_good = best_thr >= 96 && best_thr <= 128;
         if (!best || (good && !best_good) || (good == best_good)) best = cb, best_thr = thr;     // later (larger) wins ties
     }
@@ -309,6 +313,7 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     sp->CB = best;
     sp->ncb = ncb;
     sp->IW = IW;
+    sp->nstrip = nstrip;
     sp->ncblk = C / best;
     sp->stage_bytes = k * IW * best * 2;
     sp->stage_stride = (sp->stage_bytes + 127) & ~127;
@@ -318,6 +323,35 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     sp->threads = 32 + (((best / CH) * ncb + 31) / 32) * 32;
     sp->smem = (size_t)nst * sp->stage_stride + (size_t)k * k * best * 4;
     return sp->smem <= 200 * 1024;
+}
+
+// Whole rows per CTA wherever that gives small CTAs (<= 4 consumer warps, three CTAs per SM).  Wide maps (>= 64 columns)
+// where it does not -- the row exceeds the 256-pixel TMA box (256 x 256 x 32 of V2 @ 512 ran on the tiles at 4.1 TB/s) or
+// even the narrowest channel block needs the 288-thread variant (one CTA per SM) -- are cut into 2 / 4 / 8 column strips:
+// the split with the most consumer threads per CTA wins (256 x 256 x 32: four strips of 64 columns x 32 channels, 5.3 TB/s).
+// A strip re-reads k - 1 halo columns (3-6 %, L2 hits).  What counts for the stride-1 stream is threads per SM, not the
+// width of the channel block: 128 x 128 x 144 in whole rows of 16 channels (128 consumers) runs at 4.4 TB/s, as four strips
+// of 48 channels (96 consumers) at 4.0.
+bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
+    if (stride != 1 || (k != 3 && k != 5) || C % 8 != 0 || H < 4) return false;
+    DwStream whole{};
+    const bool whole_ok = dws_plan_strips(W, C, k, 1, false, &whole);
+    if (W >= 64 && dn_dw_strips() && !(whole_ok && whole.threads <= 160)) {
+        DwStream pick{};
+        int pick_thr = 0;
+        for (int nstrip = 2; nstrip <= 8; nstrip *= 2) {
+            DwStream cand{};
+            if (!dws_plan_strips(W, C, k, nstrip, true, &cand)) continue;
+            const int thr = (cand.CB / ((k == 3) ? dws_ch<3>() : dws_ch<5>())) * cand.ncb;
+            if (thr > pick_thr) pick = cand, pick_thr = thr;
+        }
+        if (pick_thr >= 64) {
+            *sp = pick;
+            return true;
+        }
+    }
+    if (whole_ok) *sp = whole;
+    return whole_ok;
 }
 
 int dw_stream_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp) {
@@ -336,8 +370,9 @@ static int dws_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
     int per_sm = 0;
     DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;
-    // a multiple of the channel-block count, at most one CTA per output row of a block
-    long long parts = (long long)per_sm * sm_count() / sp.ncblk;
+    // a multiple of the (channel block, column strip) count, at most one CTA per output row of a block
+    const int ncs = sp.ncblk * sp.nstrip;
+    long long parts = (long long)per_sm * sm_count() / ncs;
     if (parts < 1) parts = 1;
     if (parts > (long long)B * H) parts = (long long)B * H;
     if (POOL) {
@@ -348,7 +383,7 @@ static int dws_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
         pool->slots = (int)slots;
         if (probe) return DN_OK;
     }
-    const long long grid = parts * sp.ncblk;
+    const long long grid = parts * ncs;
     launch_pdl(kern, (unsigned)grid, sp.threads, smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C,
                POOL ? pool->partial : (float*)nullptr, POOL ? pool->slots : 0);
     DN_CHECK_LAUNCH();
@@ -358,7 +393,7 @@ static int dws_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
 template <int KS, int ACT, int NT>
 static int dws_launch_n(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
                         int C, DwPool* pool, cudaStream_t stream) {
-    if (pool && pool->partial) {
+    if (pool && pool->partial && sp.nstrip == 1) {       // (column strips do not pool: a slot is one CTA share of whole rows)
         // the pooled variant has its own occupancy: see whether its split keeps the slots of an image within bounds
         int rc = dws_launch_p<KS, ACT, NT, true>(tm, sp, w, bias, y, B, H, W, C, pool, true, stream);
         if (rc) return rc;
@@ -390,7 +425,7 @@ static int dws_launch_k(const CUtensorMap& tm, const DwStream& sp, const float* 
 
 int dwconv_stream_launch(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H,
                          int W, int C, int k, int act, cudaStream_t stream, DwPool* pool) {
-    DN_REQUIRE((long long)sp.ncblk * B * H < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
+    DN_REQUIRE((long long)sp.ncblk * sp.nstrip * B * H < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
     if (k == 3) return dws_launch_k<3>(tm, sp, w, bias, y, B, H, W, C, act, pool, stream);
     return dws_launch_k<5>(tm, sp, w, bias, y, B, H, W, C, act, pool, stream);
 }

@@ -80,9 +80,12 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     pdl_wait();
 
     // this CTA's channel block and its share of that block's output-row stream (B * Ho rows)
+    // (wide maps: sp.nstrip column strips, as in the stride-1 stream)
+    const int ncs = sp.ncblk * sp.nstrip;
     const int cblk = blockIdx.x % sp.ncblk;
+    const int col0 = ((blockIdx.x / sp.ncblk) % sp.nstrip) * sp.ncb * TW;       // first output column of the strip
     const long long T = (long long)B * Ho;
-    const int part = blockIdx.x / sp.ncblk, parts = gridDim.x / sp.ncblk;
+    const int part = blockIdx.x / ncs, parts = gridDim.x / ncs;
     const long long g_begin = T * part / parts, g_end = T * (part + 1) / parts;
 
     if (warp == 0) {
@@ -102,7 +105,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
                     asm volatile(
                         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
                         "[%2];" ::"r"(dw2_u32(stages + (size_t)slot * sp.stage_stride)),
-                        "l"(&tmap_x), "r"(bar), "r"(cblk * sp.CB), "r"(-P), "r"(2 * o0 - P + gi * G), "r"(b)
+                        "l"(&tmap_x), "r"(bar), "r"(cblk * sp.CB), "r"(2 * col0 - P), "r"(2 * o0 - P + gi * G), "r"(b)
                         : "memory");
                 }
                 g += o1 - o0;
@@ -116,7 +119,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     const int nqb = sp.CB >> 1;                      // channel pairs per block
     const int q = ct % nqb, cb = ct / nqb;
     const bool active = cb < sp.ncb;
-    const int ow0 = cb * TW;
+    const int ow0 = col0 + cb * TW;
     const int cw = C >> 1;                           // 32-bit words per output pixel
     const int row_bytes = sp.IW * sp.CB * 2;
     const int n_cons = n_cons_warps * 32;
@@ -130,7 +133,7 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
     const uint32_t wq = dw2_u32(wsm + q * (KS * KS) * 2);
     const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + cblk * sp.CB + (active ? q : 0) * 2));
-    const uint32_t stage0 = dw2_u32(stages) + (uint32_t)((2 * ow0 * sp.CB + q * 2) * 2);
+    const uint32_t stage0 = dw2_u32(stages) + (uint32_t)((2 * cb * TW * sp.CB + q * 2) * 2);
     const uint32_t cstep = (uint32_t)sp.CB * 2;     // bytes between staged pixels
     float2 acc[R][TW];                              // ring of the open output rows (slot = row mod R)
 #pragma unroll
@@ -231,15 +234,12 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
-bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out) {
-    if ((k != 3 && k != 5) || C % 8 != 0) return false;
-    const int P = k / 2, R = (k + 1) / 2, G = 2 * R;
-    const int Ho = (H + 2 * P - k) / 2 + 1, Wo = (W + 2 * P - k) / 2 + 1;
-    if (Ho < 4) return false;
+static bool dw2_plan_strips(int Wo, int C, int k, int nstrip, DwStream* sp, int* tw_out) {
+    const int R = (k + 1) / 2, G = 2 * R;
     const int TW = Wo >= 16 ? 4 : 2;
-    const int ncb = (Wo + TW - 1) / TW;
+    const int ncb = ((Wo + nstrip - 1) / nstrip + TW - 1) / TW;       // column blocks per strip
     const int IW = 2 * ncb * TW + k - 2;
-    if (IW > 256) return false;
+    if (IW > 256 || (nstrip - 1) * ncb * TW >= Wo) return false;
     // channel block: consumers (CB/2 x ncb threads) should fill the four consumer warps
     int best = 0, best_thr = 0;
     for (int cb = 8; cb <= C; cb += 8) {
@@ -252,6 +252,7 @@ bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out) {
     sp->CB = best;
     sp->ncb = ncb;
     sp->IW = IW;
+    sp->nstrip = nstrip;
     sp->ncblk = C / best;
     sp->stage_bytes = G * IW * best * 2;
     sp->stage_stride = (sp->stage_bytes + 127) & ~127;
@@ -262,6 +263,36 @@ bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out) {
     sp->smem = (size_t)nst * sp->stage_stride + (size_t)k * k * best * 4;
     if (tw_out) *tw_out = TW;
     return sp->smem <= 72 * 1024;
+}
+
+// Whole output rows per CTA, or -- on wide maps (>= 64 output columns) where that leaves a channel block narrower than 32
+// channels or does not fit the 256-pixel TMA box -- the first split into 2 / 4 / 8 column strips with >= 32-channel blocks
+// (see dw_stream_plan).
+bool dw_stream2_plan(int H, int W, int C, int k, DwStream* sp, int* tw_out) {
+    if ((k != 3 && k != 5) || C % 8 != 0) return false;
+    const int P = k / 2;
+    const int Ho = (H + 2 * P - k) / 2 + 1, Wo = (W + 2 * P - k) / 2 + 1;
+    if (Ho < 4) return false;
+    DwStream whole{};
+    int tw = 0;
+    const bool whole_ok = dw2_plan_strips(Wo, C, k, 1, &whole, &tw);
+    const int want = C < 32 ? C : 32;
+    if (Wo >= 64 && dn_dw_strips() && !(whole_ok && whole.CB >= want)) {
+        for (int nstrip = 2; nstrip <= 8; nstrip *= 2) {
+            DwStream cand{};
+            int twc = 0;
+            if (dw2_plan_strips(Wo, C, k, nstrip, &cand, &twc) && cand.CB >= want) {
+                *sp = cand;
+                if (tw_out) *tw_out = twc;
+                return true;
+            }
+        }
+    }
+    if (whole_ok) {
+        *sp = whole;
+        if (tw_out) *tw_out = tw;
+    }
+    return whole_ok;
 }
 
 int dw_stream2_make_tmap(CUtensorMap* map, const void* x, int B, int H, int W, int C, int k, const DwStream& sp) {
@@ -280,7 +311,8 @@ static int dw2_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
     int per_sm = 0;
     DN_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sp.threads, smem));
     if (per_sm < 1) per_sm = 1;
-    long long parts = (long long)per_sm * sm_count() / sp.ncblk;
+    const int ncs = sp.ncblk * sp.nstrip;
+    long long parts = (long long)per_sm * sm_count() / ncs;
     if (parts < 1) parts = 1;
     if (parts > (long long)B * Ho) parts = (long long)B * Ho;
     if (POOL) {
@@ -291,7 +323,7 @@ static int dw2_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
         pool->slots = (int)slots;
         if (probe) return DN_OK;
     }
-    const long long grid = parts * sp.ncblk;
+    const long long grid = parts * ncs;
     launch_pdl(kern, (unsigned)grid, sp.threads, smem, stream, tm, w, bias, (uint32_t*)y, sp, B, H, W, C, Ho, Wo,
                POOL ? pool->partial : (float*)nullptr, POOL ? pool->slots : 0);
     DN_CHECK_LAUNCH();
@@ -301,7 +333,7 @@ static int dw2_launch_p(const CUtensorMap& tm, const DwStream& sp, const float* 
 template <int KS, int TW, int ACT>
 static int dw2_launch_t(const CUtensorMap& tm, const DwStream& sp, const float* w, const float* bias, void* y, int B, int H, int W,
                         int C, int Ho, int Wo, DwPool* pool, cudaStream_t stream) {
-    if (pool && pool->partial) {
+    if (pool && pool->partial && sp.nstrip == 1) {       // (column strips do not pool)
         int rc = dw2_launch_p<KS, TW, ACT, true>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, true, stream);
         if (rc) return rc;
         if (pool->parts > 0) return dw2_launch_p<KS, TW, ACT, true>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, pool, false, stream);
@@ -326,7 +358,7 @@ int dwconv_stream2_launch(const CUtensorMap& tm, const DwStream& sp, int tw, con
                           int H, int W, int C, int k, int act, cudaStream_t stream, DwPool* pool) {
     const int P = k / 2;
     const int Ho = (H + 2 * P - k) / 2 + 1, Wo = (W + 2 * P - k) / 2 + 1;
-    DN_REQUIRE((long long)sp.ncblk * B * Ho < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
+    DN_REQUIRE((long long)sp.ncblk * sp.nstrip * B * Ho < (1ll << 40), DN_ERR_UNSUPPORTED, "depthwise problem too large");
     if (k == 3) return tw == 4 ? dw2_launch_a<3, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream)
                                : dw2_launch_a<3, 2>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream);
     return tw == 4 ? dw2_launch_a<5, 4>(tm, sp, w, bias, y, B, H, W, C, Ho, Wo, act, pool, stream)

@@ -25,7 +25,10 @@ def _close_h16(dt, got, want, extra_abs=1e-3):
 DW_CASES = [(16, 3, 1, 160), (64, 3, 2, 160), (72, 5, 2, 80), (120, 5, 1, 40), (240, 3, 2, 40), (672, 3, 1, 20),
             (672, 5, 2, 20), (480, 5, 1, 10), (256, 3, 2, 10), (128, 3, 2, 5), (128, 3, 2, 3), (64, 3, 2, 2),
             (128, 3, 1, 1), (96, 3, 1, 19), (144, 3, 2, 75), (32, 3, 1, 150), (1280, 3, 1, 16), (8, 5, 2, 7),
-            (200, 3, 1, 20), (72, 3, 1, 80), (24, 5, 1, 33), (8, 3, 1, 9), (184, 3, 1, 20)]
+            (200, 3, 1, 20), (72, 3, 1, 80), (24, 5, 1, 33), (8, 3, 1, 9), (184, 3, 1, 20),
+            # wide maps: the row streams cut the width into column strips (config 5's largest layers, V2 @ 300, ragged widths)
+            (32, 3, 1, 256), (96, 3, 2, 256), (144, 3, 1, 128), (144, 3, 2, 128), (96, 3, 2, 150), (24, 5, 1, 70),
+            (48, 5, 2, 131), (16, 3, 1, 97)]
 
 
 @pytest.mark.parametrize("C,k,s,H", DW_CASES)
@@ -58,6 +61,24 @@ def test_dwconv_rect_many_images(B, H, W, C, k, s, dt):
     ref = ACTS["hardswish"](ref).permute(0, 2, 3, 1)
     assert y.shape == ref.shape
     _close_h16(dt, y, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C,k,s", [(20, 9, 130, 48, 3, 1), (20, 17, 131, 48, 5, 2), (3, 256, 256, 32, 3, 1), (3, 128, 128, 144, 3, 2),
+                                         (7, 12, 70, 24, 5, 1)])
+def test_dwconv_column_strips_bit_identical(B, H, W, C, k, s, dt, monkeypatch):
+    """Column strips (wide maps) only change which CTA computes an output, not the order of its multiply-adds: the result
+    equals the whole-row plan bit for bit where that plan exists, and fp32 torch within 1 ulp either way."""
+    g = torch.Generator().manual_seed(B + H * 3 + W * 5 + C * 7 + k + s)
+    x = (torch.randn(B, H, W, C, generator=g) * 2).to(dt).cuda()
+    w = (torch.randn(k * k, C, generator=g) / k).cuda()
+    b = torch.randn(C, generator=g).cuda()
+    y = ops.dwconv(x, w, b, k, s, "relu6")
+    monkeypatch.setenv("DN_DW_STRIPS", "0")
+    y0 = ops.dwconv(x, w, b, k, s, "relu6")
+    monkeypatch.delenv("DN_DW_STRIPS")
+    assert torch.equal(y, y0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.t().reshape(C, 1, k, k), b, s, (k - 1) // 2, 1, C)
+    _close_h16(dt, y, F.relu6(ref).permute(0, 2, 3, 1))
 
 
 # (M, K, N): Appendix C GEMM shapes (per-image M times a small batch), incl. N not multiple of 16 / > 256
