@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--gather-every", type=int, default=1,
                     help="N > 1: all-gather the detections of this many consecutive batches in ONE collective (1 = a collective "
                          "per step; every detection is gathered inside the timed region either way)")
-    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--pipeline", type=int, default=4, choices=[1, 2, 3, 4],
                     help="batches in flight per GPU (2 = the engine's pipeline mode, 1 = one forward at a time)")
     return ap.parse_args()
 
@@ -455,13 +455,17 @@ def main():
     else:
         B = args.batch or cfg["batch"]
     stream = torch.cuda.current_stream(dev)
-    nslot = 2 if args.pipeline == 2 else 1
+    nslot = args.pipeline if args.pipeline >= 2 else 1
     peaks = load_peaks()
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
-    def timed(fn, steps, warmup, sampler=None, finish=None):
-        for _ in range(warmup):
+    def timed(fn, steps, warmup, sampler=None, finish=None, prime=0):
+        # `prime` untimed calls in front of the W warm-up steps: engine set-up, not warm-up -- every engine instance runs a
+        # new (batch, input buffer, output buffers) combination eagerly once, captures its CUDA graph on the second call and
+        # replays it from the third, so 3 calls per slot (6 on the host legs, which alternate two staging buffers per slot)
+        # put the graph instantiation outside the timed region whatever W is
+        for _ in range(prime + warmup):
             fn()
         if finish:
             finish()
@@ -558,7 +562,7 @@ def main():
                             "cuda_graph": False, "gflop_per_image": flops / 1e9},
                     gpu_launches=launches * args.steps, gpu_launches_per_step=launches)
         if not args.no_extras:
-            e2e_ms, _ = timed(step_host, args.steps, warm)
+            e2e_ms, _ = timed(step_host, args.steps, warm, prime=6 * nslot)
             line["e2e"] = {"value": to_metric(e2e_ms, args.steps), "unit": cfg["unit"], "ms_per_step": e2e_ms / args.steps,
                            "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
                            "api": "pinned fp32 images in (H2D inside the timed region), layer-by-layer C-ABI calls, detections out"}
@@ -667,25 +671,26 @@ def main():
             # forward of batch i on slot i % nslot; the previous batch (its forward is joined, this one keeps running) goes
             # into the gather ring
             i = tick["dev"]                 # logical batch index (position in the gather ring)
-            k = tick["calls"] % nslot       # the engine alternates its two instances per call: keep output buffers paired with them
+            k = tick["calls"] % nslot       # the engine goes round its instances call by call: keep output buffers paired with them
             tick["dev"] += 1
             tick["calls"] += 1
             eng.forward(imgs, io[k])
             if world > 1:
                 if nslot == 1:
                     collect(i, 0)
-                elif i > tick["base"]:
+                elif i - (nslot - 1) >= tick["base"]:      # every slot is busy: the oldest batch in flight is joined and handed over
                     eng.join_previous()
-                    collect(i - 1, k ^ 1)
+                    collect(i - (nslot - 1), (k + 1) % nslot)
 
         def finish_device():
             # drain inside the timed region: join the last forward, hand its batch over and gather the (partial) last group
-            if nslot == 2:
+            if nslot >= 2:
                 eng.join()
             if world > 1:
                 i = tick["dev"]
-                if nslot == 2 and i > tick["base"]:
-                    collect(i - 1, (tick["calls"] - 1) % nslot)
+                if nslot >= 2:
+                    for j in range(max(tick["base"], i - (nslot - 1)), i):
+                        collect(j, (tick["calls"] - (i - j)) % nslot)
                 if i % G != 0:
                     g0 = (i - i % G) % (2 * G)
                     dist.all_gather_into_tensor(gathered, ring[g0 * nb:(g0 + G) * nb])
@@ -704,7 +709,7 @@ def main():
             tick["u8"] += 1
             eng.forward_host_u8(imgs_u8_host, host_outs[k])
 
-        total_ms, clocks = timed(step_device, args.steps, warm, sampler, finish_device)
+        total_ms, clocks = timed(step_device, args.steps, warm, sampler, finish_device, prime=3 * nslot)
         n_launch = eng.launches_per_forward
         st = eng.stats()
         line.update(value=to_metric(total_ms, args.steps), ms_per_step=total_ms / args.steps, dtype=model.act_dtype, clocks=clocks,
@@ -715,12 +720,14 @@ def main():
                             "weights": "seeded re-init 1234 (demonet_b200/seeded.py)", "images": "torch.rand seed 1+rank",
                             "l2": "inputs larger than L2 (%.0f MB fp32 images per step; device memory %.1f GB)"
                                   % (B * 3 * S * S * 4 / 1e6, eng.device_bytes / 1e9),
-                            "cuda_graph": True, "batches_in_flight": nslot, "host_affinity": affinity_note, "engine": st},
+                            "cuda_graph": True, "batches_in_flight": nslot,
+                            "graph_priming": "%d untimed calls in front of the warm-up steps (eager, capture, first replay per engine "
+                                             "instance: set-up, not counted as warm-up)" % (3 * nslot), "host_affinity": affinity_note, "engine": st},
                     gpu_launches=n_launch * args.steps, gpu_launches_per_step=n_launch)
         if not args.no_extras:
-            e2e_ms, _ = timed(step_host, args.steps, warm)
+            e2e_ms, _ = timed(step_host, args.steps, warm, prime=6 * nslot)
             counts_ok = all(int(h["counts"].min()) >= 0 for h in host_outs)
-            u8_ms, _ = timed(step_host_u8, args.steps, warm)
+            u8_ms, _ = timed(step_host_u8, args.steps, warm, prime=6 * nslot)
             line["e2e"] = {"value": to_metric(e2e_ms, args.steps), "unit": cfg["unit"], "ms_per_step": e2e_ms / args.steps,
                            "h2d_bytes_per_step": B * 3 * S * S * 4, "d2h_bytes_per_step": B * D * 28 + B * 4,
                            "api": "dn_engine_forward_host (pinned fp32 images in, detections out: the reference's input contract)",
@@ -735,7 +742,7 @@ def main():
 
             def step_api():
                 holder["d"] = model(img_list)
-            api_ms, _ = timed(step_api, args.steps, warm)
+            api_ms, _ = timed(step_api, args.steps, warm, prime=3 * nslot)
             one = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=K, act_dtype=args.act_dtype) if cfg["model"] == "v3" else \
                 demonet_b200.ssd_lite_mobilenet_v2(image_size=S, num_classes=K, score_thresh=0.5, act_dtype=args.act_dtype)
             one.load_state_dict(weights.seeded_state_dict(one.state_dict()))

@@ -28,6 +28,7 @@ struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     unsigned long long last_use = 0;
 };
+constexpr int DN_MAX_SLOTS = 4;           // engine instances of the pipeline mode (batches in flight)
 constexpr size_t DN_MAX_GRAPHS = 16;      // per engine instance; least recently used entries are dropped beyond this
 
 struct dn_engine {
@@ -70,17 +71,19 @@ struct dn_engine {
     std::vector<cudaEvent_t> op_done;               // per op, nullptr when nobody waits for it
     std::vector<std::vector<int>> deps;             // per op: producers on other lanes
     cudaEvent_t fork_ev = nullptr;
-    // pipeline mode (dn_model_desc.pipeline_slots == 2): `twin` is a second complete engine (own arena, tensor maps,
-    // graphs); consecutive forwards alternate between the two on engine-owned streams, so the latency-bound tail of
-    // forward i (tiny layers, NMS rounds) overlaps the bandwidth-bound head of forward i+1
-    dn_engine* twin = nullptr;
+    // pipeline mode (dn_model_desc.pipeline_slots = n in 2..4): twins[0..n-2] are further complete engines (own arena,
+    // tensor maps, graphs); consecutive forwards go round the n instances on engine-owned streams, so the latency-bound
+    // tail of forward i (tiny layers, NMS rounds) overlaps the bandwidth-bound head of the forwards behind it
+    // (measured at B = 256, one box: 72.6k img/s with one in flight, 79.4k with two, 81.3k with three, 82.3k with four)
+    std::vector<dn_engine*> twins;
+    int n_slots = 1;
     int next_slot = 0;
     int last_slot = 0;                              // slot of the forward issued last (dn_engine_copy_buffer reads it)
     long long n_graph_replays = 0;                  // forwards that were one cudaGraphLaunch
     long long n_forwards = 0;
-    cudaStream_t slot_stream[2] = {nullptr, nullptr};
-    cudaEvent_t slot_in[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
-    bool slot_pending[2] = {false, false};
+    cudaStream_t slot_stream[DN_MAX_SLOTS] = {};
+    cudaEvent_t slot_in[DN_MAX_SLOTS] = {}, slot_done[DN_MAX_SLOTS] = {};
+    bool slot_pending[DN_MAX_SLOTS] = {};
     // staging for dn_engine_forward_host: two input buffers so that the H2D copy of call i+1 (on copy_stream)
     // overlaps the forward of call i (on the caller's stream)
     float* stage_images = nullptr;              // [2][max_batch,3,H,W]
@@ -107,6 +110,8 @@ static void drop_graphs(dn_engine* e) {
 extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max_batch) {
     DN_REQUIRE(out && d, DN_ERR_INVALID, "NULL argument");
     DN_REQUIRE(max_batch > 0, DN_ERR_INVALID, "max_batch must be positive");
+    DN_REQUIRE(d->pipeline_slots >= 0 && d->pipeline_slots <= DN_MAX_SLOTS, DN_ERR_INVALID, "pipeline_slots must be in 0..%d (got %d)",
+               DN_MAX_SLOTS, d->pipeline_slots);
     DN_REQUIRE(d->n_ops > 0 && d->n_bufs > 0 && d->ops_host && d->bufs_host && d->anchors_host, DN_ERR_INVALID,
                "model description is incomplete");
     DN_REQUIRE(d->logits_buf >= 0 && d->logits_buf < d->n_bufs && d->bbox_buf >= 0 && d->bbox_buf < d->n_bufs,
@@ -237,12 +242,17 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
         set_error("%s failed: %s", #x, cudaGetErrorString(cudaGetLastError())); \
         return fail(DN_ERR_CUDA);                                               \
     }
-    if (d->pipeline_slots == 2) {
+    if (d->pipeline_slots >= 2) {
         dn_model_desc d1 = *d;
         d1.pipeline_slots = 0;
-        int rc = dn_engine_create(&e->twin, &d1, max_batch);
-        if (rc) return fail(rc);
-        for (int i = 0; i < 2; ++i) {
+        e->n_slots = d->pipeline_slots;
+        for (int i = 1; i < e->n_slots; ++i) {
+            dn_engine* t = nullptr;
+            int rc = dn_engine_create(&t, &d1, max_batch);
+            if (rc) return fail(rc);
+            e->twins.push_back(t);
+        }
+        for (int i = 0; i < e->n_slots; ++i) {
             TRY_AFTER(cudaStreamCreateWithFlags(&e->slot_stream[i], cudaStreamNonBlocking));
             TRY_AFTER(cudaEventCreateWithFlags(&e->slot_in[i], cudaEventDisableTiming));
             TRY_AFTER(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
@@ -255,11 +265,9 @@ extern "C" int dn_engine_create(dn_engine** out, const dn_model_desc* d, int max
 
 extern "C" int dn_engine_destroy(dn_engine* e) {
     if (!e) return DN_OK;
-    if (e->twin) {
-        cudaDeviceSynchronize();
-        dn_engine_destroy(e->twin);
-    }
-    for (int i = 0; i < 2; ++i) {
+    if (!e->twins.empty()) cudaDeviceSynchronize();
+    for (dn_engine* t : e->twins) dn_engine_destroy(t);
+    for (int i = 0; i < DN_MAX_SLOTS; ++i) {
         if (e->slot_stream[i]) cudaStreamDestroy(e->slot_stream[i]);
         if (e->slot_in[i]) cudaEventDestroy(e->slot_in[i]);
         if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
@@ -292,8 +300,8 @@ extern "C" int dn_engine_destroy(dn_engine* e) {
 
 extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes) {
     DN_REQUIRE(e && blob_host && bytes > 0, DN_ERR_INVALID, "NULL argument");
-    if (e->twin) {
-        int rc = dn_engine_load_weights(e->twin, blob_host, bytes);
+    for (dn_engine* t : e->twins) {
+        int rc = dn_engine_load_weights(t, blob_host, bytes);
         if (rc) return rc;
     }
     for (size_t i = 0; i < e->ops.size(); ++i) {
@@ -528,17 +536,17 @@ static int forward_one(dn_engine* e, const float* images_dev, int B, float* out_
 extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
                                  int64_t* out_labels, int32_t* out_counts, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
-    if (!e->twin) return forward_one(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, stream_);
+    if (e->twins.empty()) return forward_one(e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, stream_);
     // pipeline mode: the forward runs on the slot's own stream behind everything already enqueued on the caller's
     // stream; the caller's stream is NOT made to wait for it here (that would serialise the next call behind this
     // one) -- dn_engine_join / dn_engine_join_previous order the results on a stream
     cudaStream_t s = (cudaStream_t)stream_;
     const int k = e->next_slot;
-    e->next_slot ^= 1;
+    e->next_slot = (k + 1) % e->n_slots;
     e->last_slot = k;
     DN_CHECK_CUDA(cudaEventRecord(e->slot_in[k], s));
     DN_CHECK_CUDA(cudaStreamWaitEvent(e->slot_stream[k], e->slot_in[k], 0));
-    int rc = forward_one(k ? e->twin : e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, e->slot_stream[k]);
+    int rc = forward_one(k ? e->twins[k - 1] : e, images_dev, B, out_boxes, out_scores, out_labels, out_counts, e->slot_stream[k]);
     if (rc) return rc;
     DN_CHECK_CUDA(cudaEventRecord(e->slot_done[k], e->slot_stream[k]));
     e->slot_pending[k] = true;
@@ -547,8 +555,8 @@ extern "C" int dn_engine_forward(dn_engine* e, const float* images_dev, int B, f
 
 extern "C" int dn_engine_join(dn_engine* e, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
-    for (int k = 0; k < 2; ++k)
-        if (e->twin && e->slot_pending[k]) {
+    for (int k = 0; k < e->n_slots; ++k)
+        if (e->slot_pending[k]) {
             DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
             e->slot_pending[k] = false;
         }
@@ -557,8 +565,8 @@ extern "C" int dn_engine_join(dn_engine* e, void* stream_) {
 
 extern "C" int dn_engine_join_previous(dn_engine* e, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
-    if (!e->twin) return DN_OK;
-    const int k = e->next_slot;          // the slot the NEXT call will use = the one used by the call before the last
+    if (e->twins.empty()) return DN_OK;
+    const int k = e->next_slot;          // the slot the NEXT call will use = the oldest forward in flight (n - 1 calls back)
     if (e->slot_pending[k]) {
         DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
         e->slot_pending[k] = false;
@@ -663,11 +671,11 @@ static int forward_host_impl(dn_engine* e, const void* images_host, bool u8, int
 static int forward_host_slots(dn_engine* e, const void* images_host, bool u8, int B, float* ob, float* os, int64_t* ol,
                               int32_t* oc, void* stream_) {
     DN_REQUIRE(e != nullptr, DN_ERR_INVALID, "engine is NULL");
-    if (!e->twin) return forward_host_impl(e, images_host, u8, B, ob, os, ol, oc, stream_);
+    if (e->twins.empty()) return forward_host_impl(e, images_host, u8, B, ob, os, ol, oc, stream_);
     const int k = e->next_slot;
-    e->next_slot ^= 1;
+    e->next_slot = (k + 1) % e->n_slots;
     e->last_slot = k;
-    int rc = forward_host_impl(k ? e->twin : e, images_host, u8, B, ob, os, ol, oc, e->slot_stream[k]);
+    int rc = forward_host_impl(k ? e->twins[k - 1] : e, images_host, u8, B, ob, os, ol, oc, e->slot_stream[k]);
     if (rc) return rc;
     DN_CHECK_CUDA(cudaEventRecord(e->slot_done[k], e->slot_stream[k]));
     DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[k], 0));
@@ -701,8 +709,8 @@ extern "C" int dn_engine_copy_buffer(dn_engine* e, int buf_id, void* dst_dev, si
     DN_REQUIRE(bytes <= cap, DN_ERR_INVALID, "copy of %zu bytes exceeds the buffer (%zu)", bytes, cap);
     // pipeline mode: the arena of the slot that ran the forward issued last, ordered behind that forward
     dn_engine* src = e;
-    if (e->twin) {
-        if (e->last_slot == 1) src = e->twin;
+    if (!e->twins.empty()) {
+        if (e->last_slot > 0) src = e->twins[e->last_slot - 1];
         if (e->slot_pending[e->last_slot]) DN_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, e->slot_done[e->last_slot], 0));
     }
     DN_CHECK_CUDA(cudaMemcpyAsync(dst_dev, buf_ptr(src, buf_id), bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
@@ -836,7 +844,7 @@ extern "C" int dn_se_project(const void* x, const float* se_w1, const float* se_
 extern "C" int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out) {
     DN_REQUIRE(e && out, DN_ERR_INVALID, "NULL argument");
     *out = dn_engine_stats{};
-    const dn_engine* last = (e->twin && e->last_slot == 1) ? e->twin : e;
+    const dn_engine* last = e->last_slot > 0 ? e->twins[e->last_slot - 1] : e;
     for (const auto& o : e->ops) {
         out->fused_pwdw += (o.kind == DN_OP_PWDW);
         out->fused_dwpw += (o.kind == DN_OP_DWPW);
@@ -845,14 +853,18 @@ extern "C" int dn_engine_get_stats(dn_engine* e, dn_engine_stats* out) {
     out->se_pooled = last->n_se_pooled;
     for (const auto& o : e->ops) out->se_folded += (o.kind == DN_OP_SE && o.se_fold && e->desc.gemm_impl == 0);
     out->launches_per_forward = dn_engine_launches_per_forward(const_cast<dn_engine*>(last));
-    out->pipeline_slots = e->twin ? 2 : 1;
+    out->pipeline_slots = e->n_slots;
     out->last_slot = e->last_slot;
-    out->forwards = e->n_forwards + (e->twin ? e->twin->n_forwards : 0);
-    out->graph_replays = e->n_graph_replays + (e->twin ? e->twin->n_graph_replays : 0);
+    out->forwards = e->n_forwards;
+    out->graph_replays = e->n_graph_replays;
+    for (const dn_engine* t : e->twins) out->forwards += t->n_forwards, out->graph_replays += t->n_graph_replays;
     out->act_dtype = DN_ACT_DTYPE_ID;
     return DN_OK;
 }
 
 extern "C" size_t dn_engine_device_bytes(dn_engine* e) {
-    return e ? e->device_bytes + (e->twin ? e->twin->device_bytes : 0) : 0;
+    if (!e) return 0;
+    size_t n = e->device_bytes;
+    for (const dn_engine* t : e->twins) n += t->device_bytes;
+    return n;
 }

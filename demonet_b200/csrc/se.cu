@@ -12,6 +12,8 @@
 // w1: fp32 [Cs][C]; w2t: fp32 [Cs][C] (fc2 weight TRANSPOSED so that threads read it coalesced).
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dn {
@@ -98,16 +100,11 @@ se_pool_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int HW,
 // se_fc1_kernel computes hidden rows [r*Cs/NC, ...) of its 16 images, CTA (r, grp) of se_fc2_kernel the scales of
 // channels [r*C/NC, ...), so each weight matrix is read once per image group and no thread has more than SE_LD
 // independent weight loads to issue.  hidden: fp32 [groups][Cs][SE_GI].
-__global__ void __launch_bounds__(SE_FC_THREADS)
-se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, const float* __restrict__ b1,
-              float* __restrict__ hidden_g, int B, int HW, int C, int Cs, int chunks, int dw_parts, int dw_rows) {
-    extern __shared__ __align__(16) float s_fc[];
-    float* pooled = s_fc;                       // [SE_GI][C]
-    pdl_trigger();
-    pdl_wait();
-    const int rank = blockIdx.x;
-    const int b0 = blockIdx.y * SE_GI;
-    float* hidden = hidden_g + (long long)blockIdx.y * Cs * SE_GI;
+// fc1 of one CTA: hidden rows [rank * Cs / NC, ...) of the 16 images from b0 on, written to `hidden` ([Cs][SE_GI], global
+// memory in the two-launch form, the CTA's own shared memory in the cluster form)
+__device__ __forceinline__ void se_fc1_body(const float* __restrict__ partial, const float* __restrict__ w1,
+                                            const float* __restrict__ b1, float* pooled, float* hidden, int rank, int b0, int B,
+                                            int HW, int C, int Cs, int chunks, int dw_parts, int dw_rows) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // pooled means: thread = 4 channels of one image, the chunk sums of a thread are all in flight together
@@ -179,21 +176,21 @@ se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, c
 }
 
 __global__ void __launch_bounds__(SE_FC_THREADS)
-se_fc2_kernel(const float* __restrict__ hidden_g, const float* __restrict__ w2t, const float* __restrict__ b2,
-              float* __restrict__ scale, int B, int C, int Cs) {
+se_fc1_kernel(const float* __restrict__ partial, const float* __restrict__ w1, const float* __restrict__ b1,
+              float* __restrict__ hidden_g, int B, int HW, int C, int Cs, int chunks, int dw_parts, int dw_rows) {
     extern __shared__ __align__(16) float s_fc[];
-    float* hidden = s_fc;                       // [Cs][SE_GI]
-    float* part = hidden + Cs * SE_GI;          // [SE_NC slices][SE_GI][C / SE_NC]
     pdl_trigger();
     pdl_wait();
-    const int rank = blockIdx.x;
-    const int b0 = blockIdx.y * SE_GI;
+    se_fc1_body(partial, w1, b1, s_fc, hidden_g + (long long)blockIdx.y * Cs * SE_GI, blockIdx.x, blockIdx.y * SE_GI, B, HW, C, Cs,
+                chunks, dw_parts, dw_rows);
+}
+
+// fc2 + hardsigmoid of one CTA: the scales of channels [rank * C / NC, ...) of the 16 images from b0 on; `hidden` is the
+// complete [Cs][SE_GI] block in shared memory, `part` [SE_NC slices][SE_GI][C / SE_NC] scratch
+__device__ __forceinline__ void se_fc2_body(const float* hidden, float* part, const float* __restrict__ w2t,
+                                            const float* __restrict__ b2, float* __restrict__ scale, int rank, int b0, int B, int C,
+                                            int Cs) {
     const int tid = threadIdx.x;
-    {
-        const float4* src = reinterpret_cast<const float4*>(hidden_g + (long long)blockIdx.y * Cs * SE_GI);
-        for (int i = tid; i < Cs * SE_GI / 4; i += SE_FC_THREADS) reinterpret_cast<float4*>(hidden)[i] = __ldg(src + i);
-    }
-    __syncthreads();
     // thread = (channel of this CTA's share, slice of the Cs inputs)
     const int cper = C / SE_NC;                 // C % 8 == 0
     const int c_begin = rank * cper;
@@ -235,6 +232,50 @@ se_fc2_kernel(const float* __restrict__ hidden_g, const float* __restrict__ w2t,
         // hardsigmoid(x) = relu6(x + 3) / 6
         scale[(long long)(b0 + g) * C + c_begin + cl] = __fdiv_rn(fminf(fmaxf(s + 3.f, 0.f), 6.f), 6.f);
     }
+}
+
+__global__ void __launch_bounds__(SE_FC_THREADS)
+se_fc2_kernel(const float* __restrict__ hidden_g, const float* __restrict__ w2t, const float* __restrict__ b2,
+              float* __restrict__ scale, int B, int C, int Cs) {
+    extern __shared__ __align__(16) float s_fc[];
+    float* hidden = s_fc;                       // [Cs][SE_GI]
+    pdl_trigger();
+    pdl_wait();
+    {
+        const float4* src = reinterpret_cast<const float4*>(hidden_g + (long long)blockIdx.y * Cs * SE_GI);
+        for (int i = threadIdx.x; i < Cs * SE_GI / 4; i += SE_FC_THREADS) reinterpret_cast<float4*>(hidden)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    se_fc2_body(hidden, hidden + Cs * SE_GI, w2t, b2, scale, blockIdx.x, blockIdx.y * SE_GI, B, C, Cs);
+}
+
+// Both layers in ONE launch: the SE_NC CTAs of an image group form a thread-block cluster.  Each computes its rows of fc1
+// into its own shared memory, the cluster synchronises, every CTA pulls the other seven CTAs' rows through distributed
+// shared memory (<= 11 KB) and goes on with its channels of fc2 -- the hidden activations never visit global memory and
+// the launch gap between the two layers (8 of the 16 SE launches of a V3 forward) is gone.  Same arithmetic in the same
+// order as the two-launch form: bit-identical scales.
+__global__ void __cluster_dims__(SE_NC, 1, 1) __launch_bounds__(SE_FC_THREADS)
+se_fc_cluster_kernel(const float* __restrict__ partial, const float* __restrict__ w1, const float* __restrict__ b1,
+                     const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ scale, int B, int HW, int C,
+                     int Cs, int chunks, int dw_parts, int dw_rows) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) float s_fc[];
+    float* pooled = s_fc;                       // [SE_GI][C]; fc2's `part` scratch afterwards
+    float* hidden = s_fc + SE_GI * C;           // [Cs][SE_GI]
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_trigger();
+    pdl_wait();
+    const int rank = (int)cluster.block_rank();
+    const int b0 = blockIdx.y * SE_GI;
+    se_fc1_body(partial, w1, b1, pooled, hidden, rank, b0, B, HW, C, Cs, chunks, dw_parts, dw_rows);
+    cluster.sync();
+    const int rows_per = ceil_div(Cs, SE_NC);
+    for (int i = threadIdx.x; i < Cs * SE_GI / 4; i += SE_FC_THREADS) {
+        const int owner = (i / (SE_GI / 4)) / rows_per;
+        if (owner != rank) reinterpret_cast<float4*>(hidden)[i] = reinterpret_cast<const float4*>(cluster.map_shared_rank(hidden, owner))[i];
+    }
+    cluster.sync();                             // every remote read is done (and the pulled rows are visible CTA-wide)
+    se_fc2_body(hidden, pooled, w2t, b2, scale, rank, b0, B, C, Cs);
 }
 
 // x[b][p][c] *= scale[b][c]
@@ -289,6 +330,14 @@ namespace dn {
 
 int se_max_pool_slots() { return SE_MAX_CHUNKS; }
 
+// DN_SE_CLUSTER=1: fc1 + fc2 as one cluster launch (read per call).  Bit-identical to the two-launch form and NOT the
+// default: with two batches in flight the eight co-scheduled 512-thread CTAs of a cluster wait for eight free SM slots at
+// once, and the step is 0.4 % slower (79.4k vs 79.7k img/s, two A/B pairs on one box) although eight launches are gone.
+static bool se_fc_cluster() {
+    const char* e = getenv("DN_SE_CLUSTER");
+    return e && e[0] == '1';
+}
+
 // dw_parts > 0: the channel sums are already in the workspace, written by the depthwise row stream that produced x
 // (dwconv_stream.cu, POOL) as [B][dw_slots][C] over dw_parts CTA shares of a B * dw_rows row stream; the pooling pass is
 // skipped.
@@ -323,11 +372,19 @@ int se_inplace_pooled(void* x, const float* w1, const float* b1, const float* w2
                    p.rows, p.pool_px);
         DN_CHECK_LAUNCH();
     }
-    launch_pdl(se_fc1_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc1_smem, s, (const float*)partial, w1, b1, hidden, B, HW, C, Cs,
-               dw_parts ? dw_slots : p.pool_chunks, dw_parts, dw_rows);
-    DN_CHECK_LAUNCH();
-    launch_pdl(se_fc2_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)hidden, w2t, b2, scale, B, C, Cs);
-    DN_CHECK_LAUNCH();
+    if (se_fc_cluster()) {
+        static SmemOptIn optin_fcc;
+        DN_CHECK_CUDA(optin_fcc.ensure(se_fc_cluster_kernel, fc2_smem, 160 * 1024));
+        launch_pdl(se_fc_cluster_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)partial, w1, b1, w2t, b2, scale,
+                   B, HW, C, Cs, dw_parts ? dw_slots : p.pool_chunks, dw_parts, dw_rows);
+        DN_CHECK_LAUNCH();
+    } else {
+        launch_pdl(se_fc1_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc1_smem, s, (const float*)partial, w1, b1, hidden, B, HW, C, Cs,
+                   dw_parts ? dw_slots : p.pool_chunks, dw_parts, dw_rows);
+        DN_CHECK_LAUNCH();
+        launch_pdl(se_fc2_kernel, dim3(SE_NC, groups), SE_FC_THREADS, fc2_smem, s, (const float*)hidden, w2t, b2, scale, B, C, Cs);
+        DN_CHECK_LAUNCH();
+    }
     if (!apply) return DN_OK;
     launch_pdl(se_scale_kernel, dim3(p.scale_chunks, B), SE_POOL_THREADS, 0, s, (uint4*)x, (const float*)scale, HW, C, p.CV, p.rows,
                p.scale_px);

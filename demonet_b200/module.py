@@ -90,7 +90,12 @@ class _Engine:
 
     @property
     def pipelined(self) -> bool:
-        return int(self._desc_kwargs.get("pipeline_slots", 0)) == 2
+        return self.n_slots >= 2
+
+    @property
+    def n_slots(self) -> int:
+        """Forwards the engine keeps in flight (1 = plain stream semantics, 2..4 = pipeline mode)."""
+        return max(1, int(self._desc_kwargs.get("pipeline_slots", 0)))
 
     def join(self):
         """Pipeline mode: order every forward issued so far before later work on the current stream."""
@@ -98,7 +103,8 @@ class _Engine:
             self._check(self._lib.dn_engine_join(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
 
     def join_previous(self):
-        """Pipeline mode: order the forward issued BEFORE the most recent one before later work on the current stream."""
+        """Pipeline mode with n slots: order the OLDEST forward in flight (issued n - 1 calls before the most recent one, the
+        one whose slot the next call reuses) before later work on the current stream; a no-op until n forwards were issued."""
         with torch.cuda.device(self.device):
             self._check(self._lib.dn_engine_join_previous(self._handle, torch.cuda.current_stream(self.device).cuda_stream))
 
@@ -259,7 +265,9 @@ class SSDLiteB200(nn.Module):
         self.image_std = list(image_std) if image_std is not None else [0.229, 0.224, 0.225]
         self._gemm_impl = gemm_impl
         self._use_cuda_graph = use_cuda_graph
-        self._pipeline_slots = int(pipeline_slots)      # 2: consecutive batches overlap on two engine instances
+        self._pipeline_slots = int(pipeline_slots)      # 2..4: consecutive batches overlap on that many engine instances
+        if not 0 <= self._pipeline_slots <= 4:
+            raise ValueError("pipeline_slots must be in 0..4 (got %d)" % self._pipeline_slots)
         self.act_dtype = act_dtype or _C.DEFAULT_ACT_DTYPE      # "fp16" (default) or "bf16": activation storage type
         if self.act_dtype not in _C.ACT_DTYPES:
             raise ValueError("act_dtype must be one of %s" % (_C.ACT_DTYPES,))
@@ -557,21 +565,22 @@ class SSDLiteB200(nn.Module):
         return io["boxes"].clone(), io["scores"].clone(), io["labels"].clone(), io["counts"].clone()
 
     def forward_batches(self, batches):
-        """Throughput path: iterate over [B,3,S,S] fp32 CUDA batches and yield their detections, keeping two batches in
-        flight when the model was built with pipeline_slots=2 (the post-processing tail of batch i overlaps the backbone
-        of batch i+1).  Every batch must stay alive and unchanged until its detections have been yielded."""
-        pending = None
+        """Throughput path: iterate over [B,3,S,S] fp32 CUDA batches and yield their detections, keeping n batches in
+        flight when the model was built with pipeline_slots=n (2..4; the post-processing tail of batch i overlaps the
+        backbone of the batches behind it).  Every batch must stay alive and unchanged until its detections have been yielded."""
+        pending = []                               # batches in flight, oldest first: (io, B, engine, source tensor)
         slot = 0
         for images in batches:
             if images.dim() != 4 or tuple(images.shape[1:]) != (3, self.plan.size, self.plan.size) or not images.is_cuda:
                 raise ValueError("forward_batches expects fp32 CUDA batches of shape [B,3,%d,%d]" % (self.plan.size, self.plan.size))
             B = images.shape[0]
             cur = self._engines.get(str(images.device))
-            if pending is not None and cur is not None and cur.max_batch < B:
+            if pending and cur is not None and cur.max_batch < B:
                 # a larger batch re-creates the engine: finish and hand out what is still in flight on the old one first
-                pending[2].join()
-                yield self._detections(pending[0], pending[1])
-                pending = None
+                pending[0][2].join()
+                for done in pending:
+                    yield self._detections(done[0], done[1])
+                pending = []
             eng = self._engine_for(images.device, B)
             key = (str(images.device) + "/slot%d" % slot, B)
             io = self._io.get(key)
@@ -583,15 +592,18 @@ class SSDLiteB200(nn.Module):
                           counts=torch.empty(B, dtype=torch.int32, device=images.device))
             src = images if images.dtype == torch.float32 and images.is_contiguous() else images.float().contiguous()
             eng.forward(src, io)
-            if pending is not None:
+            pending.append((io, B, eng, src))      # `src` (possibly a temporary) stays alive until its batch was joined
+            depth = max(2, eng.n_slots)            # (one engine instance: still two sets of outputs, batch i - 1 is read while i runs)
+            if len(pending) >= depth:              # every slot is busy: the oldest batch is handed out before its slot is reused
                 if eng.pipelined:
                     eng.join_previous()
-                yield self._detections(pending[0], pending[1])
-            pending = (io, B, eng, src)            # `src` (possibly a temporary) stays alive until its batch was joined
-            slot ^= 1
-        if pending is not None:
-            pending[2].join()
-            yield self._detections(pending[0], pending[1])
+                done = pending.pop(0)
+                yield self._detections(done[0], done[1])
+            slot = (slot + 1) % depth
+        if pending:
+            pending[0][2].join()
+            for done in pending:
+                yield self._detections(done[0], done[1])
 
     def head_outputs(self, images: Tensor):
         """(cls_logits [B,P,K], bbox_regression [B,P,4]) of a [B,3,S,S] CUDA batch -- parity hook."""

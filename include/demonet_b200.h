@@ -324,8 +324,8 @@ typedef struct {
     dn_postprocess_params post;
     int32_t gemm_impl;                     /* 0 = tcgen05 (product), 1 = SIMT self-check      */
     int32_t use_cuda_graph;
-    int32_t pipeline_slots;                /* 0 / 1: one forward at a time (strict stream semantics).  2: consecutive
-                                              dn_engine_forward calls alternate between two complete engine instances on
+    int32_t pipeline_slots;                /* 0 / 1: one forward at a time (strict stream semantics).  n = 2..4: consecutive
+                                              dn_engine_forward calls go round n complete engine instances on
                                               engine-owned streams and overlap; see dn_engine_join                     */
     int32_t reserved;
 } dn_model_desc;
@@ -339,10 +339,11 @@ int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_t bytes);
 /* images_dev: fp32 [B,3,H,W]; outputs as in dn_postprocess */
 int dn_engine_forward(dn_engine* e, const float* images_dev, int B, float* out_boxes, float* out_scores,
                       int64_t* out_labels, int32_t* out_counts, void* stream);
-/* Pipeline mode only (pipeline_slots == 2): dn_engine_forward returns with the forward enqueued on an engine-owned
+/* Pipeline mode only (pipeline_slots = n >= 2): dn_engine_forward returns with the forward enqueued on an engine-owned
  * stream (ordered behind the work already on `stream`), NOT yet ordered before later work on `stream`.
- * dn_engine_join makes `stream` wait for every forward issued so far; dn_engine_join_previous only for the forward
- * issued before the most recent one (so that a consumer of batch i-1 runs while batch i computes).
+ * dn_engine_join makes `stream` wait for every forward issued so far; dn_engine_join_previous only for the OLDEST
+ * forward in flight -- the one issued n - 1 calls before the most recent one, whose slot the next call reuses (n = 2: the
+ * forward before the most recent one) -- so that a consumer of batch i-n+1 runs while batches i-n+2 .. i compute.
  * Both are no-ops without pipeline mode.  The host entry points keep their plain contract in either mode. */
 int dn_engine_join(dn_engine* e, void* stream);
 int dn_engine_join_previous(dn_engine* e, void* stream);
@@ -377,7 +378,7 @@ typedef struct {
     int32_t fused_pwdw, fused_dwpw;      /* fused expand+depthwise / depthwise+project launches in the plan          */
     int32_t se_layers, se_pooled;        /* squeeze-excitation layers / those whose pooling the depthwise launch did */
     int32_t se_folded, reserved;         /* ... / those whose scaling pass is folded into the project GEMM           */
-    int32_t pipeline_slots, last_slot;   /* 1 or 2 engine instances; the slot of the forward issued last             */
+    int32_t pipeline_slots, last_slot;   /* 1..4 engine instances; the slot of the forward issued last              */
     int32_t act_dtype;                   /* storage type of the activations: 0 = bf16, 1 = fp16                      */
     int64_t forwards, graph_replays;     /* forwards enqueued so far / those that were one cudaGraphLaunch           */
 } dn_engine_stats;

@@ -198,21 +198,21 @@ def test_fp16_is_closer_to_the_reference_than_bf16():
 
 
 def test_benchmarked_configuration_against_oracle():
-    """The configuration bench.py times -- batch 256, pipeline_slots=2, CUDA-graph replay, fused blocks, squeeze-excitation
+    """The configuration bench.py times -- batch 256, pipeline_slots=4, CUDA-graph replay, fused blocks, squeeze-excitation
     pooled by the depthwise row streams -- compared with the fp32 oracle on 16 sampled images, after asserting that those
     paths were really taken (dn_engine_get_stats).  Also: an image's detections do not depend on the batch it travels in."""
     B = 256
-    model, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large, pipeline_slots=2)
+    model, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large, pipeline_slots=4)
     x = weights.synthetic_images(B, 320, seed=77)
     xd = x.cuda()
-    outs = list(model.forward_batches([xd] * 6))          # per slot: eager, capture, replay
+    outs = list(model.forward_batches([xd] * 12))         # per slot: eager, capture, replay
     eng = model._engine_for(xd.device, B)
     st = eng.stats()
-    assert st["pipeline_slots"] == 2 and st["graph_replays"] >= 2, st
+    assert st["pipeline_slots"] == 4 and st["graph_replays"] >= 4, st
     assert st["fused_pwdw"] == 1 and st["fused_dwpw"] == 1, st
     assert st["se_layers"] == 8 and st["se_pooled"] == 8 and st["se_folded"] == 8, st
     assert st["act_dtype"] == model.act_dtype
-    dets = outs[-1]                                       # a replayed graph on the second slot
+    dets = outs[-1]                                       # a replayed graph on the last slot
     for o in outs[:-1]:
         for a, b in zip(o[::37], dets[::37]):
             assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["labels"], b["labels"])
@@ -341,16 +341,18 @@ def test_default_box_generator_op():
     assert gen.num_anchors_per_location() == [6] * 6
 
 
-def test_pipeline_mode_matches_plain_engine():
-    """pipeline_slots=2: consecutive batches alternate between two engine instances on engine-owned streams.  The
-    detections must equal the plain engine's, batch by batch, for the streaming API, single calls and host inputs."""
+@pytest.mark.parametrize("slots", [2, 3, 4])
+def test_pipeline_mode_matches_plain_engine(slots):
+    """pipeline_slots=n: consecutive batches go round n engine instances on engine-owned streams.  The detections must
+    equal the plain engine's, batch by batch, for the streaming API (more and fewer batches than slots), single calls and
+    host inputs."""
     plain, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large)
-    piped, _ = _model(demonet_b200.ssdlite320_mobilenet_v3_large, pipeline_slots=2)
-    batches = [weights.synthetic_images(4, 320, seed=10 + i).cuda() for i in range(5)]
+    piped, _ = _model(demonet_b200.ssdlite320_mobilenet_v3_large, pipeline_slots=slots)
+    batches = [weights.synthetic_images(4, 320, seed=10 + i).cuda() for i in range(9)]
     want = [plain(list(b)) for b in batches]
-    got = list(piped.forward_batches(batches))
-    assert len(got) == len(want)
-    for g, w in zip(got, want):
+    got = list(piped.forward_batches(batches)) + list(piped.forward_batches(batches[:2]))
+    assert len(got) == len(want) + 2
+    for g, w in zip(got, want + want[:2]):
         for a, b in zip(g, w):
             assert torch.equal(a["scores"], b["scores"]) and torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["labels"], b["labels"])
     for _ in range(3):                                   # single calls join at once; slots keep alternating underneath

@@ -186,6 +186,26 @@ def test_se(C, Cs, HW, dt):
     _close_h16(dt, y, ref, extra_abs=2e-3)
 
 
+@pytest.mark.parametrize("B,C,Cs,HW", [(3, 72, 24, 1600), (37, 480, 120, 400), (64, 672, 168, 100), (17, 16, 8, 9), (50, 120, 32, 64)])
+def test_se_cluster_form_is_bit_identical(B, C, Cs, HW, dt, monkeypatch):
+    """fc1 + fc2 as ONE launch (thread-block clusters of eight CTAs, hidden activations exchanged through distributed shared
+    memory) against the two-launch form: same arithmetic, same order, identical bits; several image groups, a ragged last one."""
+    g = torch.Generator().manual_seed(B + C + HW)
+    x = (torch.randn(B, HW, C, generator=g)).to(dt).cuda()
+    w1 = (torch.randn(Cs, C, generator=g) / C ** 0.5).cuda()
+    b1 = torch.randn(Cs, generator=g).cuda() * 0.5
+    w2t = (torch.randn(Cs, C, generator=g) / Cs ** 0.5).cuda()
+    b2 = torch.randn(C, generator=g).cuda() * 0.5
+    y0 = ops.se_inplace(x.clone(), w1, b1, w2t, b2)
+    monkeypatch.setenv("DN_SE_CLUSTER", "1")
+    y = ops.se_inplace(x.clone(), w1, b1, w2t, b2)
+    monkeypatch.delenv("DN_SE_CLUSTER")
+    assert torch.equal(y, y0)
+    xf = x.float()
+    scale = F.hardsigmoid(F.relu(xf.mean(1) @ w1.t() + b1) @ w2t + b2)
+    _close_h16(dt, y, xf * scale[:, None, :], extra_abs=2e-3)
+
+
 @pytest.mark.parametrize("B,H,W,C,Cs,k,stride,act,want_pooled", [
     (64, 40, 40, 120, 32, 5, 1, "relu", True),            # V3 blocks 4-5 at batch size
     (48, 20, 20, 480, 120, 3, 1, "hardswish", True),      # block 10
