@@ -12,12 +12,15 @@ fake (shape-only) implementations:
                                                                       -> boxes [B,D,4], scores [B,D], labels [B,D], counts [B]
     torch.ops.demonet_b200.ssdlite_forward(images, engine_id)         -> the same four padded tensors
 
+`ExportableSSDLite` wraps the last one for `torch.export` / `torch.compile(fullgraph=True)`, `ScriptableSSDLite` for
+`torch.jit.script` (List[Tensor] in, (losses, List[Dict]) out like the scripted reference).
+
 `postprocess` and `ssdlite_forward` have static output shapes (padded to detections_per_img + counts), which is what
 makes the exported graph free of data-dependent shapes.  `ssdlite_forward` addresses a live engine through the integer
 id `SSDLiteB200.export_handle()` returns (an exported program captures it as a constant; the module must outlive it).
 The CUDA implementations are the ones of `demonet_b200.ops`; there is no CPU kernel.
 """
-from typing import Dict, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 from torch import Tensor
@@ -100,3 +103,33 @@ class ExportableSSDLite(torch.nn.Module):
 
     def forward(self, images: Tensor):
         return torch.ops.demonet_b200.ssdlite_forward(images, self.engine_id)
+
+
+class ScriptableSSDLite(torch.nn.Module):
+    """The detector in the form `torch.jit.script` accepts — the reference's own main test scripts its model and compares
+    the scripted with the eager detections (test/test_model.py:85-119).  The arithmetic lives behind the C ABI, so the
+    scripted graph is: stack the images, ONE call of the registered operator `demonet_b200::ssdlite_forward`, slice the
+    padded outputs by the per-image counts.  Like the scripted reference (generalized_ssd.py:336-349, `eager_outputs` under
+    scripting) the module returns `(losses, detections)` with an empty loss dict, scripted or not.
+    Images must already have the network's S x S size (the resize of GeneralizedSSDTransform is done by
+    `SSDLiteB200.forward`; a scripted caller resizes beforehand)."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.engine_id: int = register_engine(model)
+        self.size: int = int(model.plan.size)
+        self._model = [model]                   # keeps the engine alive without registering it as a submodule
+
+    def forward(self, images: List[Tensor]) -> Tuple[Dict[str, Tensor], List[Dict[str, Tensor]]]:
+        for img in images:
+            if img.dim() != 3 or img.shape[0] != 3 or img.shape[1] != self.size or img.shape[2] != self.size:
+                raise ValueError("ScriptableSSDLite expects images of shape [3, S, S] with S the network input size")
+        batch = torch.stack(images, 0).to(torch.float32)
+        boxes, scores, labels, counts = torch.ops.demonet_b200.ssdlite_forward(batch, self.engine_id)
+        n: List[int] = counts.to(torch.int64).tolist()
+        detections: List[Dict[str, Tensor]] = []
+        for i in range(len(images)):
+            k = n[i]
+            detections.append({"boxes": boxes[i, :k], "scores": scores[i, :k], "labels": labels[i, :k]})
+        losses: Dict[str, Tensor] = {}
+        return losses, detections

@@ -367,6 +367,23 @@ def test_pipeline_mode_matches_plain_engine(slots):
     assert torch.equal(cls_p, cls_q)
 
 
+def test_scripted_module_matches_eager():
+    """The reference's main test (test/test_model.py:85-119): torch.jit.script the detector, run two 3x320x320 images,
+    scripted detections == eager detections.  Here the scripted graph calls the registered operator."""
+    from demonet_b200 import custom_ops
+    model, sd = _model(demonet_b200.ssdlite320_mobilenet_v3_large)
+    x = [t for t in weights.synthetic_images(2, 320, seed=5).cuda()]
+    want = model(x)
+    scripted = torch.jit.script(custom_ops.ScriptableSSDLite(model))
+    assert "demonet_b200::ssdlite_forward" in str(scripted.graph)
+    losses, got = scripted(x)
+    assert losses == {} and len(got) == 2
+    for g, w in zip(got, want):
+        assert torch.equal(g["scores"], w["scores"]) and torch.equal(g["labels"], w["labels"]) and torch.equal(g["boxes"], w["boxes"])
+    with pytest.raises(Exception):
+        scripted([x[0][:, :100]])
+
+
 def test_exported_program_runs_the_engine():
     """torch.export captures the detector through torch.ops.demonet_b200.ssdlite_forward (static, padded
     output shapes) and the exported program reproduces the module's detections; the post-processing op exports too."""

@@ -239,3 +239,14 @@ def test_se_pool_slot_arithmetic():
             last = ((b + 1) * H * parts + T - 1) // T - 1
             assert first == owner[b * H] and last == owner[(b + 1) * H - 1]
             assert last - first + 1 <= bound
+
+
+def test_detector_wrapper_scripts_without_a_gpu():
+    """torch.jit.script of the scriptable wrapper needs no device: the graph holds ONE call of the registered operator."""
+    import torch
+    import demonet_b200
+    from demonet_b200 import custom_ops
+    model = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=91)
+    scripted = torch.jit.script(custom_ops.ScriptableSSDLite(model))
+    g = str(scripted.graph)
+    assert g.count("demonet_b200::ssdlite_forward") == 1
