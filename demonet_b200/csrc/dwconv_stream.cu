@@ -106,9 +106,35 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // taps of this CTA's channel block, staged once by ALL threads and BEFORE the programmatic-dependency wait (weights are
+    // not produced by the previous kernel, so this runs while that kernel drains).  Eight independent loads per thread and
+    // round: one dependent load per round had every CTA spend 5-10 us here (ncu, 10 x 10 x 480 k5: 10 % of the samples on
+    // the store behind the load).  smem layout [channel group][tap][CH]: a thread's k*k taps are contiguous, so every tap
+    // is base + immediate offset (no per-tap address registers); lanes are k*k*16 bytes apart = 4 banks mod 32,
+    // conflict-free for LDS.128
+    {
+        const float* wsrc = w + (blockIdx.x % sp.ncblk) * sp.CB;
+        const int total = KS * KS * sp.CB;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                v[u] = (i < total) ? __ldg(wsrc + (i / sp.CB) * C + (i % sp.CB)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int c = i % sp.CB, t = i / sp.CB;
+                    wsm[((c / CH) * (KS * KS) + t) * CH + (c % CH)] = v[u];
+                }
+            }
+        }
+    }
     pdl_trigger();
     __syncthreads();
-    pdl_wait();                 // the barriers are set up; nothing above touches activation memory
+    pdl_wait();                 // the barriers are set up and the taps staged; nothing above touches activation memory
 
     // this CTA's channel block and its share of that block's output-row stream (B * H rows)
     // (wide maps: the width is cut into sp.nstrip column strips and a CTA also keeps its strip for its whole life)
@@ -154,15 +180,6 @@ dwconv_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __
     const int row_bytes = sp.IW * sp.CB * 2;
     const int n_cons = n_cons_warps * 32;
 
-    // taps and bias of this channel block, staged once
-    // smem layout [channel quad][tap][4]: a thread's k*k taps are contiguous, so every tap is base + immediate offset
-    // (no per-tap address registers); lanes are k*k*16 bytes apart = 4 banks mod 32, conflict-free for LDS.128
-    for (int i = ct; i < KS * KS * sp.CB; i += n_cons) {
-        const int c = i % sp.CB, t = i / sp.CB;
-        wsm[((c / CH) * (KS * KS) + t) * CH + (c % CH)] = __ldg(w + t * C + cblk * sp.CB + c);
-    }
-    __syncwarp();
-    asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
     const uint32_t wq = dws_u32(wsm + q * (KS * KS) * CH);
     float2 bv[NP];
 #pragma unroll

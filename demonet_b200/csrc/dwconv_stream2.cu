@@ -75,6 +75,29 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // taps of this CTA's channel block, staged once by all threads BEFORE the programmatic-dependency wait, eight
+    // independent loads per thread and round (see dwconv_stream.cu): [channel pair][tap][2] so that a thread's taps are
+    // base + immediate
+    {
+        const float* wsrc = w + (blockIdx.x % sp.ncblk) * sp.CB;
+        const int total = KS * KS * sp.CB;
+        for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                v[u] = (i < total) ? __ldg(wsrc + (i / sp.CB) * C + (i % sp.CB)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int c = i % sp.CB, t = i / sp.CB;
+                    wsm[((c >> 1) * (KS * KS) + t) * 2 + (c & 1)] = v[u];
+                }
+            }
+        }
+    }
     pdl_trigger();
     __syncthreads();
     pdl_wait();
@@ -124,13 +147,6 @@ dwconv_stream2_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* _
     const int row_bytes = sp.IW * sp.CB * 2;
     const int n_cons = n_cons_warps * 32;
 
-    // taps of this channel block, staged once: [channel pair][tap][2] so that a thread's taps are base + immediate
-    for (int i = ct; i < KS * KS * sp.CB; i += n_cons) {
-        const int c = i % sp.CB, t = i / sp.CB;
-        wsm[((c >> 1) * (KS * KS) + t) * 2 + (c & 1)] = __ldg(w + t * C + cblk * sp.CB + c);
-    }
-    __syncwarp();
-    asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
     const uint32_t wq = dw2_u32(wsm + q * (KS * KS) * 2);
     const float2 bv = __ldg(reinterpret_cast<const float2*>(bias + cblk * sp.CB + (active ? q : 0) * 2));
     const uint32_t stage0 = dw2_u32(stages) + (uint32_t)((2 * cb * TW * sp.CB + q * 2) * 2);
