@@ -353,6 +353,13 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
     if (stride != 1 || (k != 3 && k != 5) || C % 8 != 0 || H < 4) return false;
     DwStream whole{};
     const bool whole_ok = dws_plan_strips(W, C, k, 1, false, &whole);
+    if (const char* f = getenv("DN_DWS_NSTRIP")) {            // measurement aid: force the strip count on wide maps
+        DwStream cand{};
+        if (W >= 64 && atoi(f) > 1 && dws_plan_strips(W, C, k, atoi(f), true, &cand)) {
+            *sp = cand;
+            return true;
+        }
+    }
     if (W >= 64 && dn_dw_strips() && !(whole_ok && whole.threads <= 160)) {
         DwStream pick{};
         int pick_thr = 0;
@@ -360,7 +367,9 @@ bool dw_stream_plan(int H, int W, int C, int k, int stride, DwStream* sp) {
             DwStream cand{};
             if (!dws_plan_strips(W, C, k, nstrip, true, &cand)) continue;
             const int thr = (cand.CB / ((k == 3) ? dws_ch<3>() : dws_ch<5>())) * cand.ncb;
-            if (thr > pick_thr) pick = cand, pick_thr = thr;
+            // more consumer threads first; at equal threads the wider channel block (256 x 256 x 32: two strips of 16 channels
+            // 0.955 ms, four strips of 32 channels 0.816 ms, both 128 consumers)
+            if (thr > pick_thr || (thr == pick_thr && cand.CB > pick.CB)) pick = cand, pick_thr = thr;
         }
         if (pick_thr >= 64) {
             *sp = pick;
