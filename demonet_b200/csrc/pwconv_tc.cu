@@ -180,11 +180,11 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         uint32_t lt = 0, stores = 0, sit = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const uint32_t buf = lt & 1u;
-            const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
-            const int m = m0 + row;
-            if constexpr (SCALE_A) {
+        // SCALE_A: rescale the A tiles of output tile `tile_s` (see the kernel comment).  Software-pipelined one tile ahead
+        // of the epilogue: the warps rescale tile i + 1 BEFORE they wait for the accumulator of tile i, so the MMAs of
+        // tile i + 1 (and the global loads of its scales) run under the epilogue of tile i instead of in front of it.
+        auto scale_tile = [&](int tile_s) {
+            const int m0 = (tile_s / n_tiles) * TC_BLOCK_M;
                 // ---- A-operand scaling.  A stage holds 128 rows of 128 bytes (SWIZZLE_128B: the 16-byte chunk at position
                 // p of row r carries the k-chunk p ^ (r & 7)).  Warp w owns rows 16 w .. 16 w + 15; one warp instruction
                 // covers 4 rows x 8 chunks = 512 contiguous bytes (conflict-free), four instructions per stage.
@@ -248,6 +248,16 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->scaled[s]);
                 }
+        };
+        if constexpr (SCALE_A) {
+            if ((int)blockIdx.x < num_tiles) scale_tile((int)blockIdx.x);
+        }
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1u;
+            const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+            const int m = m0 + row;
+            if constexpr (SCALE_A) {
+                if (tile + (int)gridDim.x < num_tiles) scale_tile(tile + (int)gridDim.x);
             }
             const int n_valid = min(block_n, N - n0);
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
