@@ -1,6 +1,6 @@
 """Experiment: more than two batches in flight (n engines x two slots each, called round-robin)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import demonet_b200
 from demonet_b200 import dist as ddist, seeded as weights
