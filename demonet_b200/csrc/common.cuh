@@ -196,6 +196,27 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);          // errors surface in DN_CHECK_LAUNCH
 }
 
+// the same with the grid cut into thread-block clusters of `cluster_x` consecutive CTAs (grid.x must be a multiple of it)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, unsigned cluster_x,
+                               Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = cluster_x;
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);          // errors surface in DN_CHECK_LAUNCH
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -51,6 +51,7 @@ struct dn_engine {
     int n_se = 0;
     std::vector<CUtensorMap> tmap_a, tmap_w, tmap_y;       // per op (PW only)
     std::vector<char> has_tmap_y;
+    std::vector<char> pw_pair;                             // per op (PW only): the weight map was built for the GEMM's pair mode
     std::vector<CUtensorMap> tmap_dw;               // per op (DW only; PWDW: the input window map)
     std::vector<DwTiling> dw_tiling;
     std::vector<DwStream> dw_stream;
@@ -361,6 +362,7 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
         e->tmap_w.resize(e->ops.size());
         e->tmap_y.resize(e->ops.size());
         e->has_tmap_y.assign(e->ops.size(), 0);
+        e->pw_pair.assign(e->ops.size(), 0);
         for (size_t i = 0; i < e->ops.size(); ++i) {
             const dn_op& o = e->ops[i];
             if (o.kind == DN_OP_DWPW) {
@@ -376,13 +378,14 @@ extern "C" int dn_engine_load_weights(dn_engine* e, const void* blob_host, size_
                 continue;
             }
             if (o.kind != DN_OP_PW) continue;
-            int bn, nt, st, cols;
+            int bn, nt, st, cols, pair;
             size_t smem;
             const long long m_max = (long long)e->max_batch * o.h_in * o.w_in;
-            pwconv_tc_plan(m_max, o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem);
+            pwconv_tc_plan(m_max, o.c_in, o.c_out, &bn, &nt, &st, &cols, &smem, nullptr, &pair);
             int rc = make_tmap_h16_2d(&e->tmap_a[i], buf_ptr(e, o.in_buf), m_max, o.c_in, 128, 64);
             if (rc) return rc;
-            rc = make_tmap_h16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, bn, 64);
+            rc = make_tmap_h16_2d(&e->tmap_w[i], e->weights + o.w_off, o.c_out, o.c_in, pair ? bn / 2 : bn, 64);
+            e->pw_pair[i] = (char)pair;
             if (rc) return rc;
             // dense bf16 outputs without a residual are written by TMA (box 32 rows x 32 columns)
             if (!o.out_fp32 && o.res_buf == DN_BUF_NONE && o.out_batch_stride == 0 && o.out_row_stride == 0 &&
@@ -466,7 +469,7 @@ static int enqueue_op(dn_engine* e, size_t i, const float* images, int B, cudaSt
                 const int M = B * hw;
                 if (e->desc.gemm_impl == 0)
                     rc = pwconv_tc_launch(e->tmap_a[i], e->tmap_w[i], e->has_tmap_y[i] ? &e->tmap_y[i] : nullptr, ep, M,
-                                          (long long)e->max_batch * hw, o.c_in, o.c_out, s);
+                                          (long long)e->max_batch * hw, o.c_in, o.c_out, s, e->pw_pair[i]);
                 else
                     rc = pwconv_simt(buf_ptr(e, o.in_buf), W + o.w_off, ep, M, o.c_in, o.c_out, s);
                 break;

@@ -44,10 +44,13 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
 int make_tmap_h16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols);
 // m_plan: the row count the tile shape is planned for (the engine passes its max-batch M so that the weight tensor
 // map built at load time and every later launch agree)
+// pair: the layer runs as clusters of two CTAs that share every weight k-block by TMA multicast (pwconv_tc.cu, PAIR mode);
+// the weight tensor map's box is then block_n / 2 rows
 void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes,
-                    int* w_stationary = nullptr);
+                    int* w_stationary = nullptr, int* pair = nullptr);
+// pair_planned: the `pair` answer of the plan the weight tensor map was built with (-1: plan again)
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
-                     int N, cudaStream_t stream);
+                     int N, cudaStream_t stream, int pair_planned = -1);
 
 // fused pointwise-expand -> depthwise (pwdw_fused.cu)
 bool pwdw_fused_supported(int H, int W, int K, int N, int ksize, int stride);

@@ -75,7 +75,7 @@ template <int ACT, bool TMA_STORE, bool SCALE_A>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
-                 int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols, int w_stat) {
+                 int M, int K, int N, int block_n, int n_tiles, int num_tiles, int num_stages, int tmem_cols, int w_stat, int pair) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // per epilogue warp: 32 rows x 32 fp32 (+pad) for the staged stores, or a 32 x 64 bf16 SWIZZLE_128B tile
     // for the TMA store
@@ -104,7 +104,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (TMA_STORE) prefetch_tmap(&tmap_y);
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
+            mbar_init(&bars->empty[s], pair ? 2 : 1);                   // pair mode: both CTAs' MMAs release a stage
             mbar_init(&bars->scaled[s], TC_SCALE_WARPS);            // one arrival per scaler warp (SCALE_A only)
         }
         for (int b = 0; b < 2; ++b) {
@@ -120,6 +120,18 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // PAIR mode (launched as clusters of two CTAs; K > 128 layers, whose weight tile is re-fetched with every output tile
+    // and, with the A tile, makes the L2 -> shared-memory operand stream the bound of the kernel): the two CTAs of a
+    // cluster work on two M tiles of the SAME N tile in lockstep, each loads HALF of every weight k-block and multicasts
+    // it into both CTAs' stage (one L2 read serves two SMs), and a stage is released by both CTAs' MMAs (multicast commit
+    // on both `empty` barriers).  `num_tiles` then counts pair tiles: (pairs of M tiles) x N tiles.
+    const uint32_t rank = pair ? cluster_ctarank() : 0u;
+    if (pair) cluster_sync_all();                     // the peer's barriers are initialised before anything lands on them
+    const int t_first = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m0 = [&](int tile) {
+        return (pair ? (tile / n_tiles) * 2 + (int)rank : tile / n_tiles) * TC_BLOCK_M;
+    };
     pdl_wait();                 // descriptors prefetched, barriers and TMEM set up while the previous kernel drains
 
     if (warp == 0) {
@@ -133,14 +145,17 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     tma_load_2d(smem_w + kb * w_stage_bytes, &tmap_w, &bars->w_full, kb * TC_BLOCK_K, n0);
             }
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+            for (int tile = t_first; tile < num_tiles; tile += t_step) {
+                const int m0 = tile_m0(tile), n0 = (tile % n_tiles) * block_n;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                     const int s = it % num_stages;
                     mbar_wait_producer(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
                     mbar_expect_tx(&bars->full[s], stage_bytes);
                     tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
-                    if (!w_stat) tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
+                    if (pair)           // my half of the weight k-block (tmap_w's box is block_n / 2 rows) into both CTAs
+                        tma_load_2d_multicast(smem_w + s * w_stage_bytes + rank * (uint32_t)(w_stage_bytes >> 1), &tmap_w, &bars->full[s],
+                                              kb * TC_BLOCK_K, n0 + (int)rank * (block_n >> 1), (uint16_t)3);
+                    else if (!w_stat) tma_load_2d(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K, n0);
                 }
             }
         }
@@ -149,7 +164,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t idesc = make_idesc(TC_BLOCK_M, block_n);
         uint32_t it = 0, lt = 0;
         if (w_stat) mbar_wait(&bars->w_full, 0u);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = t_first; tile < num_tiles; tile += t_step, ++lt) {
             const uint32_t buf = lt & 1u;
             mbar_wait(&bars->tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
             tcgen05_fence_after();
@@ -167,7 +182,9 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4) units
                         umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&bars->empty[s]);                       // frees this smem stage when the MMAs retire
+                    // frees this smem stage when the MMAs retire (pair mode: in both CTAs, each of which wrote half of it)
+                    if (pair) umma_commit_multicast(&bars->empty[s], (uint16_t)3);
+                    else umma_commit(&bars->empty[s]);
                     if (kb == num_k_blocks - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete
                 }
                 __syncwarp();
@@ -184,7 +201,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // of the epilogue: the warps rescale tile i + 1 BEFORE they wait for the accumulator of tile i, so the MMAs of
         // tile i + 1 (and the global loads of its scales) run under the epilogue of tile i instead of in front of it.
         auto scale_tile = [&](int tile_s) {
-            const int m0 = (tile_s / n_tiles) * TC_BLOCK_M;
+            const int m0 = tile_m0(tile_s);
                 // ---- A-operand scaling.  A stage holds 128 rows of 128 bytes (SWIZZLE_128B: the 16-byte chunk at position
                 // p of row r carries the k-chunk p ^ (r & 7)).  Warp w owns rows 16 w .. 16 w + 15; one warp instruction
                 // covers 4 rows x 8 chunks = 512 contiguous bytes (conflict-free), four instructions per stage.
@@ -250,14 +267,14 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
         };
         if constexpr (SCALE_A) {
-            if ((int)blockIdx.x < num_tiles) scale_tile((int)blockIdx.x);
+            if (t_first < num_tiles) scale_tile(t_first);
         }
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = t_first; tile < num_tiles; tile += t_step, ++lt) {
             const uint32_t buf = lt & 1u;
-            const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+            const int m0 = tile_m0(tile), n0 = (tile % n_tiles) * block_n;
             const int m = m0 + row;
             if constexpr (SCALE_A) {
-                if (tile + (int)gridDim.x < num_tiles) scale_tile(tile + (int)gridDim.x);
+                if (tile + t_step < num_tiles) scale_tile(tile + t_step);
             }
             const int n_valid = min(block_n, N - n0);
             mbar_wait(&bars->tmem_full[buf], (lt >> 1) & 1u);
@@ -403,6 +420,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();                     // neither CTA leaves while the other may still signal its barriers
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
@@ -455,7 +473,7 @@ static size_t smem_cap(int n) {
 }
 
 void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes,
-                    int* w_stationary) {
+                    int* w_stationary, int* pair) {
     static const int bn_max = [] {                     // measurement aid: DN_PW_BN_MAX=64|128 caps the tile width
         const char* v = getenv("DN_PW_BN_MAX");
         const int x = v ? atoi(v) : 256;
@@ -512,16 +530,31 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     *stages = st;
     *tmem_cols = cols;
     *smem_bytes = need(st);
+    // PAIR mode (DN_PW_PAIR=1, read per call; OFF by default): layers whose weight tile travels through the ring (K > 128) and
+    // is wide enough to matter, on maps with at least two M tiles per SM.  Measured (scripts/experiments/exp_gemm_pair.py,
+    // B = 256 shapes, L2 flushed): 672 -> 546 fp32 0.1176 -> 0.1137 ms, 200 -> 80 + residual 0.0337 -> 0.0317, 240 -> 80 @ 40 x 40
+    // 0.0635 -> 0.0602, but 672 -> 112 0.0440 -> 0.0460 and 480 -> 112 0.0357 -> 0.0379: halving the L2 reads of the weight
+    // tile changes next to nothing, i.e. these GEMMs are NOT bound by the L2 -> SM operand stream but by the SM's own
+    // shared-memory bandwidth (every UMMA 128 x 192 x 16 reads 10 KB of operands in 96 cycles while TMA writes the next 10 KB
+    // and the epilogue stages 196 KB per tile: ~1 MB per tile against 128 B / cycle).  Multicast does not touch that;
+    // cta_group::2, where each CTA reads half of the B operand, would.
+    const char* pv = getenv("DN_PW_PAIR");
+    const bool pair_on = pv && atoi(pv) == 1;
+    if (pair) *pair = (pair_on && !ws && bn >= 64 && m_tiles >= 2 * (long long)sm_count()) ? 1 : 0;
 }
 
 template <int ACT, bool TMA_STORE, bool SCALE_A = false>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
                           int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
-                          cudaStream_t stream, int w_stat = 0) {
+                          cudaStream_t stream, int w_stat = 0, int pair = 0) {
     static SmemOptIn optin;
     DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, smem_cap(1)));
-    launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt, tiles,
-               st, cols, w_stat);
+    if (pair)
+        launch_pdl_cluster(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, grid, TC_THREADS, smem_req, stream, 2u, ta, tw, ty, ep, M, K, N,
+                           bn, nt, tiles, st, cols, w_stat, pair);
+    else
+        launch_pdl(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, grid, TC_THREADS, smem_req, stream, ta, tw, ty, ep, M, K, N, bn, nt,
+                   tiles, st, cols, w_stat, pair);
     DN_CHECK_LAUNCH();
     return DN_OK;
 }
@@ -529,10 +562,11 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CU
 // ty: tensor map of the bf16 output ([rows, N], box 32 x 64) or nullptr.  The TMA-store epilogue is used when
 // ty is given and the layer has neither a residual nor fp32 / strided output.
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
-                     int N, cudaStream_t stream) {
-    int bn, nt, st, cols, ws;
+                     int N, cudaStream_t stream, int pair_planned) {
+    int bn, nt, st, cols, ws, pair;
     size_t smem;
-    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws);
+    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair);
+    if (pair_planned >= 0) pair = pair_planned;       // the mode `tw` was built for (its box is block_n / 2 rows in pair mode)
     // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
     // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
     // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).
@@ -544,10 +578,14 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
             break;
         }
     const size_t smem_req = smem_cap(per_sm);
-    const long long tiles = (long long)ceil_div(M, TC_BLOCK_M) * nt;
+    long long tiles = (long long)ceil_div(M, TC_BLOCK_M) * nt;
     DN_REQUIRE(tiles < (1ll << 31), DN_ERR_UNSUPPORTED, "GEMM too large");
     long long grid = (long long)sm_count() * per_sm;
-    if (grid > tiles) grid = tiles;
+    if (pair) {                  // pair tiles: two M tiles of one N tile per cluster step; an even grid of whole clusters
+        tiles = (long long)ceil_div(ceil_div(M, TC_BLOCK_M), 2) * nt;
+        grid &= ~1ll;
+        if (grid > 2 * tiles) grid = 2 * tiles;
+    } else if (grid > tiles) grid = tiles;
     if (ws) {                    // a CTA must keep meeting the same weight tile: tile % nt == blockIdx.x % nt
         grid = grid / nt * nt;
         if (grid < nt) ws = 0, grid = std::min<long long>((long long)sm_count() * per_sm, tiles);
@@ -558,15 +596,15 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
         DN_REQUIRE(ep.act == DN_ACT_NONE && ep.a_scale_c > 0 && ep.a_scale_c % 8 == 0 && K % ep.a_scale_c == 0, DN_ERR_UNSUPPORTED,
                    "A-operand scaling needs a linear GEMM whose K is a multiple of the scale width");
         return tma_store ? launch_variant<DN_ACT_NONE, true, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
-                                                                   (unsigned)grid, smem_req, stream, ws)
+                                                                   (unsigned)grid, smem_req, stream, ws, pair)
                          : launch_variant<DN_ACT_NONE, false, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols,
-                                                                    (unsigned)grid, smem_req, stream, ws);
+                                                                    (unsigned)grid, smem_req, stream, ws, pair);
     }
 #define DN_PW_CASE(ACT)                                                                                                   \
     return tma_store ? launch_variant<ACT, true>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid,  \
-                                                 smem_req, stream, ws)                                                    \
+                                                 smem_req, stream, ws, pair)                                              \
                      : launch_variant<ACT, false>(ta, tw, tyr, ep, M, K, N, bn, nt, (int)tiles, st, cols, (unsigned)grid, \
-                                                  smem_req, stream, ws)
+                                                  smem_req, stream, ws, pair)
     switch (ep.act) {
         case DN_ACT_RELU: DN_PW_CASE(DN_ACT_RELU);
         case DN_ACT_RELU6: DN_PW_CASE(DN_ACT_RELU6);
@@ -577,13 +615,13 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
 }
 
 int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, int N, cudaStream_t stream) {
-    int bn, nt, st, cols;
+    int bn, nt, st, cols, pair;
     size_t smem;
-    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem, nullptr);
+    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem, nullptr, &pair);
     CUtensorMap ta, tw, ty;
     int rc = make_tmap_h16_2d(&ta, x, M, K, TC_BLOCK_M, TC_BLOCK_K);
     if (rc) return rc;
-    rc = make_tmap_h16_2d(&tw, w, N, K, bn, TC_BLOCK_K);
+    rc = make_tmap_h16_2d(&tw, w, N, K, pair ? bn / 2 : bn, TC_BLOCK_K);
     if (rc) return rc;
     const bool dense = !ep.out_fp32 && !ep.residual && N % 8 == 0 && ep.out_row_stride == N &&
                        (ep.hw >= M || ep.out_batch_stride == (long long)ep.hw * N);
@@ -591,7 +629,7 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
         rc = make_tmap_h16_2d(&ty, ep.y, M, N, 32, 32);
         if (rc) return rc;
     }
-    return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, M, K, N, stream);
+    return pwconv_tc_launch(ta, tw, dense ? &ty : nullptr, ep, M, M, K, N, stream, pair);
 }
 
 }  // namespace dn
