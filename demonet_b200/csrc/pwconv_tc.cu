@@ -31,6 +31,7 @@ constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_RING_MAX = 8;                  // barrier slots; the cta_group::2 form (half-size weight stages) rings deeper
 constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SCALE_WARPS = TC_EPI_WARPS;    // SCALE_A variant: the epilogue warps also rescale the A tiles in shared memory
@@ -40,11 +41,11 @@ constexpr int TC_STAGE_BYTES = 5120;                               // >= 32*36*4
 constexpr int TC_STATIC_SMEM = TC_EPI_WARPS * TC_STAGE_BYTES + 1024;      // epilogue staging (+ alignment)
 
 struct __align__(8) TcBarriers {
-    uint64_t full[TC_MAX_STAGES];        // TMA -> MMA: k-block landed in smem
-    uint64_t empty[TC_MAX_STAGES];       // MMA -> TMA: smem stage consumed
+    uint64_t full[TC_RING_MAX];        // TMA -> MMA: k-block landed in smem
+    uint64_t empty[TC_RING_MAX];       // MMA -> TMA: smem stage consumed
     uint64_t tmem_full[2];               // MMA -> epilogue: accumulator buffer complete
     uint64_t tmem_empty[2];              // epilogue -> MMA: accumulator buffer drained
-    uint64_t scaled[TC_MAX_STAGES];      // SCALE_A: scaler warps -> MMA: the A tile of the stage has been rescaled
+    uint64_t scaled[TC_RING_MAX];      // SCALE_A: scaler warps -> MMA: the A tile of the stage has been rescaled
     uint64_t w_full;                     // W-stationary mode: the CTA's weight tile (all k-blocks) has landed
     uint32_t tmem_base;
     uint32_t pad;
@@ -71,7 +72,9 @@ __device__ __forceinline__ float act_fn(float v) {
 // to HBM in the unfused path -- between the TMA completion and the MMA issue.  The scaled tensor never exists in HBM:
 // one read and one write of every SE tensor disappear.  (The K loop of tile i + 1 then starts behind the epilogue of
 // tile i; these GEMMs have long K and narrow N, and the other CTAs of the SM fill the gap.)
-template <int ACT, bool TMA_STORE, bool SCALE_A>
+// CG2: the cta_group::2 form of PAIR mode (pair == 2).  A kernel that contains cta_group::2 instructions can only be launched
+// as clusters ("cluster misconfiguration" otherwise), so that code lives in its own instantiations.
+template <int ACT, bool TMA_STORE, bool SCALE_A, bool CG2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_y, PwEpilogue ep,
@@ -82,7 +85,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __shared__ __align__(1024) uint8_t s_stage_raw[TC_EPI_WARPS][TC_STAGE_BYTES];
     // carve: [stages x A tile][stages x W tile][barriers]; tiles must be 1024-B aligned for SWIZZLE_128B
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic keeps the shared address space
-    const int w_stage_bytes = block_n * TC_BLOCK_K * 2;
+    const int w_stage_bytes = (CG2 ? block_n >> 1 : block_n) * TC_BLOCK_K * 2;      // cta_group::2: a CTA only holds its half of B
     uint8_t* smem_a = smem;
     // W-stationary mode (w_stat): the grid is a multiple of n_tiles, so a CTA meets ONE weight tile for its whole life; all
     // its k-blocks are loaded once into their own buffers and the ring only carries A.  Otherwise the (L2-resident)
@@ -104,17 +107,20 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (TMA_STORE) prefetch_tmap(&tmap_y);
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], pair ? 2 : 1);                   // pair mode: both CTAs' MMAs release a stage
+            mbar_init(&bars->empty[s], pair == 1 ? 2 : 1);              // multicast pair mode: both CTAs' MMAs release a stage
             mbar_init(&bars->scaled[s], TC_SCALE_WARPS);            // one arrival per scaler warp (SCALE_A only)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars->tmem_full[b], 1);
-            mbar_init(&bars->tmem_empty[b], TC_EPI_WARPS);          // one arrival per epilogue warp
+            mbar_init(&bars->tmem_empty[b], CG2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);      // one arrival per epilogue warp (of both CTAs)
         }
         mbar_init(&bars->w_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
+    if (warp == 1) {
+        if constexpr (CG2) tmem_alloc_pair(&bars->tmem_base, (uint32_t)tmem_cols);
+        else tmem_alloc(&bars->tmem_base, (uint32_t)tmem_cols);
+    }
     pdl_trigger();
     tcgen05_fence_before();
     __syncthreads();
@@ -150,6 +156,15 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                     const int s = it % num_stages;
                     mbar_wait_producer(&bars->empty[s], ((it / num_stages) & 1u) ^ 1u);
+                    if constexpr (CG2) {
+                        // cta_group::2: my A rows and my HALF of the weight k-block stay in my shared memory; the bytes of
+                        // both CTAs complete on the leader's barrier, which the leader arms for both
+                        if (rank == 0) mbar_expect_tx(&bars->full[s], 2u * (uint32_t)(TC_A_STAGE_BYTES + w_stage_bytes));
+                        tma_load_2d_pair(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
+                        tma_load_2d_pair(smem_w + s * w_stage_bytes, &tmap_w, &bars->full[s], kb * TC_BLOCK_K,
+                                         n0 + (int)rank * (block_n >> 1));
+                        continue;
+                    }
                     mbar_expect_tx(&bars->full[s], stage_bytes);
                     tma_load_2d(smem_a + s * TC_A_STAGE_BYTES, &tmap_a, &bars->full[s], kb * TC_BLOCK_K, m0);
                     if (pair)           // my half of the weight k-block (tmap_w's box is block_n / 2 rows) into both CTAs
@@ -159,9 +174,9 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        const uint32_t idesc = make_idesc(TC_BLOCK_M, block_n);
+    } else if (warp == 1 && !(CG2 && rank != 0)) {
+        // ===== MMA issuer (cta_group::2: the leader CTA issues 256 x block_n UMMAs for the pair) =====
+        const uint32_t idesc = make_idesc(CG2 ? 2 * TC_BLOCK_M : TC_BLOCK_M, block_n);
         uint32_t it = 0, lt = 0;
         if (w_stat) mbar_wait(&bars->w_full, 0u);
         for (int tile = t_first; tile < num_tiles; tile += t_step, ++lt) {
@@ -180,17 +195,22 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int ksteps = k_left >= TC_BLOCK_K ? TC_BLOCK_K / TC_UMMA_K : (k_left + TC_UMMA_K - 1) / TC_UMMA_K;
                     for (int k = 0; k < ksteps; ++k) {
                         // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4) units
-                        umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CG2) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    // frees this smem stage when the MMAs retire (pair mode: in both CTAs, each of which wrote half of it)
-                    if (pair) umma_commit_multicast(&bars->empty[s], (uint16_t)3);
+                    // frees this smem stage when the MMAs retire (pair modes: in both CTAs)
+                    if constexpr (CG2) umma_commit_pair(&bars->empty[s], (uint16_t)3);
+                    else if (pair) umma_commit_multicast(&bars->empty[s], (uint16_t)3);
                     else umma_commit(&bars->empty[s]);
-                    if (kb == num_k_blocks - 1) umma_commit(&bars->tmem_full[buf]);   // accumulator complete
+                    if (kb == num_k_blocks - 1) {                              // accumulator complete (cta_group::2: in both CTAs)
+                        if constexpr (CG2) umma_commit_pair(&bars->tmem_full[buf], (uint16_t)3);
+                        else umma_commit(&bars->tmem_full[buf]);
+                    }
                 }
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column chunks interleaved between the
         // two warps that share a quarter =====
         const int quarter = warp & 3;
@@ -414,7 +434,10 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // all tcgen05.ld of this warp have completed (wait::ld above): hand the buffer back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[buf]);
+            if (lane == 0) {
+                if constexpr (CG2) mbar_arrive_leader(&bars->tmem_empty[buf]);
+                else mbar_arrive(&bars->tmem_empty[buf]);
+            }
         }
         if (TMA_STORE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -423,7 +446,8 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (pair) cluster_sync_all();                     // neither CTA leaves while the other may still signal its barriers
     if (warp == 1) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+        if constexpr (CG2) tmem_dealloc_pair(tmem_base, (uint32_t)tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }
 }
 
@@ -505,8 +529,19 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     const bool ws = wstat_on && kb <= 2;
     if (w_stationary) *w_stationary = ws ? 1 : 0;
     if (ws) st = st_max = TC_MAX_STAGES;                   // A-only stages: the ring can run several tiles ahead
+    // PAIR modes (DN_PW_PAIR=1|2, read per call; OFF by default), for layers whose weight tile travels through the ring
+    // (K > 128) and is wide enough to matter, on maps with at least two M tiles per SM:
+    //   1  clusters of two CTAs, every weight k-block loaded half by each CTA and TMA-multicast into both ring stages
+    //   2  cta_group::2: the pair's leader issues 256 x block_n UMMAs, each CTA keeps only ITS half of B in shared memory
+    //      (half-size weight stages -> a deeper ring in the same shared memory)
+    const char* pv = getenv("DN_PW_PAIR");
+    const int pair_env = pv ? atoi(pv) : 0;
+    const int pm = ((pair_env == 1 || pair_env == 2) && !ws && bn >= 64 && m_tiles >= 2 * (long long)sm_count()) ? pair_env : 0;
+    if (pair) *pair = pm;
+    const size_t w_stage = (size_t)(pm == 2 ? bn / 2 : bn) * TC_BLOCK_K * 2;
+    if (pm == 2) st = st_max = TC_RING_MAX;
     auto need = [&](int stg) {
-        const size_t ring = ws ? (size_t)stg * TC_A_STAGE_BYTES + w_total : (size_t)stg * (TC_A_STAGE_BYTES + (size_t)bn * TC_BLOCK_K * 2);
+        const size_t ring = ws ? (size_t)stg * TC_A_STAGE_BYTES + w_total : (size_t)stg * (TC_A_STAGE_BYTES + w_stage);
         return 1024 + ring + sizeof(TcBarriers) + ((size_t)nt * bn + 32) * 4;
     };
     while (st > 2 && need(st) > smem_cap(1)) --st;
@@ -522,7 +557,7 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
         for (int n = 4; n >= 2; --n)
             if (n * cols <= 512 && need(2) <= smem_cap(n)) {
                 int s2 = 2;
-                while (s2 < TC_MAX_STAGES && s2 < st_max && need(s2 + 1) <= smem_cap(n)) ++s2;
+                while (s2 < (pm == 2 ? TC_RING_MAX : TC_MAX_STAGES) && s2 < st_max && need(s2 + 1) <= smem_cap(n)) ++s2;
                 st = s2;
                 break;
             }
@@ -530,23 +565,22 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     *stages = st;
     *tmem_cols = cols;
     *smem_bytes = need(st);
-    // PAIR mode (DN_PW_PAIR=1, read per call; OFF by default): layers whose weight tile travels through the ring (K > 128) and
-    // is wide enough to matter, on maps with at least two M tiles per SM.  Measured (scripts/experiments/exp_gemm_pair.py,
-    // B = 256 shapes, L2 flushed): 672 -> 546 fp32 0.1176 -> 0.1137 ms, 200 -> 80 + residual 0.0337 -> 0.0317, 240 -> 80 @ 40 x 40
-    // 0.0635 -> 0.0602, but 672 -> 112 0.0440 -> 0.0460 and 480 -> 112 0.0357 -> 0.0379: halving the L2 reads of the weight
-    // tile changes next to nothing, i.e. these GEMMs are NOT bound by the L2 -> SM operand stream but by the SM's own
-    // shared-memory bandwidth (every UMMA 128 x 192 x 16 reads 10 KB of operands in 96 cycles while TMA writes the next 10 KB
-    // and the epilogue stages 196 KB per tile: ~1 MB per tile against 128 B / cycle).  Multicast does not touch that;
-    // cta_group::2, where each CTA reads half of the B operand, would.
-    const char* pv = getenv("DN_PW_PAIR");
-    const bool pair_on = pv && atoi(pv) == 1;
-    if (pair) *pair = (pair_on && !ws && bn >= 64 && m_tiles >= 2 * (long long)sm_count()) ? 1 : 0;
 }
 
 template <int ACT, bool TMA_STORE, bool SCALE_A = false>
 static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& ty, const PwEpilogue& ep, int M,
                           int K, int N, int bn, int nt, int tiles, int st, int cols, unsigned grid, size_t smem_req,
                           cudaStream_t stream, int w_stat = 0, int pair = 0) {
+    if constexpr (!SCALE_A) {
+        if (pair == 2) {
+            static SmemOptIn optin2;
+            DN_CHECK_CUDA(optin2.ensure(pwconv_tc_kernel<ACT, TMA_STORE, false, true>, smem_cap(1)));
+            launch_pdl_cluster(pwconv_tc_kernel<ACT, TMA_STORE, false, true>, grid, TC_THREADS, smem_req, stream, 2u, ta, tw, ty, ep, M,
+                               K, N, bn, nt, tiles, st, cols, w_stat, pair);
+            DN_CHECK_LAUNCH();
+            return DN_OK;
+        }
+    }
     static SmemOptIn optin;
     DN_CHECK_CUDA(optin.ensure(pwconv_tc_kernel<ACT, TMA_STORE, SCALE_A>, smem_cap(1)));
     if (pair)
@@ -567,6 +601,7 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
     size_t smem;
     pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair);
     if (pair_planned >= 0) pair = pair_planned;       // the mode `tw` was built for (its box is block_n / 2 rows in pair mode)
+    if (pair == 2 && ep.a_scale) pair = 1;            // A scaling is per CTA: the SE GEMMs take the multicast form (same weight map)
     // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
     // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
     // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).

@@ -90,17 +90,20 @@ PW_CASES = [(25600, 16, 16), (25600, 16, 64), (6400, 64, 24), (6400, 24, 72), (1
 
 @pytest.mark.parametrize("M,K,N,res,fp32", [(40960, 672, 546, False, True), (38017, 200, 80, True, False), (40960, 480, 112, False, False),
                                             (51200, 240, 1000, False, False)])
-def test_pwconv_pair_mode_is_bit_identical(M, K, N, res, fp32, dt, monkeypatch):
-    """PAIR mode (DN_PW_PAIR=1: clusters of two CTAs, each loads half of every weight k-block and multicasts it into both CTAs'
-    ring stage, stages released by both CTAs' MMAs) computes exactly what the single-CTA kernel computes: same UMMAs on the same
-    operands.  Odd M-tile counts (a cluster whose second CTA has no rows), residual / fp32 / multi-N-tile outputs."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pwconv_pair_mode_is_bit_identical(M, K, N, res, fp32, mode, dt, monkeypatch):
+    """PAIR modes compute exactly what the single-CTA kernel computes (same products, same accumulation order along K).
+    DN_PW_PAIR=1: clusters of two CTAs, each loads half of every weight k-block and multicasts it into both CTAs' ring stage,
+    stages released by both CTAs' MMAs.  DN_PW_PAIR=2: tcgen05 cta_group::2 -- the pair's leader issues 256 x N UMMAs, each CTA
+    keeps its 128 A rows and its half of B, both CTAs' loads complete on the leader's barrier, commits are multicast.
+    Odd M-tile counts (a cluster whose second CTA has no rows), residual / fp32 / multi-N-tile outputs."""
     g = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g).to(dt).cuda()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dt).cuda()
     b = torch.randn(N, generator=g).cuda()
     r = torch.randn(M, N, generator=g).to(dt).cuda() if res else None
     y0 = ops.pwconv(x, w, b, "relu6" if not res and not fp32 else "none", r, fp32)
-    monkeypatch.setenv("DN_PW_PAIR", "1")
+    monkeypatch.setenv("DN_PW_PAIR", str(mode))
     y1 = ops.pwconv(x, w, b, "relu6" if not res and not fp32 else "none", r, fp32)
     monkeypatch.delenv("DN_PW_PAIR")
     assert torch.equal(y0, y1)
