@@ -47,7 +47,7 @@ int make_tmap_h16_2d(CUtensorMap* map, const void* base, long long rows, long lo
 // pair: the layer runs as clusters of two CTAs that share every weight k-block by TMA multicast (pwconv_tc.cu, PAIR mode);
 // the weight tensor map's box is then block_n / 2 rows
 void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes,
-                    int* w_stationary = nullptr, int* pair = nullptr);
+                    int* w_stationary = nullptr, int* pair = nullptr, int pair_force = -1);
 // pair_planned: the `pair` answer of the plan the weight tensor map was built with (-1: plan again)
 int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap* ty, const PwEpilogue& ep, int M, long long m_plan, int K,
                      int N, cudaStream_t stream, int pair_planned = -1);

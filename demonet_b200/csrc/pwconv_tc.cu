@@ -497,7 +497,7 @@ static size_t smem_cap(int n) {
 }
 
 void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, int* stages, int* tmem_cols, size_t* smem_bytes,
-                    int* w_stationary, int* pair) {
+                    int* w_stationary, int* pair, int pair_force) {
     static const int bn_max = [] {                     // measurement aid: DN_PW_BN_MAX=64|128 caps the tile width
         const char* v = getenv("DN_PW_BN_MAX");
         const int x = v ? atoi(v) : 256;
@@ -535,7 +535,7 @@ void pwconv_tc_plan(long long m_plan, int K, int N, int* block_n, int* n_tiles, 
     //   2  cta_group::2: the pair's leader issues 256 x block_n UMMAs, each CTA keeps only ITS half of B in shared memory
     //      (half-size weight stages -> a deeper ring in the same shared memory)
     const char* pv = getenv("DN_PW_PAIR");
-    const int pair_env = pv ? atoi(pv) : 0;
+    const int pair_env = pair_force >= 0 ? pair_force : (pv ? atoi(pv) : 0);      // pair_force: the mode a caller already committed to
     const int pm = ((pair_env == 1 || pair_env == 2) && !ws && bn >= 64 && m_tiles >= 2 * (long long)sm_count()) ? pair_env : 0;
     if (pair) *pair = pm;
     const size_t w_stage = (size_t)(pm == 2 ? bn / 2 : bn) * TC_BLOCK_K * 2;
@@ -599,9 +599,10 @@ int pwconv_tc_launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
                      int N, cudaStream_t stream, int pair_planned) {
     int bn, nt, st, cols, ws, pair;
     size_t smem;
-    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair);
-    if (pair_planned >= 0) pair = pair_planned;       // the mode `tw` was built for (its box is block_n / 2 rows in pair mode)
-    if (pair == 2 && ep.a_scale) pair = 1;            // A scaling is per CTA: the SE GEMMs take the multicast form (same weight map)
+    // pair_planned: the mode `tw` was built for (its box is block_n / 2 rows in the pair modes).  A scaling is per CTA, so the
+    // SE GEMMs take the multicast form where cta_group::2 was asked for (same weight map, but full-size weight stages: plan again)
+    pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair, pair_planned);
+    if (pair == 2 && ep.a_scale) pwconv_tc_plan(m_plan, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair, 1);
     // Resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM).  The dynamic request is
     // padded up to the largest size that still lets `per_sm` CTAs co-reside, so that the hardware cannot place
     // one more (a CTA that cannot get its TMEM columns would spin until a neighbour exits).
