@@ -7,7 +7,7 @@ from demonet_b200 import dist as ddist, seeded as weights
 
 B, S, K, D = 256, 320, 91, 300
 dev = torch.device("cuda:0")
-for n_eng, slots in [(1, 2), (2, 2), (2, 1), (3, 1), (1, 1), (1, 2)]:
+for n_eng, slots in [(1, 4), (2, 3), (2, 4), (3, 4), (1, 4)]:
     engs, ios = [], []
     for _ in range(n_eng):
         m = demonet_b200.ssdlite320_mobilenet_v3_large(num_classes=K, pipeline_slots=slots)
@@ -29,7 +29,7 @@ for n_eng, slots in [(1, 2), (2, 2), (2, 1), (3, 1), (1, 1), (1, 2)]:
     def drain():
         for j in range(n_eng):
             with torch.cuda.stream(streams[j]):
-                if slots == 2:
+                if slots >= 2:
                     engs[j][1].join()
         torch.cuda.synchronize()
 
@@ -45,7 +45,7 @@ for n_eng, slots in [(1, 2), (2, 2), (2, 1), (3, 1), (1, 1), (1, 2)]:
         step(i)
     for j in range(n_eng):
         with torch.cuda.stream(streams[j]):
-            if slots == 2:
+            if slots >= 2:
                 engs[j][1].join()
         torch.cuda.current_stream().wait_stream(streams[j])
     t1.record()
