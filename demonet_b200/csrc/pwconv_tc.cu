@@ -125,7 +125,6 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
     // PAIR mode (launched as clusters of two CTAs; K > 128 layers, whose weight tile is re-fetched with every output tile
     // and, with the A tile, makes the L2 -> shared-memory operand stream the bound of the kernel): the two CTAs of a
     // cluster work on two M tiles of the SAME N tile in lockstep, each loads HALF of every weight k-block and multicasts
@@ -133,6 +132,7 @@ pwconv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // on both `empty` barriers).  `num_tiles` then counts pair tiles: (pairs of M tiles) x N tiles.
     const uint32_t rank = pair ? cluster_ctarank() : 0u;
     if (pair) cluster_sync_all();                     // the peer's barriers are initialised before anything lands on them
+    const uint32_t tmem_base = bars->tmem_base;       // (read behind the cluster barrier: a cta_group::2 allocation is collective)
     const int t_first = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int t_step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     auto tile_m0 = [&](int tile) {
