@@ -660,6 +660,12 @@ def main():
 
         def collect(j, k):
             """batch j (computed on slot k, already joined) -> ring; close the group when it is complete"""
+            if G == 1:
+                # one collective per batch: gather straight from the slot's packed output buffer, no ring copy (the buffer is
+                # rewritten by the forward issued n_slots calls later on the same stream order, i.e. behind this collective)
+                dist.all_gather_into_tensor(gathered, packed_det[k].buffer)
+                tick["gathers"] += 1
+                return
             pos = j % (2 * G)
             ring[pos * nb:(pos + 1) * nb].copy_(packed_det[k].buffer, non_blocking=True)
             if (j + 1) % G == 0:
