@@ -69,6 +69,7 @@ _SIGNATURES = {
     "dn_last_error": (ctypes.c_char_p, []),
     "dn_abi_version": (c_int, []),
     "dn_dwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dn_dwconv_plan_info": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int32)]),
     "dn_pwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int64, c_int64, c_int, c_void_p]),
     "dn_pwdw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

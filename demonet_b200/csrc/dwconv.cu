@@ -260,6 +260,27 @@ extern "C" int dn_dwconv(const void* x, const float* w, const float* bias, void*
     return launch_dw<5, 2, 2>(x, w, bias, y, B, H, W, C, Ho, Wo, act, s);
 }
 
+extern "C" int dn_dwconv_plan_info(int H, int W, int C, int k, int stride, int32_t* out8) {
+    DN_REQUIRE(out8 != nullptr, DN_ERR_INVALID, "NULL argument");
+    DN_REQUIRE(H > 0 && W > 0 && C > 0 && C % 8 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2), DN_ERR_INVALID,
+               "bad depthwise shape");
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    const DwImpl impl = dw_choose(H, W, C, k, stride);
+    out8[0] = (int32_t)impl;
+    DwStream sp{};
+    int tw = 4;
+    if (impl == DW_STREAM) {
+        DN_REQUIRE(dw_stream_plan(H, W, C, k, stride, &sp), DN_ERR_UNSUPPORTED, "no stream plan");
+    } else if (impl == DW_STREAM2) {
+        DN_REQUIRE(dw_stream2_plan(H, W, C, k, &sp, &tw), DN_ERR_UNSUPPORTED, "no stride-2 stream plan");
+    } else {
+        return DN_OK;
+    }
+    out8[1] = sp.CB, out8[2] = sp.ncb, out8[3] = sp.nstrip, out8[4] = tw, out8[5] = sp.threads, out8[6] = sp.nst;
+    out8[7] = (int32_t)sp.smem;
+    return DN_OK;
+}
+
 // Depthwise conv followed by squeeze-excitation of its output (InvertedResidual with use_se, mobilenetv3.py:43-96):
 // when the layer runs on a row-stream kernel (either stride) and the batch is large enough, the stream leaves the SE
 // channel sums in the workspace and the SE pooling pass is skipped (*pooled_out = 1); otherwise dn_dwconv + dn_se_inplace.

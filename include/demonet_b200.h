@@ -51,6 +51,11 @@ int dn_abi_version(void);
  * Ho = (H + 2*(k/2) - k)/stride + 1.  k in {3,5}, stride in {1,2}, C % 8 == 0. */
 int dn_dwconv(const void* x, const float* w, const float* bias, void* y, int B, int H, int W, int C, int k,
               int stride, int act, void* stream);
+/* Host-only: which kernel dn_dwconv runs for a layer shape and how it is tiled (no device work; usable without a GPU).
+ * out8 = { impl (1 direct, 2 TMA tiles, 4 stride-1 row stream, 8 stride-2 row stream), channels per block, column blocks
+ * per CTA, column strips across the width, output columns per thread, threads per CTA, ring stages, dynamic shared
+ * memory bytes }; the last six are 0 for impl 1 / 2. */
+int dn_dwconv_plan_info(int H, int W, int C, int k, int stride, int32_t* out8);
 
 /* Pointwise (1x1) convolution as a GEMM on the tcgen05 tensor cores, with folded BatchNorm / bias,
  * activation and the residual add fused in the epilogue.

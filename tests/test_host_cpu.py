@@ -250,3 +250,45 @@ def test_detector_wrapper_scripts_without_a_gpu():
     scripted = torch.jit.script(custom_ops.ScriptableSSDLite(model))
     g = str(scripted.graph)
     assert g.count("demonet_b200::ssdlite_forward") == 1
+
+
+def _dw_plan(H, W, C, k, s):
+    out = (ctypes.c_int32 * 8)()
+    assert _C.lib().dn_dwconv_plan_info(H, W, C, k, s, out) == 0, _C.lib().dn_last_error()
+    return dict(zip(("impl", "CB", "ncb", "nstrip", "TW", "threads", "stages", "smem"), list(out)))
+
+
+def test_depthwise_row_stream_plans():
+    """Host logic of the depthwise planner (no GPU): invariants of every row-stream plan over a sweep of shapes, and the
+    choices DESIGN.md quotes for the wide maps of V2 @ 512 (column strips) and for the V3 @ 320 layers (whole rows)."""
+    STREAM, STREAM2 = 4, 8
+    for H in (8, 10, 19, 20, 38, 40, 64, 75, 80, 128, 150, 160, 256):
+        for C in (8, 16, 24, 32, 64, 72, 96, 120, 144, 184, 200, 240, 480, 672, 960):
+            for k in (3, 5):
+                for s in (1, 2):
+                    p = _dw_plan(H, H, C, k, s)
+                    if p["impl"] not in (STREAM, STREAM2):
+                        continue
+                    Wo = H if s == 1 else (H + 2 * (k // 2) - k) // 2 + 1
+                    assert C % p["CB"] == 0 and p["CB"] % 8 == 0
+                    assert p["nstrip"] >= 1 and p["ncb"] * p["TW"] * p["nstrip"] >= Wo            # the strips cover the width
+                    assert (p["nstrip"] - 1) * p["ncb"] * p["TW"] < Wo                            # and none of them is empty
+                    staged = p["ncb"] * p["TW"] + k - 1 if s == 1 else 2 * p["ncb"] * p["TW"] + k - 2
+                    assert staged <= 256                                                          # TMA box limit
+                    assert 64 <= p["threads"] <= 288 and p["stages"] >= 2 and 0 < p["smem"] <= 200 * 1024
+                    if p["nstrip"] > 1:
+                        assert Wo >= 64 and p["threads"] <= 160
+    # config 5 (V2 @ 512): the four largest depthwise layers
+    assert _dw_plan(256, 256, 32, 3, 1) | {"smem": 0, "stages": 0} == dict(impl=STREAM, CB=32, ncb=16, nstrip=4, TW=4, threads=160, stages=0, smem=0)
+    p = _dw_plan(256, 256, 96, 3, 2)
+    assert (p["impl"], p["CB"], p["nstrip"]) == (STREAM2, 32, 4)
+    p = _dw_plan(128, 128, 144, 3, 2)
+    assert (p["impl"], p["CB"], p["nstrip"]) == (STREAM2, 48, 4)
+    p = _dw_plan(128, 128, 144, 3, 1)
+    assert (p["impl"], p["CB"], p["nstrip"], p["threads"]) == (STREAM, 16, 1, 160)              # whole rows: more consumers win
+    # config 2 (V3 @ 320): no strips anywhere, three-CTA-per-SM variants except the 184 / 200-channel layers
+    for (H, C, k, s) in [(80, 72, 3, 1), (80, 72, 5, 2), (40, 120, 5, 1), (40, 240, 3, 2), (20, 480, 3, 1), (20, 672, 3, 1),
+                         (20, 672, 5, 2), (10, 480, 5, 1), (10, 480, 3, 1)]:
+        p = _dw_plan(H, H, C, k, s)
+        assert p["impl"] == (STREAM if s == 1 else STREAM2) and p["nstrip"] == 1 and p["threads"] == 160, (H, C, k, s, p)
+    assert _dw_plan(20, 20, 200, 3, 1)["threads"] == 288 and _dw_plan(5, 5, 512, 3, 1)["impl"] == 1
