@@ -72,6 +72,7 @@ _SIGNATURES = {
     "dn_dwconv_plan_info": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int32)]),
     "dn_pwconv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int64, c_int64, c_int, c_void_p]),
+    "dn_pwconv_plan_info": (c_int, [ctypes.c_longlong, c_int, c_int, ctypes.POINTER(c_int32)]),
     "dn_pwdw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_int, c_void_p]),
     "dn_dwpw_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -672,6 +672,21 @@ int pwconv_tc(const void* x, const void* w, const PwEpilogue& ep, int M, int K, 
 
 using namespace dn;
 
+extern "C" int dn_pwconv_plan_info(long long M, int K, int N, int32_t* out8) {
+    DN_REQUIRE(out8 != nullptr && M > 0 && K > 0 && N > 0 && K % 8 == 0, DN_ERR_INVALID, "bad GEMM shape");
+    int bn, nt, st, cols, ws, pair;
+    size_t smem;
+    pwconv_tc_plan(M, K, N, &bn, &nt, &st, &cols, &smem, &ws, &pair);
+    int per_sm = 0;
+    for (int n = 4; n >= 1; --n)
+        if (smem <= smem_cap(n) && n * cols <= 512) {
+            per_sm = n;
+            break;
+        }
+    out8[0] = bn, out8[1] = nt, out8[2] = st, out8[3] = cols, out8[4] = (int32_t)smem, out8[5] = ws, out8[6] = pair, out8[7] = per_sm;
+    return DN_OK;
+}
+
 extern "C" int dn_pwconv(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
                          int N, int act, int out_fp32, int hw, int64_t out_batch_stride, int64_t out_row_stride, int impl,
                          void* stream_) {

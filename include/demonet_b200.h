@@ -70,6 +70,11 @@ int dn_dwconv_plan_info(int H, int W, int C, int k, int stride, int32_t* out8);
 int dn_pwconv(const void* x, const void* w, const float* bias, const void* residual, void* y, int M, int K,
               int N, int act, int out_fp32, int hw, int64_t out_batch_stride, int64_t out_row_stride,
               int impl, void* stream);
+/* Host-only: the tile plan dn_pwconv uses for a GEMM shape (no device work; usable without a GPU).
+ * out8 = { block_n (columns per output tile), n_tiles, ring stages, TMEM columns (two accumulator buffers), dynamic shared
+ * memory bytes, weight-stationary (K <= 128: the weight tile stays in shared memory), pair mode (DN_PW_PAIR: 0 off,
+ * 1 TMA multicast, 2 cta_group::2), resident CTAs per SM }. */
+int dn_pwconv_plan_info(long long M, int K, int N, int32_t* out8);
 
 /* Fused pointwise expand (1x1 conv + folded BN + act) -> depthwise k x k (+ folded BN + act): the expanded tensor stays
  * in shared memory.  Replaces InvertedResidual.block[0:2] (mobilenetv3.py:75-83, mobilenetv2.py:84-87) where the shape

@@ -292,3 +292,35 @@ def test_depthwise_row_stream_plans():
         p = _dw_plan(H, H, C, k, s)
         assert p["impl"] == (STREAM if s == 1 else STREAM2) and p["nstrip"] == 1 and p["threads"] == 160, (H, C, k, s, p)
     assert _dw_plan(20, 20, 200, 3, 1)["threads"] == 288 and _dw_plan(5, 5, 512, 3, 1)["impl"] == 1
+
+
+def _pw_plan(M, K, N):
+    out = (ctypes.c_int32 * 8)()
+    assert _C.lib().dn_pwconv_plan_info(M, K, N, out) == 0, _C.lib().dn_last_error()
+    return dict(zip(("block_n", "n_tiles", "stages", "tmem_cols", "smem", "w_stat", "pair", "per_sm"), list(out)))
+
+
+def test_gemm_tile_plans(monkeypatch):
+    """Host logic of the GEMM planner (no GPU): every V3 / V2 / head shape gets a tile plan that fits the SM (shared memory,
+    512 TMEM columns, at least two ring stages, at least one resident CTA); weight-stationary exactly for K <= 128; the pair
+    modes only where asked for, only for ring-carried weights on large maps, with a deeper ring for cta_group::2."""
+    shapes = [(256 * hw, k, n) for hw, k, n in [(25600, 16, 16), (6400, 64, 24), (6400, 24, 72), (6400, 72, 24), (1600, 72, 40),
+                                                (1600, 40, 120), (1600, 120, 40), (1600, 40, 240), (400, 240, 80), (400, 80, 200),
+                                                (400, 200, 80), (400, 80, 184), (400, 184, 80), (400, 80, 480), (400, 480, 112),
+                                                (400, 112, 672), (400, 672, 112), (100, 672, 80), (100, 80, 480), (100, 480, 80),
+                                                (100, 480, 256), (25, 256, 512), (25, 512, 128), (9, 128, 256), (4, 256, 64),
+                                                (1, 64, 128), (400, 672, 546), (100, 480, 546), (25, 512, 546), (400, 672, 24),
+                                                (1024, 96, 576), (256, 320, 1280), (256, 1280, 126)]]
+    for M, K, N in shapes:
+        p = _pw_plan(M, K, N)
+        assert p["block_n"] % 16 == 0 and 16 <= p["block_n"] <= 256 and p["block_n"] * p["n_tiles"] >= N, (M, K, N, p)
+        assert 2 * p["block_n"] <= p["tmem_cols"] <= 512 and p["tmem_cols"] & (p["tmem_cols"] - 1) == 0
+        assert 2 <= p["stages"] <= 4 and 1 <= p["per_sm"] <= 4 and p["per_sm"] * p["tmem_cols"] <= 512
+        assert 0 < p["smem"] <= 227 * 1024 and p["w_stat"] == (1 if K <= 128 else 0) and p["pair"] == 0
+    assert _pw_plan(102400, 672, 546) | {"smem": 0} == dict(block_n=192, n_tiles=3, stages=4, tmem_cols=512, smem=0, w_stat=0, pair=0, per_sm=1)
+    monkeypatch.setenv("DN_PW_PAIR", "1")
+    assert _pw_plan(102400, 672, 546)["pair"] == 1 and _pw_plan(102400, 112, 672)["pair"] == 0        # weight-stationary: no pair
+    assert _pw_plan(25600, 672, 80)["pair"] == 0                                                          # small map: no pair
+    monkeypatch.setenv("DN_PW_PAIR", "2")
+    p = _pw_plan(102400, 672, 546)
+    assert p["pair"] == 2 and 4 < p["stages"] <= 8 and p["smem"] <= 227 * 1024                            # half-size weight stages
